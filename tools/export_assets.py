@@ -1,0 +1,59 @@
+"""Export the reference's DATA tables (index lists, normalisation stats, shipped prior weights,
+sample parameter clips) into the small asset/fixture files this repo ships.
+
+Runs ONLY in the build container (needs /root/reference).  No reference *source* is copied: the
+outputs are integer index tables, float statistics and network weights.
+
+  lemo_b200/assets/lemo_tables.npz   marker / foot-vertex index tables + smooth/infill stats
+  lemo_b200/assets/enc_smooth_15217.npz   Enc weights of runs/15217/Enc_last_model.pkl
+  tests/golden/seed_clips.npz        the ten shipped [119,72] result clips + contact labels
+
+Index provenance (all under /root/reference):
+  loader/SSM2.json, loader/SSM2_withhand.json              (opt_amass_temp.py:237-241)
+  body_segments/{L,R}_Leg.json o foot_verts_id/*.npy       (opt_amass_temp.py:97-113)
+The foot tables are resolved with the reference's own expression
+`np.asarray(list(set(verts_ind)))[bool_mask]` in THIS interpreter.
+"""
+import json, os, sys
+import numpy as np
+import torch
+
+REF = '/root/reference'
+OUT_A = os.path.join(os.path.dirname(__file__), '..', 'lemo_b200', 'assets')
+OUT_G = os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden')
+
+
+def main():
+    j = lambda p: json.load(open(os.path.join(REF, p)))
+    ssm2 = list(j('loader/SSM2.json')['markersets'][0]['indices'].values())
+    ssm2h = list(j('loader/SSM2_withhand.json')['markersets'][0]['indices'].values())
+    assert ssm2h[:67] == ssm2
+    tabs = dict(markers67=np.asarray(ssm2, np.int32), markers81=np.asarray(ssm2h, np.int32))
+    for side, S in (('left', 'L'), ('right', 'R')):
+        leg = np.asarray(list(set(j('body_segments/%s_Leg.json' % S)['verts_ind'])))
+        for part in ('heel', 'toe'):
+            m = np.load(os.path.join(REF, 'foot_verts_id/%s_%s_verts_id.npy' % (side, part)))
+            tabs['%s_%s' % (side, part)] = leg[m].astype(np.int32)
+    st = np.load(os.path.join(REF, 'preprocess_stats/preprocess_stats_smooth_withHand_global_markers.npz'))
+    tabs['smooth_Xmean'] = st['Xmean'].reshape(243).astype(np.float32)
+    tabs['smooth_Xstd'] = st['Xstd'].reshape(243).astype(np.float32)
+    st = np.load(os.path.join(REF, 'preprocess_stats/preprocess_stats_infill_local_markers_4chan.npz'))
+    for k in st.files:
+        tabs['infill_' + k] = np.asarray(st[k], np.float32)
+    np.savez(os.path.join(OUT_A, 'lemo_tables.npz'), **tabs)
+    print({k: v.shape for k, v in tabs.items()})
+
+    w = torch.load(os.path.join(REF, 'runs/15217/Enc_last_model.pkl'), map_location='cpu')
+    np.savez(os.path.join(OUT_A, 'enc_smooth_15217.npz'), **{k: v.numpy() for k, v in w.items()})
+
+    clips = {}
+    for stage in ('perframe', 'temp'):
+        for c in (0, 20, 40, 60, 80):
+            d = os.path.join(REF, 'res_opt_amass_%s/TotalCapture' % stage)
+            clips['%s_params_%d' % (stage, c)] = np.load(os.path.join(d, 'body_params_opt_clip_%d.npy' % c))
+            clips['%s_contact_%d' % (stage, c)] = np.load(os.path.join(d, 'contact_lbl_rec_clip_%d.npy' % c))
+    np.savez_compressed(os.path.join(OUT_G, 'seed_clips.npz'), **clips)
+
+
+if __name__ == '__main__':
+    main()
