@@ -1,0 +1,213 @@
+/* lemo_b200 -- C ABI of the B200-native temporal body-fitting engine (liblemo_b200.so).
+ *
+ * This is the drop-in boundary for the fitting hot path of sanweiliti/LEMO.  The reference has no FFI of its
+ * own: its "operator API" is nn.Module.__call__ + autograd.  Each entry point below
+ * names the reference call it replaces (path:line under the reference tree).  The Python mirror of the
+ * reference modules (lemo_b200/smplx.py, models/, temp_prox/, utils/, fit.py) binds exactly these symbols
+ * through ctypes; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch types.  `stream` is a cudaStream_t passed as void*.
+ *   - every tensor pointer is a DEVICE pointer to contiguous row-major fp32 (int32 for indices) unless the
+ *     parameter name starts with h_ (host).  The caller owns all tensors; the library owns only opaque
+ *     handles and the scratch allocated when a handle is created.  Nothing allocates, synchronises or touches
+ *     the default stream on the hot path.
+ *   - all functions return 0 on success; otherwise lemo_last_error() holds a thread-local message.  Nothing
+ *     throws across the ABI.  A handle is used by one host thread at a time; distinct handles are independent.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels on the handle's device.
+ */
+#ifndef LEMO_B200_H
+#define LEMO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEMO_NUM_JOINTS 55
+#define LEMO_NUM_OUT_JOINTS 127 /* 55 + 21 vertex joints + 51 landmarks (smplx SMPLX.forward) */
+
+const char* lemo_last_error(void);
+int lemo_version(void);
+
+/* ---------------------------------------------------------------- body model (smplx.create) ------------ */
+typedef struct LemoModel LemoModel;   /* immutable model tensors on one device        */
+typedef struct LemoBody LemoBody;     /* forward/backward state for a fixed max batch  */
+
+/* Host-side description of an SMPL-X model file (smplx==0.1.26 .npz keys). */
+typedef struct LemoModelDescC {
+    int32_t n_verts;                 /* 10475 */
+    int32_t n_faces;                 /* 20908 */
+    int32_t num_pca_comps;           /* 12    */
+    int32_t n_extra_joints;          /* 21    */
+    int32_t n_landmarks;             /* 51    */
+    const float* h_v_template;       /* [V,3]            */
+    const float* h_shapedirs;        /* [V,3,20] betas(10) then expression(10) */
+    const float* h_posedirs;         /* [486, 3V]  element (p, 3v+k)   (body_model.py:126-128) */
+    const float* h_J_regressor;      /* [55,V]           */
+    const float* h_lbs_weights;      /* [V,55]           */
+    const int32_t* h_parents;        /* [55], parents[0] = -1 */
+    const float* h_hand_comp_l;      /* [num_pca_comps,45] */
+    const float* h_hand_comp_r;
+    const float* h_pose_mean;        /* [165]  (hands_mean in the two hand slots when flat_hand_mean=False) */
+    const int32_t* h_extra_joint_vids; /* [n_extra_joints] */
+    const int32_t* h_faces;          /* [F,3]            */
+    const int32_t* h_lmk_faces_idx;  /* [n_landmarks]    */
+    const float* h_lmk_bary;         /* [n_landmarks,3]  */
+} LemoModelDescC;
+
+/* replaces smplx.create(...)            (opt_amass_temp.py:73-87, temp_prox/main_slide.py:160-179) */
+int lemo_model_create(const LemoModelDescC* desc, int device, LemoModel** out);
+/* compact sub-model holding only the given vertex rows (the loss rows of a fit: markers + foot verts) */
+int lemo_model_select_rows(const LemoModel* model, const int32_t* h_rows, int32_t n_rows, LemoModel** out);
+int lemo_model_destroy(LemoModel* model);
+int lemo_model_num_verts(const LemoModel* model);
+
+/* Pose inputs of body_model(**params) (utils/utils.py:141-152).  Null pointers mean "module default" (zeros). */
+typedef struct LemoPoseC {
+    const float* transl;          /* [B,3]  */
+    const float* global_orient;   /* [B,3]  axis-angle */
+    const float* body_pose;       /* [B,63] axis-angle */
+    const float* jaw_pose;        /* [B,3]  */
+    const float* leye_pose;       /* [B,3]  */
+    const float* reye_pose;       /* [B,3]  */
+    const float* left_hand_pose;  /* [B,num_pca_comps] (use_pca) or [B,45] */
+    const float* right_hand_pose;
+    const float* betas;           /* [B,10] or [1,10] when betas_shared */
+    const float* expression;      /* [B,10] */
+    const float* R_global;        /* [B,9]    optional rotation-matrix override of global_orient */
+    const float* R_body;          /* [B,21,9] optional rotation-matrix override of body_pose     */
+    int32_t betas_shared;         /* 1: one betas row for the whole batch */
+    int32_t use_pca;              /* 1: hand poses are PCA coefficients   */
+} LemoPoseC;
+
+typedef struct LemoPoseGradC {    /* outputs of backward; any may be NULL */
+    float* transl; float* global_orient; float* body_pose; float* jaw_pose; float* leye_pose; float* reye_pose;
+    float* left_hand_pose; float* right_hand_pose; float* betas; float* expression; float* R_global; float* R_body;
+} LemoPoseGradC;
+
+int lemo_body_create(const LemoModel* model, int32_t max_batch, int32_t with_backward, LemoBody** out);
+int lemo_body_destroy(LemoBody* body);
+
+/* replaces SMPLX.forward / lbs()       (human_body_prior/body_model/lbs.py:34-119; smplx call sites
+ * opt_amass_perframe.py:335, opt_amass_temp.py:357,364, fitting_temp_slide.py:248-258).
+ * verts [B,V,3]; joints [B,127,3] (NULL for sub-models / when not needed); full_pose [B,165] (nullable). */
+int lemo_smplx_forward(LemoBody* body, const LemoPoseC* pose, int32_t B,
+                       float* verts, float* joints, float* full_pose, void* stream);
+/* adjoint of lemo_smplx_forward for the same (body, pose, B): d_verts [B,V,3] and/or d_joints [B,127,3]. */
+int lemo_smplx_backward(LemoBody* body, const LemoPoseC* pose, int32_t B,
+                        const float* d_verts, const float* d_joints, const LemoPoseGradC* grads, void* stream);
+
+/* replaces verts[:, ids, :] gathers     (opt_amass_temp.py:359,366,416-425; bit-exact integer indexing) */
+int lemo_gather_rows(const float* src, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* out, void* stream);
+int lemo_scatter_rows_add(const float* g_rows, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* g_dense, void* stream);
+
+/* ---------------------------------------------------------------- rotation conversions (utils/utils.py) - */
+int lemo_rot6d_to_rotmat(const float* x6, int32_t n, float* R, void* stream);                /* utils.py:64-70  */
+int lemo_rot6d_to_rotmat_backward(const float* x6, const float* dR, int32_t n, float* dx6, void* stream);
+int lemo_rotmat_to_aa(const float* R, int32_t n, float* aa, void* stream);                   /* utils.py:74-81 (tgm) */
+int lemo_aa_to_rot6d(const float* aa, int32_t n, float* x6, void* stream);                   /* utils.py:127-130 (tgm) */
+int lemo_rodrigues(const float* aa, int32_t n, float* R, void* stream);                      /* lbs.py:166-193  */
+int lemo_rodrigues_backward(const float* aa, const float* dR, int32_t n, float* daa, void* stream);
+
+/* ---------------------------------------------------------------- VPoser decoder ---------------------- */
+typedef struct LemoVPoser LemoVPoser;
+/* weights: nn.Linear layout [out,in]; replaces load_vposer(...).decode (vposer_smpl.py:107-121) */
+int lemo_vposer_create(const float* h_fc1_w, const float* h_fc1_b, const float* h_fc2_w, const float* h_fc2_b,
+                       const float* h_out_w, const float* h_out_b, int32_t max_batch, int device, LemoVPoser** out);
+int lemo_vposer_destroy(LemoVPoser* vp);
+/* z [B,32] -> R_body [B,21,9] (output_type 'matrot') and, if aa != NULL, [B,63] axis-angle (tgm, 'aa') */
+int lemo_vposer_decode(LemoVPoser* vp, const float* z, int32_t B, float* R_body, float* aa, void* stream);
+int lemo_vposer_decode_backward(LemoVPoser* vp, const float* z, int32_t B, const float* dR_body, float* dz, void* stream);
+
+/* ---------------------------------------------------------------- motion priors (models/AE_sep.py, AE.py) */
+typedef struct LemoConvNet LemoConvNet;
+/* kind 0: Enc(downsample=False, z_channel=64)  (models/AE_sep.py:77-99) -- 10 conv3x3 + LeakyReLU(0.2)
+ * kind 1: AE(downsample=True, in_channel=C, kernel=3) (models/AE.py:79-108)
+ * h_weights: concatenation of the state_dict tensors in the reference's key order
+ * (enc_blc{1-5}.main.{0,2}.{weight,bias} [, dec_blc{1-5}.deconv{1,2}.{weight,bias}]). */
+int lemo_convnet_create(int32_t kind, int32_t in_channels, const float* h_weights, int64_t n_weights,
+                        int32_t max_n, int32_t H, int32_t W, int32_t with_backward, int device, LemoConvNet** out);
+int lemo_convnet_destroy(LemoConvNet* net);
+int lemo_convnet_set_weights(LemoConvNet* net, const float* weights_dev, void* stream); /* device, same order  */
+int lemo_convnet_get_weights(LemoConvNet* net, float* weights_dev, void* stream);
+int64_t lemo_convnet_num_weights(const LemoConvNet* net);
+/* Enc.forward: x [N,1,H,W] -> z [N,64,H,W]                                  (opt_amass_temp.py:389) */
+int lemo_enc_forward(LemoConvNet* net, const float* x, int32_t N, float* z, void* stream);
+/* input gradient of the last lemo_enc_forward: dz [N,64,H,W] -> dx [N,1,H,W] */
+int lemo_enc_backward_input(LemoConvNet* net, const float* dz, int32_t N, float* dx, void* stream);
+/* measurement hook: relaunch ONE conv layer of an Enc handle `reps` times on its resident activations
+ * (forward: layer l of 0..9; backward: the input-gradient conv of layer l >= 1) so bench.py can time the
+ * dominant kernel alone with CUDA events. */
+int lemo_convnet_profile_layer(LemoConvNet* net, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream);
+/* AE.forward: x [N,C,H,W] -> rec [N,1,H,W], z [N,256,h5,w5] (nullable)      (opt_amass_perframe.py:160) */
+int lemo_ae_forward(LemoConvNet* net, const float* x, int32_t N, float* rec, float* z, void* stream);
+/* weight gradients of the last lemo_ae_forward: d_rec [N,1,H,W] -> d_weights (same order as weights) */
+int lemo_ae_backward_weights(LemoConvNet* net, const float* d_rec, int32_t N, float* d_weights, void* stream);
+
+/* ---------------------------------------------------------------- Chamfer (temp_prox/dist_chamfer.py) --- */
+/* xyz1 [B,n,3]; xyz2 [B,m,3] with xyz2_batch_stride floats between batches (0 = one shared scene).
+ * dist = squared L2 to the nearest neighbour (first minimum wins), idx int32.  (dist_chamfer.py:10-28) */
+int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m,
+                         int64_t xyz2_batch_stride, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                         void* stream);
+/* grad 2*g*(x1-x2) scattered to both clouds (dist_chamfer.py:30-45).  d_xyz2 has the same batch stride
+ * as xyz2 (a shared scene accumulates over the batch).  Outputs are overwritten. */
+int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m,
+                          int64_t xyz2_batch_stride, const float* g_dist1, const float* g_dist2,
+                          const int32_t* idx1, const int32_t* idx2, float* d_xyz1, float* d_xyz2, void* stream);
+
+/* ---------------------------------------------------------------- optimiser (torch.optim.Adam.step) ----- */
+/* p,g,m,v [n]; t = 1-based step; bias-corrected, no weight decay / amsgrad (opt_amass_temp.py:345,455) */
+int lemo_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                   double eps, int32_t t, void* stream);
+
+/* ---------------------------------------------------------------- fused fitting drivers ----------------- */
+typedef struct LemoFit LemoFit;
+typedef struct LemoFitConfigC {
+    int32_t mode;               /* 0 temporal (opt_amass_temp.py:329-455), 1 per-frame (opt_amass_perframe.py:293-361) */
+    int32_t n_seq;              /* S sequences fitted side by side on this device          */
+    int32_t n_frames;           /* T frames per sequence                                   */
+    float w_rec, w_vposer, w_shape, w_hand, w_contact, w_smooth;  /* loss weights (argparse defaults of the scripts) */
+    float vel_thres;            /* 0.1  (opt_amass_temp.py:428) */
+    float fps;                  /* 30                            */
+    const int32_t* h_markers67; /* [67]  loader/SSM2.json                                   */
+    const int32_t* h_markers81; /* [81]  loader/SSM2_withhand.json                          */
+    const int32_t* h_foot_ids[4];   /* left_heel, right_heel, left_toe, right_toe (opt_amass_temp.py:97-113) */
+    int32_t n_foot[4];
+    const float* h_smooth_mean; /* [243] */
+    const float* h_smooth_std;  /* [243] */
+    int32_t use_cuda_graph;     /* capture one iteration and replay it */
+} LemoFitConfigC;
+
+int lemo_fit_create(const LemoModel* model, LemoVPoser* vposer_or_null, const float* h_vposer_weights_unused,
+                    LemoConvNet* enc_or_null, const LemoFitConfigC* cfg, int device, LemoFit** out);
+int lemo_fit_destroy(LemoFit* fit);
+/* per-sequence inputs (device pointers): init params [T,72] (transl3, aa3, betas10, z32, lh12, rh12),
+ * target markers [T,67,3], contact labels [T,4].  Temporal mode.  (opt_amass_temp.py:253,329-341) */
+int lemo_fit_set_sequence(LemoFit* fit, int32_t s, const float* init72, const float* markers_rec, const float* contact,
+                          void* stream);
+/* n_iters Adam iterations with the script's LR schedule (lr0 until step>lr_switch, then lr1).
+ * Entirely on device: no host synchronisation inside. */
+int lemo_fit_run(LemoFit* fit, int32_t n_iters, float lr0, float lr1, int32_t lr_switch, void* stream);
+/* per-frame mode: runs all T frames x n_iters of sequence-parallel B=1 problems (lr .1/.01 -> .01@>60 -> .003@>80) */
+int lemo_fit_run_perframe(LemoFit* fit, int32_t n_iters, void* stream);
+/* results: params72 [S,T,72] as of the LAST forward (what the scripts save), losses [S,8] of the last iteration
+ * (total, rec, vposer, shape, hand, contact, smooth, reserved) */
+int lemo_fit_get(LemoFit* fit, float* params72, float* losses, void* stream);
+/* raw optimisation state after the last step: transl [S,T,3], rot6d [S,T,6], other [S,T,56]; grads of last iteration */
+int lemo_fit_get_state(LemoFit* fit, float* transl, float* rot6d, float* other, float* g_transl, float* g_rot6d,
+                       float* g_other, void* stream);
+int64_t lemo_fit_kernel_launches(const LemoFit* fit);   /* kernels enqueued by this handle so far */
+
+/* ---------------------------------------------------------------- test hooks (host math, no GPU) -------- */
+void lemo_host_rodrigues(const float* aa, float* R);
+void lemo_host_rodrigues_bwd(const float* aa, const float* dR, float* daa);
+void lemo_host_gs6d(const float* x6, float* R);
+void lemo_host_gs6d_bwd(const float* x6, const float* dR, float* dx6);
+void lemo_host_rotmat_to_aa(const float* R, float* aa);
+void lemo_host_aa_to_rotmat_tgm(const float* aa, float* R);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

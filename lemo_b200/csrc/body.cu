@@ -1,0 +1,700 @@
+// SMPL-X body-model path on sm_100a: pose -> rotations, kinematic chain, fused blend-shape contraction,
+// linear blend skinning, output joints, and the adjoint of all of it.
+//
+// Reference semantics reproduced (paths under the reference tree):
+//   human_body_prior/body_model/lbs.py:34-263   (lbs, blend_shapes, vertices2joints, batch_rodrigues,
+//                                                batch_rigid_transform)
+//   smplx==0.1.26 SMPLX.forward                 (hand PCA, +pose_mean, betas|expression, vertex joints,
+//                                                landmarks, +transl)
+// B200-first restructuring:
+//   * shape and pose blend shapes are ONE contraction  v_posed = v_template + X[B,512] . Wt[512,3V]
+//     with X = [R(1..54)-I | betas | expression | 0]; the joint regressor is folded into
+//     J_template/J_dirs at model-create time, so nothing of size V is touched per frame except Wt.
+//   * rigid transforms are 3x4 (the reference carries 4x4 with a constant last row).
+//   * no W.repeat(B) (274 MB at B=119 in the reference), no [B,V,4,4] T tensor.
+#include "body.cuh"
+#include "gemm.cuh"
+#include "../../include/lemo_b200.h"
+#include <vector>
+#include <cstring>
+#include <algorithm>
+
+namespace lemo {
+
+// =============================================================================================
+// model
+// =============================================================================================
+template <typename T>
+static int dev_upload(T** dst, const T* src, size_t n) {
+    LEMO_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+    LEMO_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <typename T>
+static int dev_alloc(T** dst, size_t n) {
+    LEMO_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+    LEMO_CUDA(cudaMemset(*dst, 0, n * sizeof(T)));
+    return 0;
+}
+
+static int compute_depth(const int* parents, int* depth, int* max_depth) {
+    *max_depth = 0;
+    for (int j = 0; j < NJ; ++j) {
+        if (j == 0) { depth[j] = 0; continue; }
+        if (parents[j] < 0 || parents[j] >= j) return 1;
+        depth[j] = depth[parents[j]] + 1;
+        if (depth[j] > *max_depth) *max_depth = depth[j];
+    }
+    return 0;
+}
+
+int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
+    LEMO_CHECK(d && out, "null argument");
+    LEMO_CHECK(d->n_verts > 0 && d->num_pca_comps > 0 && d->num_pca_comps <= 45, "bad model sizes");
+    LEMO_CUDA(cudaSetDevice(device));
+    Model* m = new Model();
+    m->device = device;
+    const int V = m->V = d->n_verts;
+    m->npc = d->num_pca_comps;
+    m->n_extra = d->h_extra_joint_vids ? d->n_extra_joints : 0;
+    m->n_lmk = (d->h_lmk_faces_idx && d->h_faces && d->h_lmk_bary) ? d->n_landmarks : 0;
+    memcpy(m->h_parents, d->h_parents, NJ * sizeof(int));
+    m->h_parents[0] = -1;
+    LEMO_CHECK(compute_depth(m->h_parents, m->h_depth, &m->max_depth) == 0, "parents must satisfy parents[j] < j");
+
+    LEMO_TRY(dev_upload(&m->v_template, d->h_v_template, (size_t)V * 3));
+    // Wt = [posedirs ; shapedirs^T ; 0]
+    {
+        std::vector<float> wt((size_t)XK * 3 * V, 0.f);
+        memcpy(wt.data(), d->h_posedirs, (size_t)NPF * 3 * V * sizeof(float));
+        for (int v = 0; v < V; ++v)
+            for (int k = 0; k < 3; ++k)
+                for (int l = 0; l < NBETA; ++l)
+                    wt[(size_t)(NPF + l) * 3 * V + 3 * v + k] = d->h_shapedirs[((size_t)v * 3 + k) * NBETA + l];
+        LEMO_TRY(dev_upload(&m->Wt, wt.data(), wt.size()));
+    }
+    {
+        std::vector<float> wjm((size_t)NJ * V);
+        for (int v = 0; v < V; ++v)
+            for (int j = 0; j < NJ; ++j) wjm[(size_t)j * V + v] = d->h_lbs_weights[(size_t)v * NJ + j];
+        LEMO_TRY(dev_upload(&m->w_jm, wjm.data(), wjm.size()));
+    }
+    {   // fold the joint regressor: J = Jreg.(v_template + shapedirs.beta) = J_template + J_dirs.beta   (double accum)
+        std::vector<float> jt(NJ * 3), jd(NJ * 3 * NBETA);
+        std::vector<double> acc(3 + 3 * NBETA);
+        for (int j = 0; j < NJ; ++j) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            const float* jr = d->h_J_regressor + (size_t)j * V;
+            for (int v = 0; v < V; ++v) {
+                const double w = jr[v];
+                if (w == 0.0) continue;
+                for (int k = 0; k < 3; ++k) {
+                    acc[k] += w * d->h_v_template[(size_t)v * 3 + k];
+                    const float* sd = d->h_shapedirs + ((size_t)v * 3 + k) * NBETA;
+                    for (int l = 0; l < NBETA; ++l) acc[3 + k * NBETA + l] += w * sd[l];
+                }
+            }
+            for (int k = 0; k < 3; ++k) {
+                jt[j * 3 + k] = (float)acc[k];
+                for (int l = 0; l < NBETA; ++l) jd[(j * 3 + k) * NBETA + l] = (float)acc[3 + k * NBETA + l];
+            }
+        }
+        LEMO_TRY(dev_upload(&m->J_template, jt.data(), jt.size()));
+        LEMO_TRY(dev_upload(&m->J_dirs, jd.data(), jd.size()));
+    }
+    LEMO_TRY(dev_upload(&m->parents, m->h_parents, NJ));
+    LEMO_TRY(dev_upload(&m->depth, m->h_depth, NJ));
+    LEMO_TRY(dev_upload(&m->hand_l, d->h_hand_comp_l, (size_t)m->npc * 45));
+    LEMO_TRY(dev_upload(&m->hand_r, d->h_hand_comp_r, (size_t)m->npc * 45));
+    LEMO_TRY(dev_upload(&m->pose_mean, d->h_pose_mean, 165));
+    if (m->n_extra) LEMO_TRY(dev_upload(&m->extra_vids, d->h_extra_joint_vids, m->n_extra));
+    if (m->n_lmk) {
+        std::vector<int> tri(m->n_lmk * 3);
+        for (int l = 0; l < m->n_lmk; ++l) {
+            const int f = d->h_lmk_faces_idx[l];
+            LEMO_CHECK(f >= 0 && f < d->n_faces, "landmark face index out of range");
+            for (int k = 0; k < 3; ++k) tri[l * 3 + k] = d->h_faces[(size_t)f * 3 + k];
+        }
+        LEMO_TRY(dev_upload(&m->lmk_tri, tri.data(), tri.size()));
+        LEMO_TRY(dev_upload(&m->lmk_bary, d->h_lmk_bary, (size_t)m->n_lmk * 3));
+    }
+    *out = m;
+    return 0;
+}
+
+__global__ void k_select_rows(const float* __restrict__ vt, const float* __restrict__ Wt, const float* __restrict__ wjm,
+                              const int* __restrict__ rows, int V, int n, float* vt_o, float* Wt_o, float* wjm_o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over n*3 columns
+    if (i >= n * 3) return;
+    const int r = i / 3, k = i - r * 3;
+    const int v = rows[r];
+    vt_o[i] = vt[v * 3 + k];
+    for (int p = 0; p < XK; ++p) Wt_o[(size_t)p * 3 * n + i] = Wt[(size_t)p * 3 * V + 3 * v + k];
+    if (k == 0)
+        for (int j = 0; j < NJ; ++j) wjm_o[(size_t)j * n + r] = wjm[(size_t)j * V + v];
+}
+
+int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) {
+    LEMO_CHECK(m && rows_host && out && n > 0, "bad arguments");
+    for (int i = 0; i < n; ++i) LEMO_CHECK(rows_host[i] >= 0 && rows_host[i] < m->V, "row index out of range");
+    LEMO_CUDA(cudaSetDevice(m->device));
+    Model* s = new Model(*m);
+    s->is_sub = true;
+    s->V = n;
+    s->n_extra = 0; s->n_lmk = 0; s->extra_vids = nullptr; s->lmk_tri = nullptr; s->lmk_bary = nullptr;
+    int* rows_dev = nullptr;
+    LEMO_TRY(dev_upload(&rows_dev, rows_host, n));
+    LEMO_TRY(dev_alloc(&s->v_template, (size_t)n * 3));
+    LEMO_TRY(dev_alloc(&s->Wt, (size_t)XK * 3 * n));
+    LEMO_TRY(dev_alloc(&s->w_jm, (size_t)NJ * n));
+    k_select_rows<<<cdiv(n * 3, 128), 128>>>(m->v_template, m->Wt, m->w_jm, rows_dev, m->V, n, s->v_template, s->Wt, s->w_jm);
+    LEMO_CUDA(cudaGetLastError());
+    LEMO_CUDA(cudaDeviceSynchronize());
+    cudaFree(rows_dev);
+    *out = s;      // shares J_template/J_dirs/parents/hand/pose_mean pointers with the parent model
+    return 0;
+}
+
+void model_free(Model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->w_jm);
+    if (!m->is_sub) {
+        cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth);
+        cudaFree(m->hand_l); cudaFree(m->hand_r); cudaFree(m->pose_mean);
+        cudaFree(m->extra_vids); cudaFree(m->lmk_tri); cudaFree(m->lmk_bary);
+    }
+    delete m;
+}
+
+int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) {
+    LEMO_CHECK(m && out && maxB > 0, "bad arguments");
+    LEMO_CUDA(cudaSetDevice(m->device));
+    BodyCtx* c = new BodyCtx();
+    c->m = m; c->maxB = maxB;
+    const size_t B = maxB, V = m->V;
+    LEMO_TRY(dev_alloc(&c->full_pose, B * 165));
+    LEMO_TRY(dev_alloc(&c->R, B * NJ * 9));
+    LEMO_TRY(dev_alloc(&c->X, B * XK));
+    LEMO_TRY(dev_alloc(&c->G, B * NJ * 12));
+    LEMO_TRY(dev_alloc(&c->A, B * NJ * 12));
+    LEMO_TRY(dev_alloc(&c->Jrest, B * NJ * 3));
+    LEMO_TRY(dev_alloc(&c->Jposed, B * NJ * 3));
+    LEMO_TRY(dev_alloc(&c->VP, B * 3 * V));
+    if (with_backward) {
+        LEMO_TRY(dev_alloc(&c->Gv, B * 3 * V));
+        LEMO_TRY(dev_alloc(&c->DVP, B * 3 * V));
+        LEMO_TRY(dev_alloc(&c->DT, V * B * 12));
+        LEMO_TRY(dev_alloc(&c->dA, (size_t)NJ * B * 12));
+        LEMO_TRY(dev_alloc(&c->dX, B * XK));
+        LEMO_TRY(dev_alloc(&c->dR, B * NJ * 9));
+        LEMO_TRY(dev_alloc(&c->dJp, B * NJ * 3));
+        LEMO_TRY(dev_alloc(&c->dtr, B * 3));
+    }
+    *out = c;
+    return 0;
+}
+
+void bodyctx_free(BodyCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->m->device);
+    float* ptrs[] = {c->full_pose, c->R, c->X, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->DT, c->dA, c->dX, c->dR, c->dJp, c->dtr};
+    for (float* p : ptrs) cudaFree(p);
+    delete c;
+}
+
+// =============================================================================================
+// pose -> rotation matrices        (one thread per (frame, joint))
+// =============================================================================================
+struct PoseK {
+    PoseIn in;
+    const float* hand_l; const float* hand_r; const float* pose_mean;
+    int npc;
+};
+
+__device__ __forceinline__ void joint_aa(const PoseK& p, int b, int j, float* aa) {
+    aa[0] = aa[1] = aa[2] = 0.f;
+    if (j == 0) { if (p.in.global_orient) for (int k = 0; k < 3; ++k) aa[k] = p.in.global_orient[b * 3 + k]; }
+    else if (j <= NBODY) { if (p.in.body_pose) for (int k = 0; k < 3; ++k) aa[k] = p.in.body_pose[b * 63 + (j - 1) * 3 + k]; }
+    else if (j == 22) { if (p.in.jaw) for (int k = 0; k < 3; ++k) aa[k] = p.in.jaw[b * 3 + k]; }
+    else if (j == 23) { if (p.in.leye) for (int k = 0; k < 3; ++k) aa[k] = p.in.leye[b * 3 + k]; }
+    else if (j == 24) { if (p.in.reye) for (int k = 0; k < 3; ++k) aa[k] = p.in.reye[b * 3 + k]; }
+    else {
+        const bool left = j < 40;
+        const int h = left ? j - 25 : j - 40;
+        const float* src = left ? p.in.lhand : p.in.rhand;
+        if (src) {
+            if (p.in.hand_is_pca) {
+                const float* comp = left ? p.hand_l : p.hand_r;
+                for (int c = 0; c < p.npc; ++c) {
+                    const float a = src[b * p.npc + c];
+                    for (int k = 0; k < 3; ++k) aa[k] = fmaf(a, comp[c * 45 + h * 3 + k], aa[k]);
+                }
+            } else {
+                for (int k = 0; k < 3; ++k) aa[k] = src[b * 45 + h * 3 + k];
+            }
+        }
+    }
+    for (int k = 0; k < 3; ++k) aa[k] += p.pose_mean[j * 3 + k];
+}
+
+__global__ void k_pose_to_rot(PoseK p, int B, float* __restrict__ full_pose, float* __restrict__ R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NJ) return;
+    const int b = i / NJ, j = i - b * NJ;
+    float aa[3], r[9];
+    const float* Rov = nullptr;
+    if (j == 0 && p.in.R_global) Rov = p.in.R_global + b * 9;
+    if (j >= 1 && j <= NBODY && p.in.R_body) Rov = p.in.R_body + (b * NBODY + (j - 1)) * 9;
+    if (Rov) {
+        for (int k = 0; k < 9; ++k) r[k] = Rov[k];
+        rotmat_to_aa_tgm(r, aa);                 // what the reference scripts store in the [T,72] result
+    } else {
+        joint_aa(p, b, j, aa);
+        rodrigues_fwd(aa, r);
+    }
+    for (int k = 0; k < 3; ++k) full_pose[b * 165 + j * 3 + k] = aa[k];
+    for (int k = 0; k < 9; ++k) R[(b * NJ + j) * 9 + k] = r[k];
+}
+
+// adjoint: dR -> parameter gradients.  One block (64 threads) per frame.
+__global__ void __launch_bounds__(64) k_pose_to_rot_bwd(PoseK p, PoseGrad g, int B, const float* __restrict__ full_pose,
+                                                        const float* __restrict__ dR) {
+    __shared__ float s_daa[NJ * 3];
+    const int b = blockIdx.x, j = threadIdx.x;
+    if (j < NJ) {
+        const float* dr = dR + (b * NJ + j) * 9;
+        const bool ov = (j == 0 && p.in.R_global) || (j >= 1 && j <= NBODY && p.in.R_body);
+        float daa[3] = {0.f, 0.f, 0.f};
+        if (ov) {
+            float* o = (j == 0) ? (g.R_global ? g.R_global + b * 9 : nullptr)
+                                : (g.R_body ? g.R_body + (b * NBODY + (j - 1)) * 9 : nullptr);
+            if (o) for (int k = 0; k < 9; ++k) o[k] = dr[k];
+        } else {
+            float aa[3] = {full_pose[b * 165 + j * 3], full_pose[b * 165 + j * 3 + 1], full_pose[b * 165 + j * 3 + 2]};
+            rodrigues_bwd(aa, dr, daa);
+        }
+        for (int k = 0; k < 3; ++k) s_daa[j * 3 + k] = daa[k];
+        if (!ov) {
+            float* o = nullptr;
+            if (j == 0) o = g.global_orient ? g.global_orient + b * 3 : nullptr;
+            else if (j <= NBODY) o = g.body_pose ? g.body_pose + b * 63 + (j - 1) * 3 : nullptr;
+            else if (j == 22) o = g.jaw ? g.jaw + b * 3 : nullptr;
+            else if (j == 23) o = g.leye ? g.leye + b * 3 : nullptr;
+            else if (j == 24) o = g.reye ? g.reye + b * 3 : nullptr;
+            else if (!p.in.hand_is_pca) {
+                const bool left = j < 40;
+                float* base = left ? g.lhand : g.rhand;
+                o = base ? base + b * 45 + (left ? j - 25 : j - 40) * 3 : nullptr;
+            }
+            if (o) for (int k = 0; k < 3; ++k) o[k] = daa[k];
+        }
+    }
+    __syncthreads();
+    if (p.in.hand_is_pca && j < 2 * p.npc) {
+        const bool left = j < p.npc;
+        const int c = left ? j : j - p.npc;
+        float* base = left ? g.lhand : g.rhand;
+        if (base) {
+            const float* comp = (left ? p.hand_l : p.hand_r) + c * 45;
+            const float* d = s_daa + (left ? 25 : 40) * 3;
+            float acc = 0.f;
+            for (int q = 0; q < 45; ++q) acc = fmaf(comp[q], d[q], acc);
+            base[b * p.npc + c] = acc;
+        }
+    }
+}
+
+// =============================================================================================
+// kinematic chain (lbs.py:196-263): one block (64 threads) per frame, level-synchronous over the tree
+// =============================================================================================
+__global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, const float* __restrict__ betas, int betas_stride,
+                                                  const float* __restrict__ expr, const float* __restrict__ J_template,
+                                                  const float* __restrict__ J_dirs, const int* __restrict__ parents,
+                                                  const int* __restrict__ depth, int max_depth,
+                                                  float* __restrict__ X, float* __restrict__ G, float* __restrict__ A,
+                                                  float* __restrict__ Jrest, float* __restrict__ Jposed) {
+    __shared__ float sG[NJ][12];
+    __shared__ float sJ[NJ][3];
+    __shared__ float sbeta[NBETA];
+    const int b = blockIdx.x, j = threadIdx.x;
+    if (j < NBETA) {
+        float v = 0.f;
+        if (j < 10) v = betas ? betas[(size_t)b * betas_stride + j] : 0.f;
+        else v = expr ? expr[b * 10 + (j - 10)] : 0.f;
+        sbeta[j] = v;
+        X[(size_t)b * XK + NPF + j] = v;
+    }
+    if (j >= NBETA && j < NBETA + (XK - NPF - NBETA)) X[(size_t)b * XK + NPF + j] = 0.f;
+    __syncthreads();
+    float r[9];
+    int par = -1, dep = 0;
+    if (j < NJ) {
+        for (int k = 0; k < 9; ++k) r[k] = R[((size_t)b * NJ + j) * 9 + k];
+        for (int k = 0; k < 3; ++k) {
+            float acc = J_template[j * 3 + k];
+            const float* jd = J_dirs + (j * 3 + k) * NBETA;
+            for (int l = 0; l < NBETA; ++l) acc = fmaf(jd[l], sbeta[l], acc);
+            sJ[j][k] = acc;
+            Jrest[((size_t)b * NJ + j) * 3 + k] = acc;
+        }
+        if (j >= 1) {
+            float* x = X + (size_t)b * XK + (j - 1) * 9;
+            for (int k = 0; k < 9; ++k) x[k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
+        }
+        par = parents[j]; dep = depth[j];
+    }
+    __syncthreads();
+    for (int lev = 0; lev <= max_depth; ++lev) {
+        if (j < NJ && dep == lev) {
+            float g[12];
+            if (lev == 0) {
+                for (int i = 0; i < 3; ++i) { g[i * 4] = r[i * 3]; g[i * 4 + 1] = r[i * 3 + 1]; g[i * 4 + 2] = r[i * 3 + 2]; g[i * 4 + 3] = sJ[j][i]; }
+            } else {
+                const float* gp = sG[par];
+                const float t[3] = {sJ[j][0] - sJ[par][0], sJ[j][1] - sJ[par][1], sJ[j][2] - sJ[par][2]};
+                for (int i = 0; i < 3; ++i) {
+                    for (int c = 0; c < 3; ++c)
+                        g[i * 4 + c] = gp[i * 4] * r[c] + gp[i * 4 + 1] * r[3 + c] + gp[i * 4 + 2] * r[6 + c];
+                    g[i * 4 + 3] = gp[i * 4] * t[0] + gp[i * 4 + 1] * t[1] + gp[i * 4 + 2] * t[2] + gp[i * 4 + 3];
+                }
+            }
+            for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
+        }
+        __syncthreads();
+    }
+    if (j < NJ) {
+        const float* g = sG[j];
+        float* go = G + ((size_t)b * NJ + j) * 12;
+        float* ao = A + ((size_t)b * NJ + j) * 12;
+        for (int k = 0; k < 12; ++k) go[k] = g[k];
+        for (int i = 0; i < 3; ++i) {
+            ao[i * 4] = g[i * 4]; ao[i * 4 + 1] = g[i * 4 + 1]; ao[i * 4 + 2] = g[i * 4 + 2];
+            ao[i * 4 + 3] = g[i * 4 + 3] - (g[i * 4] * sJ[j][0] + g[i * 4 + 1] * sJ[j][1] + g[i * 4 + 2] * sJ[j][2]);
+            Jposed[((size_t)b * NJ + j) * 3 + i] = g[i * 4 + 3];
+        }
+    }
+}
+
+// adjoint of k_chain_fwd.  dA is joint-major [55][B*12]; dJp [B,55,3]; dX [B,512].
+// Writes dR [B,55,9]; betas/expression grads (per frame, or atomically into one row when betas_stride==0).
+__global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
+                                                  const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
+                                                  const float* __restrict__ J_dirs, const int* __restrict__ parents,
+                                                  const int* __restrict__ depth, int max_depth, int B, int betas_stride,
+                                                  float* __restrict__ dR, float* __restrict__ dbetas, float* __restrict__ dexpr) {
+    __shared__ float sdG[NJ][12];     // dL/dG  (3x4)
+    __shared__ float sdJ[NJ][3];      // dL/dJrest
+    const int b = blockIdx.x, j = threadIdx.x;
+    float r[9], gl[12], Jr[3];
+    int par = -1, dep = 0;
+    if (j < NJ) {
+        for (int k = 0; k < 9; ++k) r[k] = R[((size_t)b * NJ + j) * 9 + k];
+        for (int k = 0; k < 12; ++k) gl[k] = G[((size_t)b * NJ + j) * 12 + k];
+        for (int k = 0; k < 3; ++k) Jr[k] = Jrest[((size_t)b * NJ + j) * 3 + k];
+        par = parents[j]; dep = depth[j];
+        const float* da = dA + (size_t)j * B * 12 + (size_t)b * 12;
+        float dAt[3] = {da[3], da[7], da[11]};
+        // A.R = G.R ; A.t = G.t - G.R J
+        for (int i = 0; i < 3; ++i) {
+            for (int c = 0; c < 3; ++c) sdG[j][i * 4 + c] = da[i * 4 + c] - dAt[i] * Jr[c];
+            sdG[j][i * 4 + 3] = dAt[i] + (dJp ? dJp[((size_t)b * NJ + j) * 3 + i] : 0.f);
+        }
+        // dJ += -G.R^T dAt
+        for (int c = 0; c < 3; ++c) sdJ[j][c] = -(gl[c] * dAt[0] + gl[4 + c] * dAt[1] + gl[8 + c] * dAt[2]);
+    }
+    __syncthreads();
+    for (int lev = max_depth; lev >= 1; --lev) {
+        if (j < NJ && dep == lev) {
+            const float* gp = G + ((size_t)b * NJ + par) * 12;        // parent's global transform
+            float gpR[9] = {gp[0], gp[1], gp[2], gp[4], gp[5], gp[6], gp[8], gp[9], gp[10]};
+            float dGr[9] = {sdG[j][0], sdG[j][1], sdG[j][2], sdG[j][4], sdG[j][5], sdG[j][6], sdG[j][8], sdG[j][9], sdG[j][10]};
+            float dGt[3] = {sdG[j][3], sdG[j][7], sdG[j][11]};
+            const float* Jp = Jrest + ((size_t)b * NJ + par) * 3;
+            const float t[3] = {Jr[0] - Jp[0], Jr[1] - Jp[1], Jr[2] - Jp[2]};
+            float dr[9], dpr[9], dt[3];
+            m3_mul_at(gpR, dGr, dr);               // dR_j = Gp.R^T dG_j.R
+            m3_mul_bt(dGr, r, dpr);                // dGp.R += dG_j.R R_j^T
+            m3t_vec(gpR, dGt, dt);                 // dt = Gp.R^T dG_j.t
+            float* o = dR + ((size_t)b * NJ + j) * 9;
+            const float* dx = dX + (size_t)b * XK + (j - 1) * 9;
+            for (int k = 0; k < 9; ++k) o[k] = dr[k] + dx[k];
+            for (int i = 0; i < 3; ++i) {
+                for (int c = 0; c < 3; ++c) atomicAdd(&sdG[par][i * 4 + c], dpr[i * 3 + c] + dGt[i] * t[c]);
+                atomicAdd(&sdG[par][i * 4 + 3], dGt[i]);
+                atomicAdd(&sdJ[j][i], dt[i]);
+                atomicAdd(&sdJ[par][i], -dt[i]);
+            }
+        }
+        __syncthreads();
+    }
+    if (j == 0) {
+        float* o = dR + ((size_t)b * NJ) * 9;
+        for (int i = 0; i < 3; ++i) {
+            for (int c = 0; c < 3; ++c) o[i * 3 + c] = sdG[0][i * 4 + c];
+            sdJ[0][i] += sdG[0][i * 4 + 3];
+        }
+    }
+    __syncthreads();
+    // betas / expression: direct (X columns) + through Jrest
+    if (j < NBETA) {
+        float acc = dX[(size_t)b * XK + NPF + j];
+        for (int q = 0; q < NJ; ++q)
+            for (int k = 0; k < 3; ++k) acc = fmaf(J_dirs[(q * 3 + k) * NBETA + j], sdJ[q][k], acc);
+        if (j < 10) {
+            if (dbetas) {
+                if (betas_stride == 0) atomicAdd(&dbetas[j], acc);
+                else dbetas[(size_t)b * 10 + j] = acc;
+            }
+        } else if (dexpr) dexpr[(size_t)b * 10 + (j - 10)] = acc;
+    }
+}
+
+// =============================================================================================
+// skinning (lbs.py:106-117): one thread per (frame, vertex); blockIdx.y = frame
+// VP holds X.Wt on entry, v_posed (= + v_template) on exit (kept for the backward pass).
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ A, const float* __restrict__ w_jm,
+                                                  const float* __restrict__ v_template, const float* __restrict__ transl,
+                                                  int V, float* __restrict__ VP, float* __restrict__ verts) {
+    __shared__ float sA[NJ * 12];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < NJ * 12; i += blockDim.x) sA[i] = A[(size_t)b * NJ * 12 + i];
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+        const float w = w_jm[(size_t)j * V + v];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = fmaf(w, sA[j * 12 + k], T[k]);
+    }
+    float* vp = VP + ((size_t)b * V + v) * 3;
+    const float p0 = vp[0] + v_template[v * 3], p1 = vp[1] + v_template[v * 3 + 1], p2 = vp[2] + v_template[v * 3 + 2];
+    vp[0] = p0; vp[1] = p1; vp[2] = p2;
+    const float t0 = transl ? transl[b * 3] : 0.f, t1 = transl ? transl[b * 3 + 1] : 0.f, t2 = transl ? transl[b * 3 + 2] : 0.f;
+    float* o = verts + ((size_t)b * V + v) * 3;
+    o[0] = T[0] * p0 + T[1] * p1 + T[2] * p2 + T[3] + t0;
+    o[1] = T[4] * p0 + T[5] * p1 + T[6] * p2 + T[7] + t1;
+    o[2] = T[8] * p0 + T[9] * p1 + T[10] * p2 + T[11] + t2;
+}
+
+// adjoint per (frame, vertex): dvp = T.R^T g ; dT = g (x) [vp;1] ; dtransl += g
+__global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, const float* __restrict__ w_jm,
+                                                  const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B,
+                                                  float* __restrict__ DVP, float* __restrict__ DT, float* __restrict__ dtr) {
+    __shared__ float sA[NJ * 12];
+    __shared__ float sred[32];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < NJ * 12; i += blockDim.x) sA[i] = A[(size_t)b * NJ * 12 + i];
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (v < V) {
+        float T[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) T[k] = 0.f;
+        for (int j = 0; j < NJ; ++j) {
+            const float w = w_jm[(size_t)j * V + v];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[i * 3 + c] = fmaf(w, sA[j * 12 + i * 4 + c], T[i * 3 + c]);
+        }
+        const float* g = Gv + ((size_t)b * V + v) * 3;
+        g0 = g[0]; g1 = g[1]; g2 = g[2];
+        const float* vp = VP + ((size_t)b * V + v) * 3;
+        const float p[4] = {vp[0], vp[1], vp[2], 1.f};
+        float* dvp = DVP + ((size_t)b * V + v) * 3;
+        dvp[0] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+        dvp[1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+        dvp[2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+        float* dt = DT + (size_t)v * B * 12 + (size_t)b * 12;
+        const float gg[3] = {g0, g1, g2};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dt[i * 4 + c] = gg[i] * p[c];
+    }
+    float s;
+    s = block_sum(g0, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3], s);
+    s = block_sum(g1, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 1], s);
+    s = block_sum(g2, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 2], s);
+}
+
+// =============================================================================================
+// output joints (smplx SMPLX.forward): 55 posed joints, 21 vertex joints, 51 barycentric landmarks
+// =============================================================================================
+__global__ void k_joints_fwd(const float* __restrict__ Jposed, const float* __restrict__ transl, const float* __restrict__ verts,
+                             const int* __restrict__ extra, int n_extra, const int* __restrict__ tri, const float* __restrict__ bary,
+                             int n_lmk, int V, int B, float* __restrict__ joints) {
+    const int nout = NJ + n_extra + n_lmk;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nout) return;
+    const int b = i / nout, q = i - b * nout;
+    float o[3];
+    if (q < NJ) {
+        for (int k = 0; k < 3; ++k) o[k] = Jposed[((size_t)b * NJ + q) * 3 + k] + (transl ? transl[b * 3 + k] : 0.f);
+    } else if (q < NJ + n_extra) {
+        const float* s = verts + ((size_t)b * V + extra[q - NJ]) * 3;
+        for (int k = 0; k < 3; ++k) o[k] = s[k];
+    } else {
+        const int l = q - NJ - n_extra;
+        o[0] = o[1] = o[2] = 0.f;
+        for (int c = 0; c < 3; ++c) {
+            const float w = bary[l * 3 + c];
+            const float* s = verts + ((size_t)b * V + tri[l * 3 + c]) * 3;
+            for (int k = 0; k < 3; ++k) o[k] = fmaf(w, s[k], o[k]);
+        }
+    }
+    for (int k = 0; k < 3; ++k) joints[((size_t)b * nout + q) * 3 + k] = o[k];
+}
+
+__global__ void k_joints_bwd(const float* __restrict__ dj, const int* __restrict__ extra, int n_extra, const int* __restrict__ tri,
+                             const float* __restrict__ bary, int n_lmk, int V, int B, float* __restrict__ Gv,
+                             float* __restrict__ dJp, float* __restrict__ dtr) {
+    const int nout = NJ + n_extra + n_lmk;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nout) return;
+    const int b = i / nout, q = i - b * nout;
+    const float* g = dj + ((size_t)b * nout + q) * 3;
+    if (q < NJ) {
+        for (int k = 0; k < 3; ++k) { atomicAdd(&dJp[((size_t)b * NJ + q) * 3 + k], g[k]); atomicAdd(&dtr[b * 3 + k], g[k]); }
+    } else if (q < NJ + n_extra) {
+        float* d = Gv + ((size_t)b * V + extra[q - NJ]) * 3;
+        for (int k = 0; k < 3; ++k) atomicAdd(&d[k], g[k]);
+    } else {
+        const int l = q - NJ - n_extra;
+        for (int c = 0; c < 3; ++c) {
+            const float w = bary[l * 3 + c];
+            float* d = Gv + ((size_t)b * V + tri[l * 3 + c]) * 3;
+            for (int k = 0; k < 3; ++k) atomicAdd(&d[k], w * g[k]);
+        }
+    }
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, const int* __restrict__ idx, int B, int V, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n * 3) return;
+    const int k = i % 3, r = (i / 3) % n, b = i / (3 * n);
+    out[i] = src[((size_t)b * V + idx[r]) * 3 + k];
+}
+__global__ void k_scatter_rows_add(const float* __restrict__ g, const int* __restrict__ idx, int B, int V, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n * 3) return;
+    const int k = i % 3, r = (i / 3) % n, b = i / (3 * n);
+    atomicAdd(&dst[((size_t)b * V + idx[r]) * 3 + k], g[i]);
+}
+
+// =============================================================================================
+// host-side composition
+// =============================================================================================
+static PoseK make_posek(const Model* m, const PoseIn& in) {
+    PoseK p;
+    p.in = in; p.hand_l = m->hand_l; p.hand_r = m->hand_r; p.pose_mean = m->pose_mean; p.npc = m->npc;
+    return p;
+}
+
+int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st) {
+    LEMO_CHECK(c && B > 0 && B <= c->maxB, "batch exceeds the size this body handle was created for");
+    const Model* m = c->m;
+    k_pose_to_rot<<<cdiv(B * NJ, 128), 128, 0, st>>>(make_posek(m, in), B, c->full_pose, c->R);
+    k_chain_fwd<<<B, 64, 0, st>>>(c->R, in.betas, in.betas_stride, in.expression, m->J_template, m->J_dirs, m->parents, m->depth,
+                                   m->max_depth, c->X, c->G, c->A, c->Jrest, c->Jposed);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st) {
+    LEMO_CHECK(c && ps && verts && B > 0 && B <= c->maxB, "bad arguments");
+    const Model* m = c->m;
+    const int V = m->V;
+    // VP[B,3V] = X[B,512] . Wt[512,3V]
+    GemmP g = gemm_rowmajor(ps->X, m->Wt, c->VP, B, 3 * V, XK, false);
+    LEMO_TRY(gemm_launch(g, st));
+    k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
+    if (joints) {
+        LEMO_CHECK(!m->is_sub, "output joints need the full model");
+        const int nout = NJ + m->n_extra + m->n_lmk;
+        k_joints_fwd<<<cdiv(B * nout, 128), 128, 0, st>>>(ps->Jposed, in.transl, verts, m->extra_vids, m->n_extra, m->lmk_tri,
+                                                            m->lmk_bary, m->n_lmk, V, B, joints);
+    }
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int body_grad_begin(BodyCtx* ps, int B, cudaStream_t st) {
+    LEMO_CHECK(ps && ps->dA, "body handle was created without backward buffers");
+    LEMO_CUDA(cudaMemsetAsync(ps->dA, 0, (size_t)NJ * B * 12 * sizeof(float), st));
+    LEMO_CUDA(cudaMemsetAsync(ps->dX, 0, (size_t)B * XK * sizeof(float), st));
+    LEMO_CUDA(cudaMemsetAsync(ps->dJp, 0, (size_t)B * NJ * 3 * sizeof(float), st));
+    LEMO_CUDA(cudaMemsetAsync(ps->dtr, 0, (size_t)B * 3 * sizeof(float), st));
+    return 0;
+}
+
+int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, const float* d_joints, cudaStream_t st) {
+    LEMO_CHECK(c && ps && c->Gv && ps->dA, "body handle was created without backward buffers");
+    const Model* m = c->m;
+    const int V = m->V;
+    if (d_verts) LEMO_CUDA(cudaMemcpyAsync(c->Gv, d_verts, (size_t)B * V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else LEMO_CUDA(cudaMemsetAsync(c->Gv, 0, (size_t)B * V * 3 * sizeof(float), st));
+    if (d_joints) {
+        LEMO_CHECK(!m->is_sub, "output joints need the full model");
+        const int nout = NJ + m->n_extra + m->n_lmk;
+        k_joints_bwd<<<cdiv(B * nout, 128), 128, 0, st>>>(d_joints, m->extra_vids, m->n_extra, m->lmk_tri, m->lmk_bary, m->n_lmk, V, B,
+                                                            c->Gv, ps->dJp, ps->dtr);
+    }
+    k_skin_bwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, c->DVP, c->DT, ps->dtr);
+    LEMO_CUDA(cudaGetLastError());
+    // dX[B,512] += DVP[B,3V] . Wt^T        (contraction over 3V: split-K with atomics)
+    {
+        GemmP g{};
+        g.A = c->DVP; g.B = m->Wt; g.C = ps->dX; g.bias = nullptr;
+        g.M = B; g.N = XK; g.K = 3 * V;
+        g.sAm = 3 * V; g.sAk = 1; g.sBk = 1; g.sBn = 3 * V; g.sCm = XK; g.sCn = 1;
+        g.splitk = 1; g.nz = std::max(1, std::min(64, (3 * V) / 2048));   // loss-row sub-models: one slice => deterministic
+        LEMO_TRY(gemm_launch(g, st));
+    }
+    // dA[55, B*12] += w_jm[55,V] . DT[V, B*12]   (contraction over V)
+    {
+        GemmP g{};
+        g.A = m->w_jm; g.B = c->DT; g.C = ps->dA; g.bias = nullptr;
+        g.M = NJ; g.N = B * 12; g.K = V;
+        g.sAm = V; g.sAk = 1; g.sBk = (long long)B * 12; g.sBn = 1; g.sCm = (long long)B * 12; g.sCn = 1;
+        g.splitk = 1; g.nz = std::max(1, std::min(32, V / 1024));
+        LEMO_TRY(gemm_launch(g, st));
+    }
+    return 0;
+}
+
+__global__ void k_copy(const float* __restrict__ s, float* __restrict__ d, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = s[i];
+}
+
+int body_pose_backward(BodyCtx* c, const PoseIn& in, int B, const PoseGrad& g, cudaStream_t st) {
+    LEMO_CHECK(c && c->dA, "body handle was created without backward buffers");
+    const Model* m = c->m;
+    if (g.betas && in.betas_stride == 0) LEMO_CUDA(cudaMemsetAsync(g.betas, 0, 10 * sizeof(float), st));
+    k_chain_bwd<<<B, 64, 0, st>>>(c->R, c->G, c->Jrest, c->dA, c->dJp, c->dX, m->J_dirs, m->parents, m->depth, m->max_depth, B,
+                                   in.betas_stride, c->dR, g.betas, g.expression);
+    k_pose_to_rot_bwd<<<B, 64, 0, st>>>(make_posek(m, in), g, B, c->full_pose, c->dR);
+    if (g.transl) k_copy<<<cdiv(B * 3, 128), 128, 0, st>>>(c->dtr, g.transl, B * 3);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gather_rows(const float* src, const int* idx, int B, int V, int n, float* out, cudaStream_t st) {
+    k_gather_rows<<<cdiv((long long)B * n * 3, 256), 256, 0, st>>>(src, idx, B, V, n, out);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+int scatter_rows_add(const float* g, const int* idx, int B, int V, int n, float* dst, cudaStream_t st) {
+    k_scatter_rows_add<<<cdiv((long long)B * n * 3, 256), 256, 0, st>>>(g, idx, B, V, n, dst);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace lemo

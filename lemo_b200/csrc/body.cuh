@@ -1,0 +1,108 @@
+// SMPL-X body-model path: internal interfaces shared by api.cu and fit.cu.
+#pragma once
+#include "common.cuh"
+#include "../../include/lemo_b200.h"
+
+namespace lemo {
+
+// Immutable device-resident model (created once per gender per device).
+struct Model {
+    int device = 0;
+    int V = 0;                 // vertices of THIS model (10475, or n rows for a loss-row sub-model)
+    int npc = 12;              // hand PCA components
+    int n_extra = 0, n_lmk = 0;
+    int max_depth = 0;
+    bool is_sub = false;
+    float* v_template = nullptr;   // [V,3]
+    float* Wt = nullptr;           // [512, 3V]  rows 0..485 posedirs, 486..505 shapedirs^T, 506..511 zero
+    float* w_jm = nullptr;         // [55, V]    skinning weights, joint-major (lbs_weights^T)
+    float* J_template = nullptr;   // [55,3]     J_regressor . v_template
+    float* J_dirs = nullptr;       // [55,3,20]  J_regressor . shapedirs
+    int* parents = nullptr;        // [55] device
+    int* depth = nullptr;          // [55] device
+    float* hand_l = nullptr;       // [npc,45]
+    float* hand_r = nullptr;
+    float* pose_mean = nullptr;    // [165]
+    int* extra_vids = nullptr;     // [n_extra]
+    int* lmk_tri = nullptr;        // [n_lmk,3] vertex ids
+    float* lmk_bary = nullptr;     // [n_lmk,3]
+    int h_parents[NJ];
+    int h_depth[NJ];
+};
+
+// Pointers describing one batch of pose inputs (device, fp32, contiguous rows).
+struct PoseIn {
+    const float* transl = nullptr;          // [B,3] or null (zeros)
+    const float* global_orient = nullptr;   // [B,3] aa, or null when R_global is given
+    const float* body_pose = nullptr;       // [B,63] aa, or null when R_body is given
+    const float* jaw = nullptr;             // [B,3] or null
+    const float* leye = nullptr;
+    const float* reye = nullptr;
+    const float* lhand = nullptr;           // [B,npc] PCA coeffs (hand_is_pca) or [B,45] aa
+    const float* rhand = nullptr;
+    const float* betas = nullptr;           // [B,10] or [1,10] (betas_stride 0)
+    const float* expression = nullptr;      // [B,10] or null
+    const float* R_global = nullptr;        // [B,9]   rotation-matrix override for joint 0
+    const float* R_body = nullptr;          // [B,21,9] override for joints 1..21
+    int betas_stride = 10;                  // floats between consecutive frames' betas (0 = shared)
+    int hand_is_pca = 1;
+};
+struct PoseGrad {                            // all nullable; written (not accumulated) unless noted
+    float* transl = nullptr;
+    float* global_orient = nullptr;
+    float* body_pose = nullptr;
+    float* jaw = nullptr;
+    float* leye = nullptr;
+    float* reye = nullptr;
+    float* lhand = nullptr;
+    float* rhand = nullptr;
+    float* betas = nullptr;                 // [B,10] (or [1,10] accumulated with atomics when betas_stride==0)
+    float* expression = nullptr;            // [B,10]
+    float* R_global = nullptr;              // [B,9]
+    float* R_body = nullptr;                // [B,21,9]
+};
+
+// Per-batch scratch/saved state for forward+backward of one model (or sub-model).
+struct BodyCtx {
+    const Model* m = nullptr;
+    int maxB = 0;
+    float* full_pose = nullptr;  // [B,165]
+    float* R = nullptr;          // [B,55,9]
+    float* X = nullptr;          // [B,512]
+    float* G = nullptr;          // [B,55,12]
+    float* A = nullptr;          // [B,55,12]
+    float* Jrest = nullptr;      // [B,55,3]
+    float* Jposed = nullptr;     // [B,55,3]  (without transl)
+    float* VP = nullptr;         // [B,3V]    v_posed (saved for backward)
+    // backward scratch
+    float* Gv = nullptr;         // [B,V,3]   dL/dverts working copy
+    float* DVP = nullptr;        // [B,3V]
+    float* DT = nullptr;         // [V, B*12]
+    float* dA = nullptr;         // [55, B*12]  joint-major
+    float* dX = nullptr;         // [B,512]
+    float* dR = nullptr;         // [B,55,9]
+    float* dJp = nullptr;        // [B,55,3]
+    float* dtr = nullptr;        // [B,3]
+};
+
+int model_create_from_host(const ::LemoModelDescC* d, int device, Model** out);
+int model_select_rows(const Model* m, const int* rows_host, int n, Model** out);
+void model_free(Model* m);
+
+int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out);
+void bodyctx_free(BodyCtx* c);
+
+// pose -> R, chain -> X, A (shared by a full model and its sub-models: pass the same ctx pose buffers)
+int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st);
+// X, A -> verts [B,V,3] (+transl) ; joints_out [B,127,3] nullable (full model only)
+int body_skin_forward(BodyCtx* c, const BodyCtx* pose_src, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st);
+// d_verts [B,V,3] nullable, d_joints [B,127,3] nullable -> accumulates into pose_src->dA / dX / dtr / dJp
+// (call body_grad_begin first), then body_pose_backward turns those into parameter gradients.
+int body_grad_begin(BodyCtx* pose_src, int B, cudaStream_t st);
+int body_skin_backward(BodyCtx* c, BodyCtx* pose_src, int B, const float* d_verts, const float* d_joints, cudaStream_t st);
+int body_pose_backward(BodyCtx* c, const PoseIn& in, int B, const PoseGrad& g, cudaStream_t st);
+
+int gather_rows(const float* src, const int* idx_dev, int B, int V, int n, float* out, cudaStream_t st);
+int scatter_rows_add(const float* g_rows, const int* idx_dev, int B, int V, int n, float* g_dense, cudaStream_t st);
+
+}  // namespace lemo

@@ -1,0 +1,107 @@
+// Chamfer nearest neighbour, forward + backward.
+// Replaces the external `chamfer` CUDA extension (ChamferDistancePytorch@719b0f1, chamfer.cu) behind
+// temp_prox/dist_chamfer.py:10-53: exact brute-force squared-L2 nearest neighbour both ways, first minimum
+// wins (strict <), int32 indices; backward scatters 2*g*(x1-x2) to both clouds with atomics.
+// Differences from the reference kernel: the target cloud may be SHARED across
+// the batch (batch stride 0) instead of being replicated B times (fitting_temp_slide.py:748), targets are
+// staged as float4 through 16 KB of shared memory, and each thread keeps 4 queries in registers so one
+// broadcast LDS.128 feeds 4 distance evaluations.
+#include "common.cuh"
+#include "../../include/lemo_b200.h"
+
+namespace lemo {
+
+constexpr int CH_TILE = 1024;   // targets per shared-memory tile
+constexpr int CH_QT = 4;        // queries per thread
+
+__global__ void __launch_bounds__(256) k_chamfer_nn(const float* __restrict__ q, long long q_bs, int nq, const float* __restrict__ t,
+                                                    long long t_bs, int nt, float* __restrict__ dist, int* __restrict__ idx) {
+    __shared__ float4 s_t[CH_TILE];
+    const int b = blockIdx.y;
+    const float* qb = q + (size_t)b * q_bs;
+    const float* tb = t + (size_t)b * t_bs;
+    float qx[CH_QT], qy[CH_QT], qz[CH_QT], best[CH_QT];
+    int bi[CH_QT];
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * CH_QT;
+#pragma unroll
+    for (int k = 0; k < CH_QT; ++k) {
+        const int i = min(i0 + k, nq - 1);
+        qx[k] = qb[i * 3]; qy[k] = qb[i * 3 + 1]; qz[k] = qb[i * 3 + 2];
+        best[k] = 3.4e38f; bi[k] = 0;
+    }
+    for (int j0 = 0; j0 < nt; j0 += CH_TILE) {
+        const int nj = min(CH_TILE, nt - j0);
+        for (int j = threadIdx.x; j < nj; j += blockDim.x) {
+            const float* p = tb + (size_t)(j0 + j) * 3;
+            s_t[j] = make_float4(p[0], p[1], p[2], 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
+            const float4 p = s_t[j];
+#pragma unroll
+            for (int k = 0; k < CH_QT; ++k) {
+                const float dx = qx[k] - p.x, dy = qy[k] - p.y, dz = qz[k] - p.z;
+                const float d = dx * dx + dy * dy + dz * dz;
+                if (d < best[k]) { best[k] = d; bi[k] = j0 + j; }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < CH_QT; ++k) {
+        const int i = i0 + k;
+        if (i < nq) { dist[(size_t)b * nq + i] = best[k]; idx[(size_t)b * nq + i] = bi[k]; }
+    }
+}
+
+// gradient of sum_i g[i] * |a_i - c_{idx[i]}|^2 : da_i += 2g(a-c), dc_idx -= 2g(a-c)
+__global__ void k_chamfer_bwd(const float* __restrict__ a, long long a_bs, int na, const float* __restrict__ c, long long c_bs,
+                              const float* __restrict__ g, const int* __restrict__ idx, float* __restrict__ da, float* __restrict__ dc, int B) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * na) return;
+    const int b = (int)(i / na), r = (int)(i - (long long)b * na);
+    const float* ap = a + (size_t)b * a_bs + (size_t)r * 3;
+    const int j = idx[i];
+    const float* cp = c + (size_t)b * c_bs + (size_t)j * 3;
+    const float gg = 2.f * g[i];
+    float* dap = da + (size_t)b * a_bs + (size_t)r * 3;
+    float* dcp = dc + (size_t)b * c_bs + (size_t)j * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = gg * (ap[k] - cp[k]);
+        atomicAdd(&dap[k], v);
+        atomicAdd(&dcp[k], -v);
+    }
+}
+
+}  // namespace lemo
+
+using namespace lemo;
+extern "C" {
+
+int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m, int64_t xyz2_batch_stride, float* dist1,
+                         float* dist2, int32_t* idx1, int32_t* idx2, void* stream) {
+    LEMO_CHECK(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2 && B > 0 && n > 0 && m > 0, "bad arguments");
+    LEMO_CHECK(xyz2_batch_stride == 0 || xyz2_batch_stride >= (int64_t)m * 3, "xyz2_batch_stride must be 0 (shared) or >= 3*m");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_chamfer_nn<<<dim3(cdiv(n, 256 * CH_QT), B), 256, 0, st>>>(xyz1, (long long)n * 3, n, xyz2, xyz2_batch_stride, m, dist1, idx1);
+    k_chamfer_nn<<<dim3(cdiv(m, 256 * CH_QT), B), 256, 0, st>>>(xyz2, xyz2_batch_stride, m, xyz1, (long long)n * 3, n, dist2, idx2);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m, int64_t xyz2_batch_stride,
+                          const float* g_dist1, const float* g_dist2, const int32_t* idx1, const int32_t* idx2, float* d_xyz1,
+                          float* d_xyz2, void* stream) {
+    LEMO_CHECK(xyz1 && xyz2 && g_dist1 && g_dist2 && idx1 && idx2 && d_xyz1 && d_xyz2, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    LEMO_CUDA(cudaMemsetAsync(d_xyz1, 0, (size_t)B * n * 3 * sizeof(float), st));
+    const size_t n2 = xyz2_batch_stride == 0 ? (size_t)m * 3 : (size_t)(B - 1) * xyz2_batch_stride + (size_t)m * 3;
+    LEMO_CUDA(cudaMemsetAsync(d_xyz2, 0, n2 * sizeof(float), st));
+    k_chamfer_bwd<<<cdiv((long long)B * n, 256), 256, 0, st>>>(xyz1, (long long)n * 3, n, xyz2, xyz2_batch_stride, g_dist1, idx1, d_xyz1, d_xyz2, B);
+    k_chamfer_bwd<<<cdiv((long long)B * m, 256), 256, 0, st>>>(xyz2, xyz2_batch_stride, m, xyz1, (long long)n * 3, g_dist2, idx2, d_xyz2, d_xyz1, B);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+}

@@ -1,0 +1,425 @@
+// conv3x3 stack on padded pitch-linear planes (see conv.cuh for the layout argument).
+// Reference semantics: models/AE_sep.py:11-30,77-99 (Enc: 10x conv3x3 p1 + LeakyReLU 0.2, no pooling) and
+// models/AE.py:11-108 (AE: + MaxPool(3,2,1), ConvTranspose(s2, output_size)).  fp32 CUDA-core FMA:
+// the north star keeps tensor cores for the blend-shape GEMM only, and 1e-4 parity rules out single-pass TF32.
+#include "conv.cuh"
+#include "../../include/lemo_b200.h"
+#include <algorithm>
+
+namespace lemo {
+
+constexpr int TP = 256;   // output pixels (linear) per CTA
+constexpr int CT = 8;     // input channels staged per smem pass
+
+// ------------------------------------------------------------------------------------------------
+// main kernel: CTA = NW warps; warp w owns output channels ocb0 + 8w .. +7 for all 256 pixels of the tile;
+// lane g owns pixels 4g..4g+3 and 128+4g..128+4g+3  -> 8 oc x 8 px register tile, weights are warp-uniform
+// (broadcast LDS.128), inputs are conflict-free LDS.128 + LDS.64 per (ic,ky).
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ in, const float* __restrict__ wk,
+                                                     const float* __restrict__ bias, const float* __restrict__ aux,
+                                                     float* __restrict__ out, int Cin, int Cout, int H, int W, int Wp, int PS,
+                                                     int SW, int epi) {
+    constexpr int OCB = NW * 8, NT = NW * 32;
+    extern __shared__ __align__(16) float smem[];
+    float* s_in = smem;                 // [CT][SW]
+    float* s_w = smem + CT * SW;        // [CT][9][OCB]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.z, ocb0 = blockIdx.y * OCB;
+    const int q0 = Wp + blockIdx.x * TP;
+    const float* in_n = in + (size_t)n * Cin * PS;
+
+    float acc[8][8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[o][i] = 0.f;
+
+    for (int ic0 = 0; ic0 < Cin; ic0 += CT) {
+        const int nic = min(CT, Cin - ic0);
+        for (int ic = 0; ic < nic; ++ic) {
+            const float* src = in_n + (size_t)(ic0 + ic) * PS;
+            for (int e = tid; e < SW; e += NT) {
+                const int q = q0 - Wp - 1 + e;
+                s_in[ic * SW + e] = (q >= 0 && q < PS) ? __ldg(src + q) : 0.f;
+            }
+        }
+        for (int idx = tid; idx < nic * 9 * OCB; idx += NT) {
+            const int o = idx % OCB, r = idx / OCB;
+            s_w[idx] = __ldg(wk + (size_t)(ic0 * 9 + r) * Cout + ocb0 + o);
+        }
+        __syncthreads();
+        for (int ic = 0; ic < nic; ++ic) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* p = s_in + ic * SW + ky * Wp + 4 * lane;
+                const float4 a0 = *reinterpret_cast<const float4*>(p);
+                const float2 a1 = *reinterpret_cast<const float2*>(p + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(p + 128);
+                const float2 b1 = *reinterpret_cast<const float2*>(p + 132);
+                const float xa[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
+                const float xb[6] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wp = s_w + (ic * 9 + ky * 3 + kx) * OCB + warp * 8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int o = 0; o < 8; ++o)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc[o][i] = fmaf(wv[o], xa[i + kx], acc[o][i]);
+                            acc[o][4 + i] = fmaf(wv[o], xb[i + kx], acc[o][4 + i]);
+                        }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int qend = (H + 1) * Wp;
+    const size_t obase = ((size_t)n * Cout + ocb0 + warp * 8) * PS;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int q = q0 + half * 128 + 4 * lane;
+        if (q >= qend) continue;
+        const int col = q % Wp;
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ok[i] = (col + i >= 1) && (col + i <= W);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float v[4];
+            const float bo = (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) ? __ldg(bias + ocb0 + warp * 8 + o) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = acc[o][half * 4 + i] + bo;
+            if (epi == EPI_BIAS_LRELU) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = lrelu(v[i]);
+            } else if (epi == EPI_MASK) {
+                const float4 a = *reinterpret_cast<const float4*>(aux + obase + (size_t)o * PS + q);
+                v[0] *= a.x > 0.f ? 1.f : 0.2f; v[1] *= a.y > 0.f ? 1.f : 0.2f;
+                v[2] *= a.z > 0.f ? 1.f : 0.2f; v[3] *= a.w > 0.f ? 1.f : 0.2f;
+            }
+            float4 r;
+            r.x = ok[0] ? v[0] : 0.f; r.y = ok[1] ? v[1] : 0.f; r.z = ok[2] ? v[2] : 0.f; r.w = ok[3] ? v[3] : 0.f;
+            *reinterpret_cast<float4*>(out + obase + (size_t)o * PS + q) = r;
+        }
+    }
+}
+
+// few output channels (the 32->1 input-gradient layer of Enc, AE's 32->1 / 1->1 output layers): thread per pixel
+template <int CO>
+__global__ void __launch_bounds__(256) k_conv3x3_small(const float* __restrict__ in, const float* __restrict__ wk,
+                                                       const float* __restrict__ bias, const float* __restrict__ aux,
+                                                       float* __restrict__ out, int Cin, int H, int W, int Wp, int PS, int epi) {
+    const int n = blockIdx.z;
+    const int q = Wp + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (H + 1) * Wp) return;
+    const int col = q % Wp;
+    const bool ok = col >= 1 && col <= W;
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    if (ok) {
+        const float* in_n = in + (size_t)n * Cin * PS;
+        for (int ic = 0; ic < Cin; ++ic) {
+            const float* p = in_n + (size_t)ic * PS + q;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float x = __ldg(p + (ky - 1) * Wp + (kx - 1));
+#pragma unroll
+                    for (int o = 0; o < CO; ++o) acc[o] = fmaf(x, __ldg(wk + (ic * 9 + ky * 3 + kx) * CO + o), acc[o]);
+                }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        float v = acc[o];
+        if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) v += bias[o];
+        if (epi == EPI_BIAS_LRELU) v = lrelu(v);
+        else if (epi == EPI_MASK) v *= aux[((size_t)n * CO + o) * PS + q] > 0.f ? 1.f : 0.2f;
+        out[((size_t)n * CO + o) * PS + q] = ok ? v : 0.f;
+    }
+}
+
+template <int NW>
+static int conv_main_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out, int N, int Cin,
+                            int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st) {
+    const int SW = (TP + 2 * g.Wp + 2 + 3) / 4 * 4;
+    const size_t smem = (size_t)(CT * SW + CT * 9 * NW * 8) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        LEMO_CUDA(cudaFuncSetAttribute(k_conv3x3<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(cdiv((long long)g.H * g.Wp, TP), Cout / (NW * 8), N);
+    k_conv3x3<NW><<<grid, NW * 32, smem, st>>>(in, wk, bias, aux, out, Cin, Cout, g.H, g.W, g.Wp, g.PS, SW, (int)epi);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int conv3x3_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out, int N, int Cin, int Cout,
+                   const PlaneGeom& g, ConvEpi epi, cudaStream_t st) {
+    if (Cout % 64 == 0) return conv_main_launch<8>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st);
+    if (Cout % 32 == 0) return conv_main_launch<4>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st);
+    dim3 grid(cdiv((long long)g.H * g.Wp, 256), 1, N);
+    if (Cout == 1) k_conv3x3_small<1><<<grid, 256, 0, st>>>(in, wk, bias, aux, out, Cin, g.H, g.W, g.Wp, g.PS, (int)epi);
+    else if (Cout == 4) k_conv3x3_small<4><<<grid, 256, 0, st>>>(in, wk, bias, aux, out, Cin, g.H, g.W, g.Wp, g.PS, (int)epi);
+    else { set_error("conv3x3: unsupported output channel count"); return 2; }
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack(const float* __restrict__ dense, float* __restrict__ planes, long long total, int H, int W, int Wp, int PS) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const long long c = r / H;
+    planes[c * PS + (y + 1) * Wp + x + 1] = dense[i];
+}
+__global__ void k_unpack(const float* __restrict__ planes, float* __restrict__ dense, long long total, int H, int W, int Wp, int PS) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const long long c = r / H;
+    dense[i] = planes[c * PS + (y + 1) * Wp + x + 1];
+}
+// planes = dz * LeakyReLU'(z_planes)   (dz dense)
+__global__ void k_pack_mask(const float* __restrict__ dz, const float* __restrict__ zpl, float* __restrict__ planes, long long total,
+                            int H, int W, int Wp, int PS) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const long long c = r / H;
+    const long long q = c * PS + (y + 1) * Wp + x + 1;
+    planes[q] = dz[i] * (zpl[q] > 0.f ? 1.f : 0.2f);
+}
+int pack_planes(const float* dense, float* planes, int NC, const PlaneGeom& g, cudaStream_t st) {
+    const long long total = (long long)NC * g.H * g.W;
+    k_pack<<<cdiv(total, 256), 256, 0, st>>>(dense, planes, total, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+int unpack_planes(const float* planes, float* dense, int NC, const PlaneGeom& g, cudaStream_t st) {
+    const long long total = (long long)NC * g.H * g.W;
+    k_unpack<<<cdiv(total, 256), 256, 0, st>>>(planes, dense, total, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: state_dict order -> kernel layouts
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prep_weights(const float* __restrict__ w, int Cin, int Cout, int transposed, float* __restrict__ wk_f,
+                               float* __restrict__ wk_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cin * Cout * 9) return;
+    const int k = i % 9, r = i / 9;
+    if (!transposed) {                       // nn.Conv2d  W[oc][ic][k]
+        const int ic = r % Cin, oc = r / Cin;
+        wk_f[((size_t)ic * 9 + k) * Cout + oc] = w[i];
+        wk_b[((size_t)oc * 9 + (8 - k)) * Cin + ic] = w[i];
+    } else {                                 // nn.ConvTranspose2d  W[ic][oc][k]  (stride-1/pad-1 == conv with flipped taps)
+        const int oc = r % Cout, ic = r / Cout;
+        wk_f[((size_t)ic * 9 + (8 - k)) * Cout + oc] = w[i];
+        wk_b[((size_t)oc * 9 + k) * Cin + ic] = w[i];
+    }
+}
+
+int convnet_refresh_weights(ConvNet* n, cudaStream_t st) {
+    for (auto& L : n->layers) {
+        const int tot = L.Cin * L.Cout * 9;
+        k_prep_weights<<<cdiv(tot, 256), 256, 0, st>>>(n->w_flat + L.w_off, L.Cin, L.Cout, L.transposed ? 1 : 0, L.wk_f, L.wk_b);
+    }
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+    LEMO_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    LEMO_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+    return 0;
+}
+
+int convnet_create(int kind, int in_ch, const float* h_weights, long long n_weights, int maxN, int H, int W, bool with_backward,
+                   int device, ConvNet** out) {
+    LEMO_CHECK(out && h_weights && maxN > 0 && H > 0 && W > 0, "bad arguments");
+    LEMO_CHECK(kind == 0, "AE (kind 1) is built by ae.cu");
+    LEMO_CUDA(cudaSetDevice(device));
+    ConvNet* n = new ConvNet();
+    n->device = device; n->kind = kind; n->in_ch = in_ch; n->maxN = maxN; n->with_backward = with_backward;
+    const int chans[11] = {in_ch, 32, 32, 64, 64, 64, 64, 64, 64, 64, 64};      // AE_sep.py:77-89, z_channel=64
+    long long off = 0;
+    for (int l = 0; l < 10; ++l) {
+        ConvLayer L;
+        L.Cin = chans[l]; L.Cout = chans[l + 1]; L.transposed = false;
+        L.w_off = off; off += (long long)L.Cin * L.Cout * 9;
+        L.b_off = off; off += L.Cout;
+        n->layers.push_back(L);
+    }
+    LEMO_CHECK(off == n_weights, "weight vector length does not match Enc(downsample=False, z_channel=64)");
+    n->n_weights = off;
+    LEMO_CUDA(cudaMalloc((void**)&n->w_flat, off * sizeof(float)));
+    LEMO_CUDA(cudaMemcpy(n->w_flat, h_weights, off * sizeof(float), cudaMemcpyHostToDevice));
+    for (auto& L : n->layers) {
+        LEMO_TRY(dalloc(&L.wk_f, (size_t)L.Cin * L.Cout * 9));
+        LEMO_TRY(dalloc(&L.wk_b, (size_t)L.Cin * L.Cout * 9));
+    }
+    LEMO_TRY(convnet_refresh_weights(n, 0));
+    const PlaneGeom g = make_geom(H, W);
+    n->geom.push_back(g);
+    n->act.resize(11, nullptr);
+    LEMO_TRY(dalloc(&n->act[0], (size_t)maxN * in_ch * g.PS));
+    for (int l = 0; l < 10; ++l) LEMO_TRY(dalloc(&n->act[l + 1], (size_t)maxN * chans[l + 1] * g.PS));
+    if (with_backward) {
+        n->grad.resize(2, nullptr);
+        LEMO_TRY(dalloc(&n->grad[0], (size_t)maxN * 64 * g.PS));
+        LEMO_TRY(dalloc(&n->grad[1], (size_t)maxN * 64 * g.PS));
+    }
+    LEMO_CUDA(cudaDeviceSynchronize());
+    *out = n;
+    return 0;
+}
+
+void convnet_free(ConvNet* n) {
+    if (!n) return;
+    cudaSetDevice(n->device);
+    cudaFree(n->w_flat); cudaFree(n->d_wflat);
+    for (auto& L : n->layers) { cudaFree(L.wk_f); cudaFree(L.wk_b); }
+    for (auto p : n->act) cudaFree(p);
+    for (auto p : n->grad) cudaFree(p);
+    for (auto p : n->pool_in) cudaFree(p);
+    for (auto p : n->pool_idx) cudaFree(p);
+    for (auto p : n->up) cudaFree(p);
+    delete n;
+}
+
+int enc_forward_planes(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
+    LEMO_CHECK(n && n->kind == 0 && N > 0 && N <= n->maxN, "bad Enc handle / batch exceeds handle size");
+    const PlaneGeom& g = n->geom[0];
+    const float* cur = x_planes;
+    for (int l = 0; l < 10; ++l) {
+        const ConvLayer& L = n->layers[l];
+        LEMO_TRY(conv3x3_launch(cur, L.wk_f, n->w_flat + L.b_off, nullptr, n->act[l + 1], N, L.Cin, L.Cout, g, EPI_BIAS_LRELU, st));
+        cur = n->act[l + 1];
+    }
+    n->launches += 10;
+    return 0;
+}
+
+int enc_backward_planes(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
+    LEMO_CHECK(n && n->kind == 0 && n->with_backward && N > 0 && N <= n->maxN, "Enc handle has no backward buffers");
+    const PlaneGeom& g = n->geom[0];
+    float* cur = n->grad[0];
+    float* nxt = n->grad[1];
+    for (int l = 9; l >= 1; --l) {          // dpre_l -> dpre_{l-1} = convT(dpre_l) * LeakyReLU'(a_{l-1})
+        const ConvLayer& L = n->layers[l];
+        LEMO_TRY(conv3x3_launch(cur, L.wk_b, nullptr, n->act[l], nxt, N, L.Cout, L.Cin, g, EPI_MASK, st));
+        std::swap(cur, nxt);
+    }
+    const ConvLayer& L0 = n->layers[0];
+    LEMO_TRY(conv3x3_launch(cur, L0.wk_b, nullptr, nullptr, dx_planes, N, L0.Cout, L0.Cin, g, EPI_NONE, st));
+    n->launches += 10;
+    return 0;
+}
+
+}  // namespace lemo
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace lemo;
+#include "handles.cuh"
+
+namespace lemo { int ae_create(int in_ch, const float* h_weights, long long n_weights, int maxN, int H, int W, bool with_backward,
+                               int device, ConvNet** out); }
+
+extern "C" {
+int lemo_convnet_create(int32_t kind, int32_t in_channels, const float* h_weights, int64_t n_weights, int32_t max_n, int32_t H,
+                        int32_t W, int32_t with_backward, int device, LemoConvNet** out) {
+    LEMO_CHECK(out, "null out");
+    ConvNet* n = nullptr;
+    if (kind == 0) LEMO_TRY(convnet_create(0, in_channels, h_weights, n_weights, max_n, H, W, with_backward != 0, device, &n));
+    else if (kind == 1) LEMO_TRY(ae_create(in_channels, h_weights, n_weights, max_n, H, W, with_backward != 0, device, &n));
+    else { set_error("unknown convnet kind"); return 2; }
+    LemoConvNet* h = new LemoConvNet{n, nullptr};
+    if (kind == 0 && with_backward) {
+        LEMO_CUDA(cudaMalloc((void**)&h->dx_planes, (size_t)max_n * in_channels * n->geom[0].PS * sizeof(float)));
+        LEMO_CUDA(cudaMemset(h->dx_planes, 0, (size_t)max_n * in_channels * n->geom[0].PS * sizeof(float)));
+    }
+    *out = h;
+    return 0;
+}
+int lemo_convnet_destroy(LemoConvNet* h) {
+    if (!h) return 0;
+    cudaFree(h->dx_planes);
+    convnet_free(h->n);
+    delete h;
+    return 0;
+}
+int64_t lemo_convnet_num_weights(const LemoConvNet* h) { return h ? h->n->n_weights : 0; }
+int lemo_convnet_set_weights(LemoConvNet* h, const float* w, void* stream) {
+    LEMO_CHECK(h && w, "bad arguments");
+    LEMO_CUDA(cudaMemcpyAsync(h->n->w_flat, w, h->n->n_weights * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return convnet_refresh_weights(h->n, (cudaStream_t)stream);
+}
+int lemo_convnet_get_weights(LemoConvNet* h, float* w, void* stream) {
+    LEMO_CHECK(h && w, "bad arguments");
+    LEMO_CUDA(cudaMemcpyAsync(w, h->n->w_flat, h->n->n_weights * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int lemo_enc_forward(LemoConvNet* h, const float* x, int32_t N, float* z, void* stream) {
+    LEMO_CHECK(h && h->n->kind == 0 && x && z, "bad arguments");
+    ConvNet* n = h->n;
+    cudaStream_t st = (cudaStream_t)stream;
+    LEMO_CHECK(N > 0 && N <= n->maxN, "batch exceeds handle size");
+    LEMO_TRY(pack_planes(x, n->act[0], N * n->in_ch, n->geom[0], st));
+    LEMO_TRY(enc_forward_planes(n, n->act[0], N, st));
+    LEMO_TRY(unpack_planes(n->act[10], z, N * 64, n->geom[0], st));
+    return 0;
+}
+int lemo_convnet_profile_layer(LemoConvNet* h, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream) {
+    LEMO_CHECK(h && h->n->kind == 0 && layer >= 0 && layer < 10 && N > 0 && N <= h->n->maxN, "bad arguments");
+    ConvNet* n = h->n;
+    const ConvLayer& L = n->layers[layer];
+    for (int r = 0; r < reps; ++r) {
+        if (!backward) {
+            LEMO_TRY(conv3x3_launch(n->act[layer], L.wk_f, n->w_flat + L.b_off, nullptr, n->act[layer + 1], N, L.Cin, L.Cout, n->geom[0],
+                                    EPI_BIAS_LRELU, (cudaStream_t)stream));
+        } else {
+            LEMO_CHECK(n->with_backward && layer >= 1, "backward profiling needs backward buffers and layer >= 1");
+            LEMO_TRY(conv3x3_launch(n->grad[0], L.wk_b, nullptr, n->act[layer], n->grad[1], N, L.Cout, L.Cin, n->geom[0], EPI_MASK,
+                                    (cudaStream_t)stream));
+        }
+    }
+    return 0;
+}
+int lemo_enc_backward_input(LemoConvNet* h, const float* dz, int32_t N, float* dx, void* stream) {
+    LEMO_CHECK(h && h->n->kind == 0 && dz && dx && h->dx_planes, "bad arguments / handle created without backward");
+    ConvNet* n = h->n;
+    cudaStream_t st = (cudaStream_t)stream;
+    LEMO_CHECK(N > 0 && N <= n->maxN, "batch exceeds handle size");
+    const PlaneGeom& g = n->geom[0];
+    const long long total = (long long)N * 64 * g.H * g.W;
+    k_pack_mask<<<cdiv(total, 256), 256, 0, st>>>(dz, n->act[10], n->grad[0], total, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    LEMO_TRY(enc_backward_planes(n, N, h->dx_planes, st));
+    LEMO_TRY(unpack_planes(h->dx_planes, dx, N * n->in_ch, g, st));
+    return 0;
+}
+}

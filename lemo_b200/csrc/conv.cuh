@@ -1,0 +1,73 @@
+// 3x3 convolution stack of the motion priors (reference models/AE_sep.py, models/AE.py) on sm_100a.
+//
+// Activation layout ("padded pitch-linear planes"): a [N,C,H,W] tensor is stored as [N][C][Hp*Wp] with
+// Hp = H+2, Wp = roundup(W+2, 8); pixel (y,x) lives at (y+1)*Wp + (x+1) and every border element is 0.
+// With the zero border physically present a 3x3/pad-1 convolution is a pure 1-D correlation over the
+// linear index  out[q] = sum in[q + (ky-1)*Wp + (kx-1)] * w[ky][kx], so CTAs tile the LINEAR pixel range
+// in 256-pixel tiles: no 2-D tile-edge waste on the 245x134 (or any T) image, 16-byte aligned vector
+// smem reads for every (ky,kx) shift, coalesced 512-byte output rows.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace lemo {
+
+struct PlaneGeom {
+    int H, W, Hp, Wp, PS;   // PS = Hp*Wp
+};
+inline PlaneGeom make_geom(int H, int W) {
+    PlaneGeom g;
+    g.H = H; g.W = W; g.Hp = H + 2; g.Wp = (W + 2 + 7) / 8 * 8; g.PS = g.Hp * g.Wp;
+    return g;
+}
+
+enum ConvEpi { EPI_BIAS_LRELU = 0, EPI_MASK = 1, EPI_BIAS = 2, EPI_NONE = 3 };
+
+// out[n][oc] = epi( sum_ic in[n][ic] (*) wk[ic][ky][kx][oc] ),  wk is [Cin][9][Cout] (oc fastest)
+int conv3x3_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out,
+                   int N, int Cin, int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st);
+// dW[oc][ic][ky][kx] (+)= sum_{n,pix} dpre[n][oc][q] * in[n][ic][q + shift];  db[oc] (+)= sum dpre
+int conv3x3_wgrad_launch(const float* in, const float* dpre, float* dW_oikk, float* db, int N, int Cin, int Cout,
+                         const PlaneGeom& g, bool transpose_io, cudaStream_t st);
+
+int pack_planes(const float* dense, float* planes, int NC, const PlaneGeom& g, cudaStream_t st);
+int unpack_planes(const float* planes, float* dense, int NC, const PlaneGeom& g, cudaStream_t st);
+
+struct ConvLayer {
+    int Cin = 0, Cout = 0;
+    bool transposed = false;   // nn.ConvTranspose2d weight layout [Cin,Cout,3,3]
+    long long w_off = 0, b_off = 0;   // offsets into the flat state_dict-ordered weight vector
+    float* wk_f = nullptr;     // forward kernel weights   [Cin][9][Cout]
+    float* wk_b = nullptr;     // input-gradient weights   [Cout][9][Cin]
+};
+
+struct ConvNet {
+    int device = 0;
+    int kind = 0;              // 0 Enc (AE_sep, no pooling), 1 AE
+    int in_ch = 1, maxN = 0;
+    bool with_backward = false;
+    long long n_weights = 0;
+    float* w_flat = nullptr;   // state_dict order (the tensor Adam updates during the AE fine-tune)
+    std::vector<ConvLayer> layers;
+    std::vector<PlaneGeom> geom;       // geometry per resolution level (Enc: 1 level; AE: 6 levels)
+    std::vector<float*> act;           // saved activations (planes) per layer output, act[0] = packed input
+    std::vector<float*> grad;          // gradient planes (two ping-pong buffers per level)
+    std::vector<float*> pool_in;       // AE: pre-pool activations
+    std::vector<int*> pool_idx;        // AE: argmax indices
+    std::vector<float*> up;            // AE: zero-upsampled planes
+    float* d_wflat = nullptr;
+    long long launches = 0;
+};
+
+int convnet_create(int kind, int in_ch, const float* h_weights, long long n_weights, int maxN, int H, int W,
+                   bool with_backward, int device, ConvNet** out);
+void convnet_free(ConvNet* n);
+int convnet_refresh_weights(ConvNet* n, cudaStream_t st);      // rebuild wk_f / wk_b from w_flat
+// Enc on planes: x_planes [N][1][PS] -> act.back() [N][64][PS]
+int enc_forward_planes(ConvNet* n, const float* x_planes, int N, cudaStream_t st);
+// dpre of the last layer must be in n->grad[0] (already multiplied by LeakyReLU'(z)); result dx_planes [N][1][PS]
+int enc_backward_planes(ConvNet* n, int N, float* dx_planes, cudaStream_t st);
+inline float* enc_z_planes(ConvNet* n) { return n->act.back(); }
+inline float* enc_gz_planes(ConvNet* n) { return n->grad[0]; }
+
+}  // namespace lemo

@@ -1,0 +1,94 @@
+// Generic strided fp32 GEMM (see gemm.cuh).  Plain CUDA-core code: this kernel is deliberately the
+// "utility" path; the roofline kernels (fused LBS forward, conv3x3) have their own files.
+#include "gemm.cuh"
+
+namespace lemo {
+
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+__global__ void __launch_bounds__(256) k_gemm(GemmP p) {
+    __shared__ float As[GBK][GBM + 4];
+    __shared__ float Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const float* A = p.A;
+    const float* B = p.B;
+    float* C = p.C;
+    int k_begin = 0, k_end = p.K;
+    if (p.splitk) {
+        const int chunk = ((p.K + p.nz - 1) / p.nz + GBK - 1) / GBK * GBK;
+        k_begin = blockIdx.z * chunk;
+        k_end = min(p.K, k_begin + chunk);
+    } else {
+        A += (long long)blockIdx.z * p.bA;
+        B += (long long)blockIdx.z * p.bB;
+        C += (long long)blockIdx.z * p.bC;
+    }
+    const bool a_kfast = (p.sAk == 1);
+    const bool b_nfast = (p.sBn == 1);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += GBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (a_kfast) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
+            const int gm = m0 + m, gk = k0 + k;
+            As[k][m] = (gm < p.M && gk < k_end) ? A[gm * p.sAm + gk * p.sAk] : 0.f;
+            int n, kb;
+            if (b_nfast) { n = idx & 63; kb = idx >> 6; } else { kb = idx & 15; n = idx >> 4; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            Bs[kb][n] = (gn < p.N && gkb < k_end) ? B[gkb * p.sBk + gn * p.sBn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= p.N) continue;
+            float* c = C + gm * p.sCm + gn * p.sCn;
+            float v = acc[i][j];
+            if (p.splitk) {
+                if (p.bias && blockIdx.z == 0) v += p.bias[gn];
+                atomicAdd(c, v);
+            } else {
+                if (p.bias) v += p.bias[gn];
+                if (p.act == 1) v = lrelu(v);
+                else if (p.act == 2) v *= (p.mask_src[gm * p.sCm + gn * p.sCn] > 0.f ? 1.f : 0.2f);
+                if (p.accumulate) v += *c;
+                *c = v;
+            }
+        }
+    }
+}
+
+int gemm_launch(const GemmP& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+    dim3 grid(cdiv(p.N, GBN), cdiv(p.M, GBM), p.nz > 0 ? p.nz : 1);
+    k_gemm<<<grid, 256, 0, st>>>(p);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace lemo

@@ -1,0 +1,89 @@
+"""Drop-in for the hot-path functions of the reference's utils/utils.py (lines 50-169): 6D <-> axis-angle
+conversions and the params72 -> body mesh helpers."""
+import torch
+
+from .. import _lib
+
+
+class _Rot6dToMat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x6):
+        x6 = x6.contiguous().float()
+        n = x6.numel() // 6
+        R = torch.empty(n, 9, device=x6.device)
+        _lib.call('lemo_rot6d_to_rotmat', _lib.ptr(x6), n, _lib.ptr(R), _lib.cur_stream(x6.device))
+        ctx.save_for_backward(x6)
+        return R.view(n, 3, 3)
+
+    @staticmethod
+    def backward(ctx, gR):
+        (x6,) = ctx.saved_tensors
+        n = x6.numel() // 6
+        dx = torch.empty_like(x6)
+        _lib.call('lemo_rot6d_to_rotmat_backward', _lib.ptr(x6), _lib.ptr(gR.contiguous().float()), n, _lib.ptr(dx),
+                  _lib.cur_stream(x6.device))
+        return dx
+
+
+def _ew(name, x, in_w, out_w):
+    x = x.contiguous().float()
+    n = x.numel() // in_w
+    out = torch.empty(n, out_w, device=x.device)
+    _lib.call(name, _lib.ptr(x), n, _lib.ptr(out), _lib.cur_stream(x.device))
+    return out
+
+
+class ContinousRotReprDecoder:
+    """utils/utils.py:50-90."""
+
+    @staticmethod
+    def decode(module_input):
+        return _Rot6dToMat.apply(module_input.reshape(-1, 6))
+
+    @staticmethod
+    def matrot2aa(pose_matrot):
+        return _ew('lemo_rotmat_to_aa', pose_matrot.detach().reshape(-1, 9), 9, 3)
+
+    @staticmethod
+    def aa2matrot(pose):
+        x6 = _ew('lemo_aa_to_rot6d', pose.detach().reshape(-1, 3), 3, 6)
+        return _Rot6dToMat.apply(x6)      # exact for a rotation's own first two columns
+
+
+def convert_to_6D_all(x_batch):
+    """utils/utils.py:127-130 (init only, no gradient in the reference's use)."""
+    return _ew('lemo_aa_to_rot6d', x_batch.detach().reshape(-1, 3), 3, 6)
+
+
+def convert_to_3D_all(x_batch):
+    return ContinousRotReprDecoder.matrot2aa(ContinousRotReprDecoder.decode(x_batch))
+
+
+def convert_to_3D_rot(x_batch):
+    """utils/utils.py:111-123, forward values ([bs,75] -> [bs,72]).  The aa slot is produced for the result vector;
+    use gen_body_mesh_v1(params75) to differentiate through the body model (it consumes the 6D part directly)."""
+    xr_aa = convert_to_3D_all(x_batch[:, 3:9])
+    return torch.cat([x_batch[:, :3], xr_aa, x_batch[:, 9:]], dim=-1)
+
+
+def gen_body_mesh_v1(body_params, smplx_model, vposer_model, return_joints=False):
+    """utils/utils.py:141-154.  body_params [T,72] (aa global orient) or [T,75] (6D global orient, differentiable:
+    the global rotation and the VPoser body rotations enter the body model as matrices, which is gradient-equivalent
+    to the reference's R -> aa -> Rodrigues round trip)."""
+    bs = body_params.shape[0]
+    six = body_params.shape[1] == 75
+    o = 3 if six else 0
+    kw = dict(transl=body_params[:, 0:3], betas=body_params[:, 6 + o:16 + o],
+              left_hand_pose=body_params[:, 48 + o:60 + o], right_hand_pose=body_params[:, 60 + o:72 + o])
+    if six:
+        kw['R_global'] = ContinousRotReprDecoder.decode(body_params[:, 3:9]).reshape(bs, 9)
+    else:
+        kw['global_orient'] = body_params[:, 3:6]
+    kw['R_body'] = vposer_model.decode(body_params[:, 16 + o:48 + o], output_type='matrot').reshape(bs, 21, 9)
+    out = smplx_model(return_verts=True, **kw)
+    return out.joints if return_joints else out.vertices
+
+
+def gen_body_joints_v1(body_params, smplx_model, vposer_model):
+    """utils/utils.py:156-169."""
+    return gen_body_mesh_v1(body_params, smplx_model, vposer_model, return_joints=True)

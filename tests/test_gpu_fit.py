@@ -1,0 +1,115 @@
+"""GPU parity of the fused fitting drivers against the oracle's restatement of the reference loops."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, ref_body as rb, ref_loops as rl
+from gpu_common import DEV, smplx_module, vposer_module, enc_module, oracle_ctx, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(s, T, ctx):
+    clean, init, contact = synth.make_sequence(s, T=T)
+    with torch.no_grad():
+        v, _ = rb.gen_body_mesh(torch.from_numpy(clean).to(ctx.dtype), ctx.smplx, ctx.vposer)
+    return init, v[:, ctx.m67].float().numpy(), contact
+
+
+def _fitter(S, T, **kw):
+    from lemo_b200.fit import TemporalFitter
+    return TemporalFitter(smplx_module(), vposer_module(), S, T, enc=enc_module(), device=DEV, **kw)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_temporal_first_iteration_gradients(graph):
+    T, S = 119, 2
+    c32, c64 = oracle_ctx(torch.float32), oracle_ctx(torch.float64)
+    fit = _fitter(S, T, use_cuda_graph=graph)
+    probs = [_problem(s, T, c32) for s in range(S)]
+    for s, (init, mrec, con) in enumerate(probs):
+        fit.set_sequence(s, init, mrec, con)
+    fit.run(n_iters=1)
+    st = fit.state()
+    p72, losses = fit.results()
+    for s, (init, mrec, con) in enumerate(probs):
+        tr32, tr64 = [], []
+        ref72, _ = rl.fit_temp(init, mrec, con, c32, n_iters=1, faithful=False, trace=tr32)
+        rl.fit_temp(init, mrec, con, c64, n_iters=1, faithful=False, trace=tr64)
+        sl = slice(s * T, (s + 1) * T)
+        for k in ('g_transl', 'g_rot6d', 'g_other'):
+            e32 = rel(tr32[0][k], tr64[0][k])
+            e = rel(st[k][sl], tr64[0][k])
+            assert e < max(5 * e32, 1e-4), (k, s, e, e32)
+        for i, k in enumerate(['loss', 'rec', 'vposer', 'shape', 'hand', 'contact', 'smooth']):
+            want = tr64[0][k]
+            assert abs(float(losses[s, i]) - want) <= 2e-4 * abs(want) + 1e-9, (k, float(losses[s, i]), want)
+        assert rel(p72[s], ref72) < 2e-5                    # parameters of the (first) forward incl. tgm axis-angle
+
+
+def test_temporal_loop_tracks_oracle():
+    T, n_it = 60, 12
+    c32 = oracle_ctx(torch.float32)
+    fit = _fitter(1, T)
+    init, mrec, con = _problem(4, T, c32)
+    fit.set_sequence(0, init, mrec, con)
+    fit.run(n_iters=n_it, lr0=0.01, lr1=0.005, lr_switch=6)
+    p72, losses = fit.results()
+    tr = []
+    ref72, _ = rl.fit_temp(init, mrec, con, c32, n_iters=n_it, lr_switch=6, faithful=True, trace=tr)
+    assert np.abs(p72[0].cpu().numpy() - ref72).max() < 2e-3           # Adam steps are O(lr): allow a few ulps of drift per step
+    assert abs(float(losses[0, 0]) - tr[-1]['loss']) < 2e-2 * abs(tr[-1]['loss'])
+    assert tr[-1]['loss'] < tr[0]['loss']
+
+
+def test_temporal_deterministic_across_slots_and_runs():
+    """Same sequence in two slots / two runs -> bitwise identical parameters (multi-GPU determinism contract)."""
+    T = 40
+    c32 = oracle_ctx(torch.float32)
+    init, mrec, con = _problem(2, T, c32)
+    outs = []
+    for _ in range(2):
+        fit = _fitter(2, T)
+        for s in range(2):
+            fit.set_sequence(s, init, mrec, con)
+        fit.run(n_iters=5)
+        outs.append(fit.state())
+    a, b = outs
+    for k in ('transl', 'rot6d', 'other'):
+        assert torch.equal(a[k][:T], a[k][T:])
+        assert torch.equal(a[k], b[k])
+
+
+def test_perframe_tracks_oracle():
+    from lemo_b200.fit import PerFrameFitter
+    T, n_it = 3, 25
+    c32 = oracle_ctx(torch.float32)
+    clean, _, _ = synth.make_sequence(1, T=T)
+    with torch.no_grad():
+        v, _ = rb.gen_body_mesh(torch.from_numpy(clean), c32.smplx, c32.vposer)
+    mrec = v[:, c32.m67].numpy()
+    fit = PerFrameFitter(smplx_module(), vposer_module(), 2, T, device=DEV)
+    for s in range(2):
+        fit.set_sequence(s, clean[0, 6:16], mrec)
+    fit.run(n_iters=n_it)
+    p72, losses = fit.results()
+    tr = []
+    ref = rl.fit_perframe(mrec, clean[0, 6:16], c32, n_frames=T, n_iters=n_it, trace=tr)
+    assert torch.equal(p72[0], p72[1])
+    assert np.abs(p72[0].cpu().numpy() - ref).max() < 2e-2              # lr 0.1 on frame 0: O(lr) steps, loose absolute bound
+    assert abs(float(losses[0, 0]) - tr[-1]) < 5e-2 * abs(tr[-1]) + 1e-4
+
+
+def test_full_size_property_rest_pose_zero_loss():
+    """Size-independent property at BASELINE's full size: targets generated from the init => rec loss 0, grads of rec term vanish,
+    and the loss decreases monotonically-ish afterwards."""
+    T = 119
+    c32 = oracle_ctx(torch.float32)
+    clean, _, con = synth.make_sequence(0, T=T)
+    with torch.no_grad():
+        v, _ = rb.gen_body_mesh(torch.from_numpy(clean), c32.smplx, c32.vposer)
+    fit = _fitter(1, T, weights=dict(w_smooth=0.0, w_contact=0.0, w_vposer=0.0, w_hand=0.0))
+    fit.set_sequence(0, clean, v[:, c32.m67].numpy(), con)
+    fit.run(n_iters=1)
+    _, losses = fit.results()
+    assert float(losses[0, 1]) < 2e-6

@@ -1,0 +1,134 @@
+"""GPU parity of the motion priors (Enc), VPoser decoder, Chamfer, rotation ops and Adam against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, ref_body as rb, ref_priors as rp
+from gpu_common import DEV, vposer_module, vposer_w, enc_module, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_enc_forward_backward_golden(golden):
+    """Enc with the shipped real weights vs the REAL reference's outputs (tests/golden)."""
+    enc = enc_module()
+    for tag in ('small', 'full'):
+        x = torch.from_numpy(golden['enc_%s_x' % tag]).to(DEV).requires_grad_(True)
+        z = enc(x)[0]
+        loss = (z[..., 1:] - z[..., :-1]).pow(2).mean()
+        loss.backward()
+        if tag == 'small':
+            assert rel(z, golden['enc_small_z']) < 1e-4
+        else:
+            assert rel(z[:, ::8, ::7, ::9], golden['enc_full_z_sub']) < 1e-4
+        assert abs(float(loss) - float(golden['enc_%s_loss' % tag])) < 1e-4 * float(golden['enc_%s_loss' % tag])
+        assert rel(x.grad, golden['enc_%s_gx' % tag]) < 1e-3, rel(x.grad, golden['enc_%s_gx' % tag])
+
+
+def test_enc_backward_tolerance_budget():
+    sd32 = {k: torch.from_numpy(v) for k, v in synth.load_enc_weights().items()}
+    sd64 = {k: v.double() for k, v in sd32.items()}
+    x = torch.from_numpy((0.5 * np.random.default_rng(9).standard_normal((2, 1, 37, 53))).astype(np.float32))
+    gz = torch.from_numpy(np.random.default_rng(10).standard_normal((2, 64, 37, 53)).astype(np.float32))
+    res = {}
+    for sd, dt in ((sd32, torch.float32), (sd64, torch.float64)):
+        xx = x.to(dt).requires_grad_(True)
+        (rp.enc_forward(xx, sd) * gz.to(dt)).sum().backward()
+        res[dt] = xx.grad
+    xg = x.to(DEV).requires_grad_(True)
+    (enc_module()(xg)[0] * gz.to(DEV)).sum().backward()
+    e32, e = rel(res[torch.float32], res[torch.float64]), rel(xg.grad, res[torch.float64])
+    assert e < max(4 * e32, 1e-5), (e, e32)
+
+
+def test_vposer_decode_and_adjoint():
+    B = 7
+    z = torch.from_numpy((np.random.default_rng(4).standard_normal((B, 32))).astype(np.float32))
+    gR = torch.from_numpy(np.random.default_rng(5).standard_normal((B * 21, 3, 3)).astype(np.float32))
+    ref = rb.VPoserRef(vposer_w(), dtype=torch.float64)
+    z64 = z.double().requires_grad_(True)
+    R64 = ref.decode_matrot(z64)
+    (R64 * gR.double()).sum().backward()
+    ref32 = rb.VPoserRef(vposer_w())
+    z32 = z.clone().requires_grad_(True)
+    (ref32.decode_matrot(z32) * gR).sum().backward()
+    zg = z.to(DEV).requires_grad_(True)
+    vp = vposer_module()
+    R = vp.decode(zg, 'matrot')
+    (R.view(B * 21, 3, 3) * gR.to(DEV)).sum().backward()
+    assert rel(R.view(B * 21, 3, 3), R64) < 1e-5
+    assert rel(zg.grad, z64.grad) < max(4 * rel(z32.grad, z64.grad), 2e-5)
+    aa = vp.decode(z.to(DEV), 'aa')
+    assert aa.shape == (B, 1, 21, 3)
+    assert rel(aa.view(-1, 3), ref32.decode_aa(z).view(-1, 3)) < 2e-5
+
+
+@pytest.mark.parametrize('B,n,m,shared', [(3, 257, 1500, False), (4, 1121, 5000, True), (1, 5, 3, False)])
+def test_chamfer_matches_oracle(B, n, m, shared):
+    from lemo_b200.temp_prox.dist_chamfer import chamferDist
+    g = np.random.default_rng(B * 100 + n)
+    a = torch.from_numpy(g.standard_normal((B, n, 3)).astype(np.float32))
+    b = torch.from_numpy(g.standard_normal((1 if shared else B, m, 3)).astype(np.float32))
+    ga = a.clone().requires_grad_(True)
+    gb = b.clone().requires_grad_(True)
+    d1, d2, i1, i2 = rp.chamfer(ga, gb.expand(B, -1, -1))
+    w1 = torch.from_numpy(g.standard_normal((B, n)).astype(np.float32))
+    w2 = torch.from_numpy(g.standard_normal((B, m)).astype(np.float32))
+    ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+    xa = a.to(DEV).requires_grad_(True)
+    xb = b.to(DEV).requires_grad_(True)
+    e1, e2, j1, j2 = chamferDist()(xa, xb)
+    ((e1 * w1.to(DEV)).sum() + (e2 * w2.to(DEV)).sum()).backward()
+    assert j1.dtype == torch.int32 and j2.dtype == torch.int32
+    assert (j1.cpu() == i1).float().mean() > 0.999 and (j2.cpu() == i2).float().mean() > 0.999   # ties may differ in the last ulp
+    assert rel(e1, d1) < 1e-5 and rel(e2, d2) < 1e-5
+    assert rel(xa.grad, ga.grad) < 1e-4
+    assert rel(xb.grad, gb.grad) < 1e-4
+
+
+def test_chamfer_identity_property():
+    """size-independent property at config-4 scale: a cloud against itself has zero distance and idx = arange."""
+    from lemo_b200.temp_prox.dist_chamfer import chamferDist
+    x = torch.randn(2, 20000, 3, device=DEV)
+    d1, d2, i1, i2 = chamferDist()(x, x)
+    ar = torch.arange(20000, device=DEV, dtype=torch.int32).expand(2, -1)
+    assert float(d1.abs().max()) == 0.0 and float(d2.abs().max()) == 0.0
+    assert torch.equal(i1, ar) and torch.equal(i2, ar)
+
+
+def test_rotation_ops_and_6d_adjoint():
+    from lemo_b200.utils import utils as U
+    g = np.random.default_rng(8)
+    aa = torch.from_numpy(g.standard_normal((50, 3)).astype(np.float32))
+    x6 = U.convert_to_6D_all(aa.to(DEV))
+    assert rel(x6, rb.convert_to_6D_all(aa)) < 2e-6
+    x = torch.from_numpy(g.standard_normal((50, 6)).astype(np.float32))
+    gR = torch.from_numpy(g.standard_normal((50, 3, 3)).astype(np.float32))
+    x64 = x.double().requires_grad_(True)
+    (rb.gram_schmidt_6d(x64) * gR.double()).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    R = U.ContinousRotReprDecoder.decode(xg)
+    (R * gR.to(DEV)).sum().backward()
+    assert rel(R, rb.gram_schmidt_6d(x)) < 2e-6
+    assert rel(xg.grad, x64.grad) < 1e-4
+    p75 = torch.from_numpy(g.standard_normal((9, 75)).astype(np.float32))
+    assert rel(U.convert_to_3D_rot(p75.to(DEV)), rb.convert_to_3D_rot(p75)) < 2e-5
+
+
+def test_adam_step_matches_torch():
+    from lemo_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=0.01)
+    p = p0.to(DEV); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for t in range(1, 31):
+        grad = torch.randn(1000, generator=g) * (1.0 if t % 3 else 1e-3)
+        p_ref.grad = grad.clone()
+        lr = 0.01 if t <= 20 else 0.005
+        for gr in opt.param_groups:
+            gr['lr'] = lr
+        opt.step()
+        gd = grad.to(DEV)
+        _lib.call('lemo_adam_step', _lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v), 1000, lr, 0.9, 0.999, 1e-8, t, _lib.cur_stream())
+    assert rel(p, p_ref) < 1e-5
