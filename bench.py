@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- fitting iterations/sec of the fused temporal fit on synthetic 120-frame SMPL-X sequences.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (N>1 under torchrun, one rank per
+GPU) prints ONE JSON line on rank 0.  One "step" = one Adam fitting iteration (forward + losses + backward + update,
+reference opt_amass_temp.py:349-455) of every in-flight sequence of the rank.
+
+Workload = BASELINE.json configs[4] shaped for weak scaling: 8 sequences x 120 frames per GPU (64 sequences on 8
+GPUs), config-3 loss (marker L1 + Enc smoothness prior + foot-contact velocity + L2 priors), fp32, synthetic
+SMPL-X-shaped model and VPoser weights, real Enc weights.  Sequences are independent: rank r fits the ones with
+id % N == r and there is no collective on the data path.
+
+`--impl reference` times the reference's own CPU op sequence (oracle/ref_loops.py: double SMPL-X + VPoser evaluation,
+6D->aa->Rodrigues round trip, eager autograd, torch.optim.Adam) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_FRAMES = 120
+METRIC = 'fitting_iters_per_sec'
+UNIT = 'sequence-iterations/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--seqs-per-gpu', type=int, default=8)
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--cpu-iters', type=int, default=8, help='timed CPU-baseline iterations (bounded sample)')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {'workload': 'configs[4] weak-scaled: %d synthetic AMASS-shaped sequences x %d frames per GPU (%d total), '
+                        'opt_amass_temp loss (marker L1 + Enc smoothness + contact velocity + L2 priors), Adam' %
+                        (a.seqs_per_gpu, T_FRAMES, a.seqs_per_gpu * world),
+            'seqs_per_gpu': a.seqs_per_gpu, 'frames': T_FRAMES, 'sharding': 'round-robin by sequence, no collective',
+            'l2_policy': 'per-iteration working set (Enc activations %.0f MB/GPU) exceeds the 126 MB L2' %
+                         (a.seqs_per_gpu * 75.6 * 2)}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=10)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        reasons = []
+        for i, name in ((3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')):
+            if any(len(r) > i and r[i].lower().startswith('active') for r in self.rows):
+                reasons.append(name)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(n_iters, warm=2):
+    """Reference op sequence on the host cores: 1 sequence x 120 frames, `n_iters` timed Adam iterations."""
+    import torch
+    from oracle import synth, ref_body as rb, ref_loops as rl
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ctx = rl.FitContext(synth.make_smplx_model(0), synth.make_vposer_weights(1), synth.load_enc_weights(), synth.load_tables())
+    clean, init, contact = synth.make_sequence(0, T=T_FRAMES)
+    with torch.no_grad():
+        v, _ = rb.gen_body_mesh(torch.from_numpy(clean), ctx.smplx, ctx.vposer)
+    mrec = v[:, ctx.m67].numpy()
+    transl, rot6d, shape, other = rl.split_init(init)
+    for t in (transl, rot6d, other):
+        t.requires_grad_(True)
+    opt = torch.optim.Adam([transl, rot6d, other], lr=0.01)
+    mrec_t, con_t = torch.from_numpy(mrec), torch.from_numpy(contact)
+    times = []
+    for it in range(warm + n_iters):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _, _ = rl.temp_losses(transl, rot6d, other, shape, mrec_t, con_t, ctx, faithful=True)
+        loss.backward()
+        opt.step()
+        if it >= warm:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {'value': len(times) / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '1 sequence x %d frames x %d Adam iterations (after %d warm-up), reference op sequence incl. double '
+                      'SMPL-X/VPoser evaluation, torch %s CPU, %d threads' % (T_FRAMES, len(times), warm, torch.__version__, cores),
+            'ms_per_iter': 1e3 * total / len(times)}
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    res = cpu_reference_rate(max(1, a.steps), warm=max(1, min(a.warmup, 3)))
+    line = {'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': res['ms_per_iter'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference', 'config': workload_config(a, world),
+            'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if a.impl == 'reference':
+        return run_reference_arm(a, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lemo_b200 import _lib, shard
+    _lib.build()
+    import lemo_b200.smplx as smplx
+    from lemo_b200.vposer import VPoserDecoder
+    from lemo_b200.fit import TemporalFitter, load_smooth_prior
+    from oracle import synth            # synthetic inputs only (data generation, not compute)
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    S, T = a.seqs_per_gpu, T_FRAMES
+    my_ids = shard.assign(S * world, world, rank)
+
+    model = synth.make_smplx_model(0)
+    body = smplx.create(model, model_type='smplx', gender='male', ext='npz', num_pca_comps=12, batch_size=T).to(dev)
+    vp = VPoserDecoder(synth.make_vposer_weights(1)).to(dev)
+    enc = load_smooth_prior().to(dev)
+
+    # synthetic sequences: targets = markers of the clean parameters through OUR forward (device), init = perturbed
+    from lemo_b200.utils.utils import gen_body_mesh_v1
+    tables = synth.load_tables()
+    m67 = torch.from_numpy(tables['markers67']).long().to(dev)
+    inits, mrecs, cons = [], [], []
+    for s in my_ids:
+        clean, init, contact = synth.make_sequence(s, T=T)
+        with torch.no_grad():
+            v = gen_body_mesh_v1(torch.from_numpy(clean).to(dev), body, vp)
+        inits.append(torch.from_numpy(init)); mrecs.append(v[:, m67].cpu()); cons.append(torch.from_numpy(contact))
+    pin = lambda ts: torch.stack(ts).contiguous().pin_memory()
+    h_init, h_mrec, h_con = pin(inits), pin(mrecs), pin(cons)
+    d_init, d_mrec, d_con = h_init.to(dev), h_mrec.to(dev), h_con.to(dev)
+
+    fit = TemporalFitter(body, vp, S, T, enc=enc, device=dev, use_cuda_graph=not a.no_graph)
+    for i in range(S):
+        fit.set_sequence(i, d_init[i], d_mrec[i], d_con[i])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput: K iterations, CUDA events, max over ranks
+    fit.run(n_iters=a.warmup)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = fit.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fit.run(n_iters=a.steps)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = fit.kernel_launches() - l0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+
+    # ---------------- end to end through the public API with HOST buffers: H2D inputs + 1 iteration + D2H losses, per step
+    h2d = int(h_init.numel() + h_mrec.numel() + h_con.numel()) * 4
+    h_loss = torch.empty(S, 8).pin_memory()
+    h_par = torch.empty(S, T, 72).pin_memory()
+
+    def e2e_step():
+        di, dm, dc = h_init.to(dev, non_blocking=True), h_mrec.to(dev, non_blocking=True), h_con.to(dev, non_blocking=True)
+        fit.set_sequences(di, dm, dc)
+        fit.run(n_iters=1)
+        p, l = fit.results()
+        h_par.copy_(p, non_blocking=True)
+        h_loss.copy_(l, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    for _ in range(max(3, a.warmup)):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(5, min(a.steps, 30))
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_rate = S * world * e2e_steps / float(e2e_s.item())
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- dominant kernel alone (conv3x3 64->64 of the Enc stack), CUDA events on the launching stream
+    roof = None
+    if rank == 0:
+        from lemo_b200.models.AE_sep import _Net  # noqa: F401
+        net = fit._enc
+        reps = 20
+        st = _lib.cur_stream(dev)
+        _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, 0, 3, st)
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, 0, reps, st)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        k_ms = c0.elapsed_time(c1) / reps
+        W = T - 1 + 16
+        flops = 2.0 * S * 64 * 64 * 9 * 245 * W                      # algorithmic flops of one 64->64 launch over S sequences
+        sm_mhz = (clocks or {}).get('sm_max_mhz') or 1965.0
+        peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12                  # fp32 FMA roof at max SM clock (no tensor cores on this path)
+        roof = {'kernel': 'k_conv3x3<8> (Enc 64->64 conv3x3+LeakyReLU, S=%d)' % S, 'bound': 'fp32', 'achieved': flops / (k_ms * 1e-3) / 1e12,
+                'peak': peak, 'unit': 'TFLOP/s', 'frac': flops / (k_ms * 1e-3) / 1e12 / peak, 'traffic': None, 'kernel_ms': k_ms,
+                'peak_source': 'computed: 148 SMs x 128 FMA/clk x 2 x clocks.max.sm (fp32 CUDA-core roof; MEASURED_PEAKS.json has no fp32 figure)',
+                'share_of_step': 20 * k_ms * 1.0 / (ms_total / a.steps) if ms_total > 0 else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = S * world * a.steps / (ms_total * 1e-3)
+    cpu = None if a.skip_cpu_baseline else cpu_reference_rate(a.cpu_iters)
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(a, world), 'clocks': clocks,
+            'e2e': {'value': e2e_rate, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(h_loss.numel() + h_par.numel()) * 4},
+            'gpu_launches': int(launches), 'roofline': roof,
+            'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

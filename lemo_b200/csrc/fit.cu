@@ -51,6 +51,8 @@ struct Fit {
     Sched* sched = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
+    cudaStream_t gstream = nullptr;          // graphs are captured/replayed on a private stream (the caller may be on the
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // legacy default stream, which cannot be captured) and fork/joined with events
     long long launches = 0, launches_per_iter = 0;
     float* tr() const { return P; }
     float* r6() const { return P + (size_t)B * 3; }
@@ -388,18 +390,27 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
 }
 
 static int fit_run_iters(Fit* f, int n_iters, cudaStream_t st) {
-    if (f->cfg.use_cuda_graph) {
+    if (f->cfg.use_cuda_graph && n_iters > 0) {
+        if (!f->gstream) {
+            LEMO_CUDA(cudaStreamCreateWithFlags(&f->gstream, cudaStreamNonBlocking));
+            LEMO_CUDA(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+            LEMO_CUDA(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
+        }
+        LEMO_CUDA(cudaEventRecord(f->ev_in, st));
+        LEMO_CUDA(cudaStreamWaitEvent(f->gstream, f->ev_in, 0));
         if (!f->gexec) {
-            LEMO_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int r = fit_iteration(f, st);
+            LEMO_CUDA(cudaStreamBeginCapture(f->gstream, cudaStreamCaptureModeThreadLocal));
+            const int r = fit_iteration(f, f->gstream);
             cudaGraph_t g = nullptr;
-            const cudaError_t e = cudaStreamEndCapture(st, &g);
-            if (r) return r;
+            const cudaError_t e = cudaStreamEndCapture(f->gstream, &g);     // always close the capture, even on error
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
             LEMO_CUDA(e);
             f->graph = g;
             LEMO_CUDA(cudaGraphInstantiate(&f->gexec, g, 0));
         }
-        for (int i = 0; i < n_iters; ++i) LEMO_CUDA(cudaGraphLaunch(f->gexec, st));
+        for (int i = 0; i < n_iters; ++i) LEMO_CUDA(cudaGraphLaunch(f->gexec, f->gstream));
+        LEMO_CUDA(cudaEventRecord(f->ev_out, f->gstream));
+        LEMO_CUDA(cudaStreamWaitEvent(st, f->ev_out, 0));
     } else {
         for (int i = 0; i < n_iters; ++i) LEMO_TRY(fit_iteration(f, st));
     }
@@ -473,6 +484,7 @@ int lemo_fit_destroy(LemoFit* h) {
     cudaSetDevice(f->device);
     if (f->gexec) cudaGraphExecDestroy(f->gexec);
     if (f->graph) cudaGraphDestroy(f->graph);
+    if (f->gstream) { cudaStreamDestroy(f->gstream); cudaEventDestroy(f->ev_in); cudaEventDestroy(f->ev_out); }
     float* ps[] = {f->P, f->Gp, f->M1, f->M2, f->betas, f->mrec, f->contact, f->Rg, f->Rb, f->dRg, f->dRb, f->Vr, f->Grows, f->xin, f->gx,
                    f->gv, f->canon, f->stats, f->acc, f->p72};
     for (float* p : ps) cudaFree(p);

@@ -118,12 +118,23 @@ class TemporalFitter(_Fitter):
     """opt_amass_temp.py:329-455 for S sequences at once."""
     MODE = 0
 
-    def set_sequence(self, s, init72, markers_rec, contact):
+    def set_sequence(self, s, init72, markers_rec, contact, sync=True):
         """init72 [T,72] (per-frame stage result), markers_rec [T,67,3] (infilled targets), contact [T,4]."""
         T = self.T
         a, b, c = self._dev(init72, (T, 72)), self._dev(markers_rec, (T, 67, 3)), self._dev(contact, (T, 4))
         _lib.call('lemo_fit_set_sequence', self.handle, s, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.cur_stream(self.device))
-        torch.cuda.current_stream(self.device).synchronize()      # inputs may be freed by the caller after return
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()      # inputs may be freed by the caller after return
+        else:
+            for t in (a, b, c):
+                t.record_stream(torch.cuda.current_stream(self.device))
+
+    def set_sequences(self, init72, markers_rec, contact):
+        """All S sequences at once from [S,T,72], [S,T,67,3], [S,T,4] (host or device); no host synchronisation."""
+        S, T = self.S, self.T
+        a, b, c = self._dev(init72, (S, T, 72)), self._dev(markers_rec, (S, T, 67, 3)), self._dev(contact, (S, T, 4))
+        for s in range(S):
+            self.set_sequence(s, a[s], b[s], c[s], sync=False)
 
     def run(self, n_iters=100, lr0=0.01, lr1=0.005, lr_switch=60):
         """total_steps=100, lr .01 -> .005 after step 60 (opt_amass_temp.py:343-352).  Asynchronous."""

@@ -32,7 +32,7 @@ def test_enc_backward_tolerance_budget():
     gz = torch.from_numpy(np.random.default_rng(10).standard_normal((2, 64, 37, 53)).astype(np.float32))
     res = {}
     for sd, dt in ((sd32, torch.float32), (sd64, torch.float64)):
-        xx = x.to(dt).requires_grad_(True)
+        xx = x.detach().clone().to(dt).requires_grad_(True)
         (rp.enc_forward(xx, sd) * gz.to(dt)).sum().backward()
         res[dt] = xx.grad
     xg = x.to(DEV).requires_grad_(True)
@@ -109,7 +109,7 @@ def test_rotation_ops_and_6d_adjoint():
     xg = x.to(DEV).requires_grad_(True)
     R = U.ContinousRotReprDecoder.decode(xg)
     (R * gR.to(DEV)).sum().backward()
-    assert rel(R, rb.gram_schmidt_6d(x)) < 2e-6
+    assert rel(R, rb.gram_schmidt_6d(x)) < 5e-6
     assert rel(xg.grad, x64.grad) < 1e-4
     p75 = torch.from_numpy(g.standard_normal((9, 75)).astype(np.float32))
     assert rel(U.convert_to_3D_rot(p75.to(DEV)), rb.convert_to_3D_rot(p75)) < 2e-5
