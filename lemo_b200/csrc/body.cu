@@ -385,6 +385,8 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
                                                   float* __restrict__ dR, float* __restrict__ dbetas, float* __restrict__ dexpr) {
     __shared__ float sdG[NJ][12];     // dL/dG  (3x4)
     __shared__ float sdJ[NJ][3];      // dL/dJrest
+    __shared__ float sC[NJ][15];      // per-joint contribution to its parent: dG (12) + dJrest[parent] (3)
+    __shared__ int spar[NJ];
     const int b = blockIdx.x, j = threadIdx.x;
     float r[9], gl[12], Jr[3];
     int par = -1, dep = 0;
@@ -403,7 +405,10 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
         // dJ += -G.R^T dAt
         for (int c = 0; c < 3; ++c) sdJ[j][c] = -(gl[c] * dAt[0] + gl[4 + c] * dAt[1] + gl[8 + c] * dAt[2]);
     }
+    if (j < NJ) spar[j] = par;
     __syncthreads();
+    // children -> parent accumulation in a FIXED order (no shared-memory atomics): results are bitwise reproducible,
+    // which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same parameters).
     for (int lev = max_depth; lev >= 1; --lev) {
         if (j < NJ && dep == lev) {
             const float* gp = G + ((size_t)b * NJ + par) * 12;        // parent's global transform
@@ -420,10 +425,18 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
             const float* dx = dX + (size_t)b * XK + (j - 1) * 9;
             for (int k = 0; k < 9; ++k) o[k] = dr[k] + dx[k];
             for (int i = 0; i < 3; ++i) {
-                for (int c = 0; c < 3; ++c) atomicAdd(&sdG[par][i * 4 + c], dpr[i * 3 + c] + dGt[i] * t[c]);
-                atomicAdd(&sdG[par][i * 4 + 3], dGt[i]);
-                atomicAdd(&sdJ[j][i], dt[i]);
-                atomicAdd(&sdJ[par][i], -dt[i]);
+                for (int c = 0; c < 3; ++c) sC[j][i * 4 + c] = dpr[i * 3 + c] + dGt[i] * t[c];
+                sC[j][i * 4 + 3] = dGt[i];
+                sC[j][12 + i] = -dt[i];
+                sdJ[j][i] += dt[i];
+            }
+        }
+        __syncthreads();
+        if (j < NJ && dep == lev - 1) {
+            for (int c = j + 1; c < NJ; ++c) {
+                if (spar[c] != j) continue;
+                for (int k = 0; k < 12; ++k) sdG[j][k] += sC[c][k];
+                for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
             }
         }
         __syncthreads();

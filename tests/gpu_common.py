@@ -54,3 +54,10 @@ def rel(a, b):
     a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
     b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def rel_q(a, b, q=0.99):
+    """q-quantile of |a-b| / max|b| (robust to isolated LeakyReLU-kink sign flips, see test_gpu_priors.py)."""
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    return float(np.quantile(np.abs(a - b), q) / max(np.abs(b).max(), 1e-30))

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import synth, ref_body as rb, ref_priors as rp
-from gpu_common import DEV, vposer_module, vposer_w, enc_module, rel
+from gpu_common import DEV, vposer_module, vposer_w, enc_module, rel, rel_q
 
 pytestmark = pytest.mark.gpu
 
@@ -22,7 +22,11 @@ def test_enc_forward_backward_golden(golden):
         else:
             assert rel(z[:, ::8, ::7, ::9], golden['enc_full_z_sub']) < 1e-4
         assert abs(float(loss) - float(golden['enc_%s_loss' % tag])) < 1e-4 * float(golden['enc_%s_loss' % tag])
-        assert rel(x.grad, golden['enc_%s_gx' % tag]) < 1e-3, rel(x.grad, golden['enc_%s_gx' % tag])
+        # The input gradient of a LeakyReLU stack is DISCONTINUOUS where a pre-activation crosses 0: an fp32 summation-order
+        # difference of 1 ulp on one of the ~1e6 activations flips 1 -> 0.2 there and perturbs a (2L+1)^2 patch of the gradient
+        # (observed: one such patch, 1.6e-3 of max|g|).  So: tight bound on the 99% quantile, loose bound on the maximum.
+        assert rel_q(x.grad, golden['enc_%s_gx' % tag]) < 2e-5, rel_q(x.grad, golden['enc_%s_gx' % tag])
+        assert rel(x.grad, golden['enc_%s_gx' % tag]) < 2e-2, rel(x.grad, golden['enc_%s_gx' % tag])
 
 
 def test_enc_backward_tolerance_budget():
@@ -37,8 +41,9 @@ def test_enc_backward_tolerance_budget():
         res[dt] = xx.grad
     xg = x.to(DEV).requires_grad_(True)
     (enc_module()(xg)[0] * gz.to(DEV)).sum().backward()
-    e32, e = rel(res[torch.float32], res[torch.float64]), rel(xg.grad, res[torch.float64])
-    assert e < max(4 * e32, 1e-5), (e, e32)
+    e32, e = rel_q(res[torch.float32], res[torch.float64]), rel_q(xg.grad, res[torch.float64])
+    assert e < max(4 * e32, 5e-6), (e, e32)                       # quantile: see the LeakyReLU-kink note above
+    assert rel(xg.grad, res[torch.float64]) < 2e-2
 
 
 def test_vposer_decode_and_adjoint():
