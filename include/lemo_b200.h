@@ -144,6 +144,13 @@ int lemo_ae_forward(LemoConvNet* net, const float* x, int32_t N, float* rec, flo
 /* weight gradients of the last lemo_ae_forward: d_rec [N,1,H,W] -> d_weights (same order as weights) */
 int lemo_ae_backward_weights(LemoConvNet* net, const float* d_rec, int32_t N, float* d_weights, void* stream);
 
+/* one step of the self-supervised fine-tune (opt_amass_perframe.py:152-173): AE forward on x [N,C,H,W] (already masked and
+ * reflect-padded), loss = mean |rec[:,0] - x[:,0]| over the rows with row_mask[y] != 0 (row_mask [H] floats, n_rows_selected
+ * of them set), weight-gradient backward, Adam(lr, betas .9/.999, eps 1e-8) on the handle's weights.  t = 1-based step (t == 1
+ * resets the moments).  loss_out: device float, nullable. */
+int lemo_ae_finetune_step(LemoConvNet* net, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr,
+                          int32_t t, float* loss_out, void* stream);
+
 /* ---------------------------------------------------------------- Chamfer (temp_prox/dist_chamfer.py) --- */
 /* xyz1 [B,n,3]; xyz2 [B,m,3] with xyz2_batch_stride floats between batches (0 = one shared scene).
  * dist = squared L2 to the nearest neighbour (first minimum wins), idx int32.  (dist_chamfer.py:10-28) */

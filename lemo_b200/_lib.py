@@ -104,6 +104,7 @@ SIGNATURES = {
     'lemo_convnet_profile_layer': (C.c_int, [_P, _I, _I, _I, _I, _P]),
     'lemo_ae_forward': (C.c_int, [_P, _P, _I, _P, _P, _P]),
     'lemo_ae_backward_weights': (C.c_int, [_P, _P, _I, _P, _P]),
+    'lemo_ae_finetune_step': (C.c_int, [_P, _P, _P, _I, _I, _D, _I, _P, _P]),
     'lemo_chamfer_forward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P]),
     'lemo_chamfer_backward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     'lemo_adam_step': (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _P]),
