@@ -138,6 +138,7 @@ int lemo_enc_backward_input(LemoConvNet* net, const float* dz, int32_t N, float*
 /* measurement hook: relaunch ONE conv layer of an Enc handle `reps` times on its resident activations
  * (forward: layer l of 0..9; backward: the input-gradient conv of layer l >= 1) so bench.py can time the
  * dominant kernel alone with CUDA events. */
+int lemo_enc_debug_backward(LemoConvNet* net, const float* dz, int32_t N, int32_t stop_layer, float* out, void* stream);
 int lemo_convnet_profile_layer(LemoConvNet* net, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream);
 /* AE.forward: x [N,C,H,W] -> rec [N,1,H,W], z [N,256,h5,w5] (nullable)      (opt_amass_perframe.py:160) */
 int lemo_ae_forward(LemoConvNet* net, const float* x, int32_t N, float* rec, float* z, void* stream);

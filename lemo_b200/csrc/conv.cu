@@ -393,6 +393,23 @@ int lemo_enc_forward(LemoConvNet* h, const float* x, int32_t N, float* z, void* 
     LEMO_TRY(unpack_planes(n->act[10], z, N * 64, n->geom[0], st));
     return 0;
 }
+// debug: dpre of layers[stop_layer] (gradient w.r.t. its pre-activation), dense [N,Cout,H,W]
+int lemo_enc_debug_backward(LemoConvNet* h, const float* dz, int32_t N, int32_t stop_layer, float* out, void* stream) {
+    LEMO_CHECK(h && h->n->kind == 0 && dz && out && stop_layer >= 0 && stop_layer <= 9, "bad arguments");
+    ConvNet* n = h->n;
+    cudaStream_t st = (cudaStream_t)stream;
+    const PlaneGeom& g = n->geom[0];
+    const long long total = (long long)N * 64 * g.H * g.W;
+    k_pack_mask<<<cdiv(total, 256), 256, 0, st>>>(dz, n->act[10], n->grad[0], total, g.H, g.W, g.Wp, g.PS);
+    float* cur = n->grad[0];
+    float* nxt = n->grad[1];
+    for (int l = 9; l > stop_layer; --l) {
+        const ConvLayer& L = n->layers[l];
+        LEMO_TRY(conv3x3_launch(cur, L.wk_b, nullptr, n->act[l], nxt, N, L.Cout, L.Cin, g, EPI_MASK, st));
+        std::swap(cur, nxt);
+    }
+    return unpack_planes(cur, out, N * n->layers[stop_layer].Cout, g, st);
+}
 int lemo_convnet_profile_layer(LemoConvNet* h, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream) {
     LEMO_CHECK(h && h->n->kind == 0 && layer >= 0 && layer < 10 && N > 0 && N <= h->n->maxN, "bad arguments");
     ConvNet* n = h->n;

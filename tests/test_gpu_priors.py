@@ -9,6 +9,15 @@ from gpu_common import DEV, vposer_module, vposer_w, enc_module, rel, rel_q
 pytestmark = pytest.mark.gpu
 
 
+# NOTE on LeakyReLU kinks.  The input gradient of a LeakyReLU stack is discontinuous where a pre-activation crosses 0.  With the
+# shipped Enc weights the pre-activations are dense around 0 (about one per layer and image lies within 3e-7 of it), so a 1-ulp
+# summation-order difference flips 1 <-> 0.2 somewhere in nearly every evaluation and perturbs a (2L+1)^2 patch of dL/dx (measured
+# on B200: one element, layer 6 channel 57, pre = 2.8e-8, our dpre = 0.2 x the oracle's).  Any two fp32 implementations of the
+# reference differ this way (cuDNN vs CPU included), so END-TO-END gradient parity is asserted on the median and bounded on the max,
+# and the arithmetic of the backward pass is asserted LAYER BY LAYER where no kink can interfere.
+_ENC_KEYS = ['enc_blc%d.main.%d' % (b, li) for b in range(1, 6) for li in (0, 2)]
+
+
 def test_enc_forward_backward_golden(golden):
     """Enc with the shipped real weights vs the REAL reference's outputs (tests/golden)."""
     enc = enc_module()
@@ -22,28 +31,45 @@ def test_enc_forward_backward_golden(golden):
         else:
             assert rel(z[:, ::8, ::7, ::9], golden['enc_full_z_sub']) < 1e-4
         assert abs(float(loss) - float(golden['enc_%s_loss' % tag])) < 1e-4 * float(golden['enc_%s_loss' % tag])
-        # The input gradient of a LeakyReLU stack is DISCONTINUOUS where a pre-activation crosses 0: an fp32 summation-order
-        # difference of 1 ulp on one of the ~1e6 activations flips 1 -> 0.2 there and perturbs a (2L+1)^2 patch of the gradient
-        # (observed: one such patch, 1.6e-3 of max|g|).  So: tight bound on the 99% quantile, loose bound on the maximum.
-        assert rel_q(x.grad, golden['enc_%s_gx' % tag]) < 2e-5, rel_q(x.grad, golden['enc_%s_gx' % tag])
-        assert rel(x.grad, golden['enc_%s_gx' % tag]) < 2e-2, rel(x.grad, golden['enc_%s_gx' % tag])
+        assert rel_q(x.grad, golden['enc_%s_gx' % tag], 0.5) < 1e-5          # median: untouched by kink patches
+        assert rel(x.grad, golden['enc_%s_gx' % tag]) < 5e-2               # kink patches stay bounded
 
 
-def test_enc_backward_tolerance_budget():
-    sd32 = {k: torch.from_numpy(v) for k, v in synth.load_enc_weights().items()}
-    sd64 = {k: v.double() for k, v in sd32.items()}
-    x = torch.from_numpy((0.5 * np.random.default_rng(9).standard_normal((2, 1, 37, 53))).astype(np.float32))
-    gz = torch.from_numpy(np.random.default_rng(10).standard_normal((2, 64, 37, 53)).astype(np.float32))
-    res = {}
-    for sd, dt in ((sd32, torch.float32), (sd64, torch.float64)):
-        xx = x.detach().clone().to(dt).requires_grad_(True)
-        (rp.enc_forward(xx, sd) * gz.to(dt)).sum().backward()
-        res[dt] = xx.grad
+def test_enc_backward_layerwise_exact():
+    """Every backward layer against fp64 arithmetic on ITS OWN input (our dpre of the layer above), masks from the oracle's
+    pre-activations, excluding only the elements whose own pre-activation is within 1e-6 of the kink."""
+    import torch.nn.functional as F
+    from lemo_b200 import _lib
+    sd = {k: torch.from_numpy(v).double() for k, v in synth.load_enc_weights().items()}
+    N, H, W = 2, 37, 53
+    x = torch.from_numpy((0.5 * np.random.default_rng(9).standard_normal((N, 1, H, W))).astype(np.float32))
+    gz = torch.from_numpy(np.random.default_rng(10).standard_normal((N, 64, H, W)).astype(np.float32))
+    pres, h = [], x.double()
+    for k in _ENC_KEYS:
+        pres.append(F.conv2d(h, sd[k + '.weight'], sd[k + '.bias'], padding=1))
+        h = F.leaky_relu(pres[-1], 0.2)
+    enc = enc_module()
     xg = x.to(DEV).requires_grad_(True)
-    (enc_module()(xg)[0] * gz.to(DEV)).sum().backward()
-    e32, e = rel_q(res[torch.float32], res[torch.float64]), rel_q(xg.grad, res[torch.float64])
-    assert e < max(4 * e32, 5e-6), (e, e32)                       # quantile: see the LeakyReLU-kink note above
-    assert rel(xg.grad, res[torch.float64]) < 2e-2
+    z = enc(xg)[0]
+    assert rel(z, h) < 1e-5
+    net = enc.net(torch.device(DEV), N, H, W)
+    gzd = gz.to(DEV).contiguous()
+    above = None
+    for l in range(9, -1, -1):
+        C = pres[l].shape[1]
+        mine = torch.empty(N, C, H, W, device=DEV)
+        _lib.call('lemo_enc_debug_backward', net.handle, _lib.ptr(gzd), N, l, _lib.ptr(mine), _lib.cur_stream())
+        mine = mine.cpu().double()
+        g_act = gz.double() if l == 9 else F.conv_transpose2d(above, sd[_ENC_KEYS[l + 1] + '.weight'], padding=1)
+        want = g_act * torch.where(pres[l] > 0, 1.0, 0.2)
+        safe = pres[l].abs() > 1e-6
+        err = ((mine - want).abs() * safe).max() / want.abs().max()
+        assert float(err) < 1e-5, (l, float(err))
+        assert float(safe.float().mean()) > 0.999
+        above = mine
+    (z * gzd).sum().backward()
+    want_dx = F.conv_transpose2d(above, sd[_ENC_KEYS[0] + '.weight'], padding=1)
+    assert rel(xg.grad, want_dx) < 1e-5
 
 
 def test_vposer_decode_and_adjoint():
