@@ -16,6 +16,19 @@ constexpr int CT = 8;     // input channels staged per smem pass
 // lane g owns pixels 4g..4g+3 and 128+4g..128+4g+3  -> 8 oc x 8 px register tile, weights are warp-uniform
 // (broadcast LDS.128), inputs are conflict-free LDS.128 + LDS.64 per (ic,ky).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = valid ? 4 : 0;                         // src-size 0 => zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(n));
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ in, const float* __restrict__ wk,
                                                      const float* __restrict__ bias, const float* __restrict__ aux,
@@ -23,8 +36,7 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
                                                      int SW, int epi) {
     constexpr int OCB = NW * 8, NT = NW * 32;
     extern __shared__ __align__(16) float smem[];
-    float* s_in = smem;                 // [CT][SW]
-    float* s_w = smem + CT * SW;        // [CT][9][OCB]
+    const int stage_floats = CT * SW + CT * 9 * OCB;    // one pipeline stage: input halo tile [CT][SW] + weights [CT][9][OCB]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = blockIdx.z, ocb0 = blockIdx.y * OCB;
     const int q0 = Wp + blockIdx.x * TP;
@@ -36,20 +48,38 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[o][i] = 0.f;
 
-    for (int ic0 = 0; ic0 < Cin; ic0 += CT) {
+    // cp.async double buffering: the global->shared copy of channel block k+1 overlaps the FMAs of block k
+    // (ncu on the single-buffered version: long_scoreboard was the top stall, fma pipe 42 % active)
+    auto issue_stage = [&](int ic0, float* st) {
+        float* s_in = st;
+        float* s_w = st + CT * SW;
         const int nic = min(CT, Cin - ic0);
         for (int ic = 0; ic < nic; ++ic) {
             const float* src = in_n + (size_t)(ic0 + ic) * PS;
             for (int e = tid; e < SW; e += NT) {
                 const int q = q0 - Wp - 1 + e;
-                s_in[ic * SW + e] = (q >= 0 && q < PS) ? __ldg(src + q) : 0.f;
+                const bool ok = (q >= 0 && q < PS);
+                cp_async4(s_in + ic * SW + e, ok ? src + q : src, ok);
             }
         }
-        for (int idx = tid; idx < nic * 9 * OCB; idx += NT) {
-            const int o = idx % OCB, r = idx / OCB;
-            s_w[idx] = __ldg(wk + (size_t)(ic0 * 9 + r) * Cout + ocb0 + o);
+        const int nw4 = nic * 9 * OCB / 4;
+        for (int idx = tid; idx < nw4; idx += NT) {
+            const int o4 = idx % (OCB / 4), r = idx / (OCB / 4);
+            cp_async16(s_w + r * OCB + o4 * 4, wk + (size_t)(ic0 * 9 + r) * Cout + ocb0 + o4 * 4);
         }
+        cp_async_commit();
+    };
+
+    const int ntiles = (Cin + CT - 1) / CT;
+    issue_stage(0, smem);
+    for (int it = 0; it < ntiles; ++it) {
+        float* st = smem + (it & 1) * stage_floats;
+        if (it + 1 < ntiles) { issue_stage((it + 1) * CT, smem + ((it + 1) & 1) * stage_floats); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
+        const float* s_in = st;
+        const float* s_w = st + CT * SW;
+        const int nic = min(CT, Cin - it * CT);
         for (int ic = 0; ic < nic; ++ic) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -151,8 +181,8 @@ template <int NW>
 static int conv_main_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out, int N, int Cin,
                             int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st) {
     const int SW = (TP + 2 * g.Wp + 2 + 3) / 4 * 4;
-    const size_t smem = (size_t)(CT * SW + CT * 9 * NW * 8) * sizeof(float);
-    static size_t configured = 0;
+    const size_t smem = 2 * (size_t)(CT * SW + CT * 9 * NW * 8) * sizeof(float);      // two pipeline stages
+    static size_t configured = 0;             // one process per GPU: a per-process cache is enough
     if (smem > configured) {
         LEMO_CUDA(cudaFuncSetAttribute(k_conv3x3<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
