@@ -97,6 +97,9 @@ int lemo_smplx_forward(LemoBody* body, const LemoPoseC* pose, int32_t B,
 int lemo_smplx_backward(LemoBody* body, const LemoPoseC* pose, int32_t B,
                         const float* d_verts, const float* d_joints, const LemoPoseGradC* grads, void* stream);
 
+/* A/B switch for the blend-shape GEMM: 1 = tcgen05 TF32 kernel (default), 0 = CUDA-core fp32 GEMM.  Debug/measurement only. */
+int lemo_debug_set_blend_tc(int32_t on);
+
 /* replaces verts[:, ids, :] gathers     (opt_amass_temp.py:359,366,416-425; bit-exact integer indexing) */
 int lemo_gather_rows(const float* src, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* out, void* stream);
 int lemo_scatter_rows_add(const float* g_rows, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* g_dense, void* stream);

@@ -18,6 +18,7 @@
 #include <vector>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 
 namespace lemo {
 
@@ -45,6 +46,24 @@ static int compute_depth(const int* parents, int* depth, int* max_depth) {
         depth[j] = depth[parents[j]] + 1;
         if (depth[j] > *max_depth) *max_depth = depth[j];
     }
+    return 0;
+}
+
+static int g_blend_tc = -1;
+bool blend_tc_enabled() {
+    if (g_blend_tc < 0) { const char* e = getenv("LEMO_BLEND"); g_blend_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
+    return g_blend_tc == 1;
+}
+void blend_tc_set(int on) { g_blend_tc = on ? 1 : 0; }
+
+// K-major transposed copy of Wt + its TMA descriptor for the tensor-core blend GEMM
+static int model_setup_tc(Model* m) {
+    m->has_tc = false;
+    LEMO_TRY(dev_alloc(&m->WtT, (size_t)3 * m->V * XK));
+    LEMO_TRY(blend_tc_transpose(m->Wt, m->WtT, 3 * m->V));
+    LEMO_CUDA(cudaDeviceSynchronize());
+    LEMO_TRY(blend_tc_map_w(m->WtT, 3 * m->V, m->map_w));
+    m->has_tc = true;
     return 0;
 }
 
@@ -102,6 +121,7 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
         LEMO_TRY(dev_upload(&m->J_template, jt.data(), jt.size()));
         LEMO_TRY(dev_upload(&m->J_dirs, jd.data(), jd.size()));
     }
+    LEMO_TRY(model_setup_tc(m));
     LEMO_TRY(dev_upload(&m->parents, m->h_parents, NJ));
     LEMO_TRY(dev_upload(&m->depth, m->h_depth, NJ));
     LEMO_TRY(dev_upload(&m->hand_l, d->h_hand_comp_l, (size_t)m->npc * 45));
@@ -151,6 +171,8 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
     LEMO_CUDA(cudaGetLastError());
     LEMO_CUDA(cudaDeviceSynchronize());
     cudaFree(rows_dev);
+    s->WtT = nullptr;
+    LEMO_TRY(model_setup_tc(s));
     *out = s;      // shares J_template/J_dirs/parents/hand/pose_mean pointers with the parent model
     return 0;
 }
@@ -158,7 +180,7 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
 void model_free(Model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->w_jm);
+    cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->WtT); cudaFree(m->w_jm);
     if (!m->is_sub) {
         cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth);
         cudaFree(m->hand_l); cudaFree(m->hand_r); cudaFree(m->pose_mean);
@@ -176,6 +198,8 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
     LEMO_TRY(dev_alloc(&c->full_pose, B * 165));
     LEMO_TRY(dev_alloc(&c->R, B * NJ * 9));
     LEMO_TRY(dev_alloc(&c->X, B * XK));
+    LEMO_TRY(dev_alloc(&c->X2, B * 2 * XK));
+    LEMO_TRY(blend_tc_map_x(c->X2, maxB, c->map_x));
     LEMO_TRY(dev_alloc(&c->G, B * NJ * 12));
     LEMO_TRY(dev_alloc(&c->A, B * NJ * 12));
     LEMO_TRY(dev_alloc(&c->Jrest, B * NJ * 3));
@@ -198,7 +222,7 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
 void bodyctx_free(BodyCtx* c) {
     if (!c) return;
     cudaSetDevice(c->m->device);
-    float* ptrs[] = {c->full_pose, c->R, c->X, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->DT, c->dA, c->dX, c->dR, c->dJp, c->dtr};
+    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->DT, c->dA, c->dX, c->dR, c->dJp, c->dtr};
     for (float* p : ptrs) cudaFree(p);
     delete c;
 }
@@ -312,8 +336,8 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
                                                   const float* __restrict__ expr, const float* __restrict__ J_template,
                                                   const float* __restrict__ J_dirs, const int* __restrict__ parents,
                                                   const int* __restrict__ depth, int max_depth,
-                                                  float* __restrict__ X, float* __restrict__ G, float* __restrict__ A,
-                                                  float* __restrict__ Jrest, float* __restrict__ Jposed) {
+                                                  float* __restrict__ X, float* __restrict__ X2, float* __restrict__ G,
+                                                  float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed) {
     __shared__ float sG[NJ][12];
     __shared__ float sJ[NJ][3];
     __shared__ float sbeta[NBETA];
@@ -362,6 +386,14 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
             for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
         }
         __syncthreads();
+    }
+    // TF32 split of the row of X for the tensor-core blend GEMM: Xhi keeps the 10 explicit mantissa bits TF32 has, Xlo the rest
+    __syncthreads();
+    for (int k = threadIdx.x; k < XK; k += blockDim.x) {
+        const float x = X[(size_t)b * XK + k];
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        X2[(size_t)b * 2 * XK + k] = hi;
+        X2[(size_t)b * 2 * XK + XK + k] = x - hi;
     }
     if (j < NJ) {
         const float* g = sG[j];
@@ -615,7 +647,7 @@ int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st) {
     const Model* m = c->m;
     k_pose_to_rot<<<cdiv(B * NJ, 128), 128, 0, st>>>(make_posek(m, in), B, c->full_pose, c->R);
     k_chain_fwd<<<B, 64, 0, st>>>(c->R, in.betas, in.betas_stride, in.expression, m->J_template, m->J_dirs, m->parents, m->depth,
-                                   m->max_depth, c->X, c->G, c->A, c->Jrest, c->Jposed);
+                                   m->max_depth, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -624,9 +656,13 @@ int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, fl
     LEMO_CHECK(c && ps && verts && B > 0 && B <= c->maxB, "bad arguments");
     const Model* m = c->m;
     const int V = m->V;
-    // VP[B,3V] = X[B,512] . Wt[512,3V]
-    GemmP g = gemm_rowmajor(ps->X, m->Wt, c->VP, B, 3 * V, XK, false);
-    LEMO_TRY(gemm_launch(g, st));
+    // VP[B,3V] = X[B,512] . Wt[512,3V]: tcgen05 TF32 GEMM (blend_tc.cu); LEMO_BLEND=simt selects the CUDA-core GEMM (debug A/B)
+    if (m->has_tc && blend_tc_enabled()) {
+        LEMO_TRY(blend_tc_launch(ps->map_x, m->map_w, c->VP, B, 3 * V, st));
+    } else {
+        GemmP g = gemm_rowmajor(ps->X, m->Wt, c->VP, B, 3 * V, XK, false);
+        LEMO_TRY(gemm_launch(g, st));
+    }
     k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
     if (joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");

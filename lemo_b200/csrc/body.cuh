@@ -15,6 +15,9 @@ struct Model {
     bool is_sub = false;
     float* v_template = nullptr;   // [V,3]
     float* Wt = nullptr;           // [512, 3V]  rows 0..485 posedirs, 486..505 shapedirs^T, 506..511 zero
+    float* WtT = nullptr;          // [3V, 512]  K-major copy for the tcgen05 blend GEMM (blend_tc.cu)
+    alignas(64) unsigned char map_w[128];   // CUtensorMap over WtT
+    bool has_tc = false;
     float* w_jm = nullptr;         // [55, V]    skinning weights, joint-major (lbs_weights^T)
     float* J_template = nullptr;   // [55,3]     J_regressor . v_template
     float* J_dirs = nullptr;       // [55,3,20]  J_regressor . shapedirs
@@ -69,6 +72,8 @@ struct BodyCtx {
     float* full_pose = nullptr;  // [B,165]
     float* R = nullptr;          // [B,55,9]
     float* X = nullptr;          // [B,512]
+    float* X2 = nullptr;         // [B,1024]  TF32 split of X: [Xhi | Xlo]  (A operand of the tcgen05 blend GEMM)
+    alignas(64) unsigned char map_x[128];   // CUtensorMap over X2
     float* G = nullptr;          // [B,55,12]
     float* A = nullptr;          // [B,55,12]
     float* Jrest = nullptr;      // [B,55,3]
@@ -101,6 +106,14 @@ int body_skin_forward(BodyCtx* c, const BodyCtx* pose_src, const PoseIn& in, int
 int body_grad_begin(BodyCtx* pose_src, int B, cudaStream_t st);
 int body_skin_backward(BodyCtx* c, BodyCtx* pose_src, int B, const float* d_verts, const float* d_joints, cudaStream_t st);
 int body_pose_backward(BodyCtx* c, const PoseIn& in, int B, const PoseGrad& g, cudaStream_t st);
+
+// tcgen05 blend GEMM (blend_tc.cu)
+int blend_tc_map_x(const float* X2, int maxB, void* map_x);
+int blend_tc_map_w(const float* WtT, int N, void* map_w);
+int blend_tc_transpose(const float* Wt, float* WtT, int N);
+int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st);
+bool blend_tc_enabled();
+void blend_tc_set(int on);
 
 int gather_rows(const float* src, const int* idx_dev, int B, int V, int n, float* out, cudaStream_t st);
 int scatter_rows_add(const float* g_rows, const int* idx_dev, int B, int V, int n, float* g_dense, cudaStream_t st);
