@@ -102,6 +102,7 @@ SIGNATURES = {
     'lemo_convnet_num_weights': (_L, [_P]),
     'lemo_enc_forward': (C.c_int, [_P, _P, _I, _P, _P]),
     'lemo_enc_backward_input': (C.c_int, [_P, _P, _I, _P, _P]),
+    'lemo_debug_set_conv_tc': (C.c_int, [_I]),
     'lemo_enc_debug_backward': (C.c_int, [_P, _P, _I, _I, _P, _P]),
     'lemo_convnet_profile_layer': (C.c_int, [_P, _I, _I, _I, _I, _P]),
     'lemo_ae_forward': (C.c_int, [_P, _P, _I, _P, _P, _P]),

@@ -1,7 +1,7 @@
 // Blend-shape contraction on the 5th-generation tensor cores:  VP[B, 3V] = X[B,512] . Wt[512,3V]
 // (shape + pose blend shapes of SMPL-X in one GEMM, reference lbs.py:81,94-99).  This is the ONE place the
 // north star puts tensor cores: tcgen05.mma kind::tf32, fp32 accumulators in TMEM, both operands staged by TMA
-// (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage mbarrier pipeline.
+// (cp.async.bulk.tensor, 128-byte swizzle) through a 3-stage mbarrier pipeline.
 //
 //   CTA tile   128 (frames) x 224 (vertex coordinates), K = 512 in 16 blocks of 32 floats (= one 128 B swizzle row), 3 stages
 //   grid       ceil(3V/224) x ceil(B/128)   -> 141 CTAs for the full mesh: one wave of the 148 SMs
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint64_t* bars = (uint64_t*)(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-    // bars[0..3] full, bars[4..7] empty, bars[8] tmem_full, then the TMEM base address slot
+    // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full, then the TMEM base address slot
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
@@ -214,7 +214,14 @@ int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int 
     return 0;
 }
 
-// WtT[c][p] = Wt[p][c]
+// WtT[c][p] = rn_tf32(Wt[p][c]): the model constant is rounded to TF32 ONCE, to nearest, at model-create time.  The tensor core
+// would otherwise truncate it on every MMA (a biased error: measured 5.5e-5 of max|v| on the full mesh); pre-rounded values
+// convert exactly, so the remaining error is unbiased and averages out over the 506 terms of the contraction.
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __global__ void k_transpose_wt(const float* __restrict__ Wt, float* __restrict__ WtT, int N) {
     __shared__ float t[32][33];
     const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
@@ -225,7 +232,7 @@ __global__ void k_transpose_wt(const float* __restrict__ Wt, float* __restrict__
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i;
-        if (c < N) WtT[(size_t)c * XK + p0 + threadIdx.x] = t[threadIdx.x][i];
+        if (c < N) WtT[(size_t)c * XK + p0 + threadIdx.x] = rn_tf32(t[threadIdx.x][i]);
     }
 }
 int blend_tc_transpose(const float* Wt, float* WtT, int N) {

@@ -276,6 +276,7 @@ int convnet_refresh_weights(ConvNet* n, cudaStream_t st) {
         k_prep_weights<<<cdiv(tot, 256), 256, 0, st>>>(n->w_flat + L.w_off, L.Cin, L.Cout, L.transposed ? 1 : 0, L.wk_f, L.wk_b);
     }
     LEMO_CUDA(cudaGetLastError());
+    if (n->tc) LEMO_TRY(enc_tc_refresh_weights(n, st));
     return 0;
 }
 
@@ -321,6 +322,7 @@ int convnet_create(int kind, int in_ch, const float* h_weights, long long n_weig
         LEMO_TRY(dalloc(&n->grad[0], (size_t)maxN * 64 * g.PS));
         LEMO_TRY(dalloc(&n->grad[1], (size_t)maxN * 64 * g.PS));
     }
+    if (in_ch == 1) LEMO_TRY(enc_tc_create(n));          // tensor-core path (conv_tc.cu); LEMO_CONV=simt keeps it idle
     LEMO_CUDA(cudaDeviceSynchronize());
     *out = n;
     return 0;
@@ -329,6 +331,7 @@ int convnet_create(int kind, int in_ch, const float* h_weights, long long n_weig
 void convnet_free(ConvNet* n) {
     if (!n) return;
     cudaSetDevice(n->device);
+    if (n->tc) enc_tc_free(n);
     cudaFree(n->w_flat); cudaFree(n->d_wflat);
     for (auto& L : n->layers) { cudaFree(L.wk_f); cudaFree(L.wk_b); }
     for (auto p : n->act) cudaFree(p);
@@ -341,6 +344,7 @@ void convnet_free(ConvNet* n) {
 
 int enc_forward_planes(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
     LEMO_CHECK(n && n->kind == 0 && N > 0 && N <= n->maxN, "bad Enc handle / batch exceeds handle size");
+    if (enc_uses_tc(n)) return enc_tc_forward(n, x_planes, N, st);
     const PlaneGeom& g = n->geom[0];
     const float* cur = x_planes;
     for (int l = 0; l < 10; ++l) {
@@ -354,6 +358,7 @@ int enc_forward_planes(ConvNet* n, const float* x_planes, int N, cudaStream_t st
 
 int enc_backward_planes(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
     LEMO_CHECK(n && n->kind == 0 && n->with_backward && N > 0 && N <= n->maxN, "Enc handle has no backward buffers");
+    if (enc_uses_tc(n)) return enc_tc_backward(n, N, dx_planes, st);
     const PlaneGeom& g = n->geom[0];
     float* cur = n->grad[0];
     float* nxt = n->grad[1];
@@ -420,12 +425,14 @@ int lemo_enc_forward(LemoConvNet* h, const float* x, int32_t N, float* z, void* 
     LEMO_CHECK(N > 0 && N <= n->maxN, "batch exceeds handle size");
     LEMO_TRY(pack_planes(x, n->act[0], N * n->in_ch, n->geom[0], st));
     LEMO_TRY(enc_forward_planes(n, n->act[0], N, st));
+    if (enc_uses_tc(n)) return enc_tc_unpack_z(n, N, z, st);
     LEMO_TRY(unpack_planes(n->act[10], z, N * 64, n->geom[0], st));
     return 0;
 }
 // debug: dpre of layers[stop_layer] (gradient w.r.t. its pre-activation), dense [N,Cout,H,W]
 int lemo_enc_debug_backward(LemoConvNet* h, const float* dz, int32_t N, int32_t stop_layer, float* out, void* stream) {
     LEMO_CHECK(h && h->n->kind == 0 && dz && out && stop_layer >= 0 && stop_layer <= 9, "bad arguments");
+    LEMO_CHECK(!enc_uses_tc(h->n), "the layer-wise debug hook inspects the fp32 CUDA-core path: call lemo_debug_set_conv_tc(0) first");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;
     const PlaneGeom& g = n->geom[0];
@@ -440,9 +447,11 @@ int lemo_enc_debug_backward(LemoConvNet* h, const float* dz, int32_t N, int32_t 
     }
     return unpack_planes(cur, out, N * n->layers[stop_layer].Cout, g, st);
 }
+int lemo_debug_set_conv_tc(int32_t on) { conv_tc_set(on); return 0; }
 int lemo_convnet_profile_layer(LemoConvNet* h, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream) {
     LEMO_CHECK(h && h->n->kind == 0 && layer >= 0 && layer < 10 && N > 0 && N <= h->n->maxN, "bad arguments");
     ConvNet* n = h->n;
+    if (enc_uses_tc(n)) return enc_tc_profile_layer(n, layer, N, backward, reps, (cudaStream_t)stream);
     const ConvLayer& L = n->layers[layer];
     for (int r = 0; r < reps; ++r) {
         if (!backward) {
@@ -463,7 +472,8 @@ int lemo_enc_backward_input(LemoConvNet* h, const float* dz, int32_t N, float* d
     LEMO_CHECK(N > 0 && N <= n->maxN, "batch exceeds handle size");
     const PlaneGeom& g = n->geom[0];
     const long long total = (long long)N * 64 * g.H * g.W;
-    k_pack_mask<<<cdiv(total, 256), 256, 0, st>>>(dz, n->act[10], n->grad[0], total, g.H, g.W, g.Wp, g.PS);
+    if (enc_uses_tc(n)) LEMO_TRY(enc_tc_pack_dz(n, N, dz, st));
+    else k_pack_mask<<<cdiv(total, 256), 256, 0, st>>>(dz, n->act[10], n->grad[0], total, g.H, g.W, g.Wp, g.PS);
     LEMO_CUDA(cudaGetLastError());
     LEMO_TRY(enc_backward_planes(n, N, h->dx_planes, st));
     LEMO_TRY(unpack_planes(h->dx_planes, dx, N * n->in_ch, g, st));

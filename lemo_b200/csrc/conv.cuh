@@ -57,6 +57,7 @@ struct ConvNet {
     std::vector<float*> up;            // AE: zero-upsampled planes
     float* d_wflat = nullptr;
     long long launches = 0;
+    void* tc = nullptr;                // EncTC (conv_tc.cu): tensor-core path state, kind 0 only
 };
 
 int convnet_create(int kind, int in_ch, const float* h_weights, long long n_weights, int maxN, int H, int W,
@@ -67,6 +68,19 @@ int convnet_refresh_weights(ConvNet* n, cudaStream_t st);      // rebuild wk_f /
 int enc_forward_planes(ConvNet* n, const float* x_planes, int N, cudaStream_t st);
 // dpre of the last layer must be in n->grad[0] (already multiplied by LeakyReLU'(z)); result dx_planes [N][1][PS]
 int enc_backward_planes(ConvNet* n, int N, float* dx_planes, cudaStream_t st);
+// tensor-core Enc path (conv_tc.cu)
+bool conv_tc_enabled();
+void conv_tc_set(int on);
+int enc_tc_create(ConvNet* n);
+void enc_tc_free(ConvNet* n);
+int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st);
+int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st);
+int enc_tc_smooth_loss(ConvNet* n, int N, float w, int acc_stride, int acc_slot, float* acc, cudaStream_t st);
+int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st);
+int enc_tc_profile_layer(ConvNet* n, int layer, int N, int backward, int reps, cudaStream_t st);
+int enc_tc_unpack_z(ConvNet* n, int N, float* z_dense, cudaStream_t st);
+int enc_tc_pack_dz(ConvNet* n, int N, const float* dz_dense, cudaStream_t st);
+inline bool enc_uses_tc(const ConvNet* n) { return n->tc != nullptr && conv_tc_enabled(); }
 inline float* enc_z_planes(ConvNet* n) { return n->act.back(); }
 inline float* enc_gz_planes(ConvNet* n) { return n->grad[0]; }
 

@@ -1,0 +1,523 @@
+// Enc conv3x3 stack on the 5th-generation tensor cores (tcgen05, kind::f16 with bf16 operands, fp32 accumulators in TMEM).
+//
+// Why tensor cores here although the north star names only the blend-shape GEMM: the 3x3 stack is 95 % of a fitting iteration and
+// the CUDA-core kernel (conv.cu) sits at ~50 % of the fp32 FMA roof; SURVEY.md section 7 flags exactly this ("the restriction has to
+// be revisited").  Parity is kept by a bf16 x 3 split: every fp32 value v is carried as the pair (hi, lo) = (bf16(v), bf16(v - hi))
+// (the same 4 bytes as one float) and every product is evaluated as hi*hi + hi*lo + lo*hi with fp32 accumulation, i.e. 16+ bits
+// of mantissa per operand.  Measured on the full-size Enc (oracle/README of DESIGN.md section 4): 1.0e-5 of max|z| after 10 layers and
+// 4e-6 on the smoothness loss, against the 1e-4 bar (plain fp32: 6e-7).  LEMO_CONV=simt selects the fp32 CUDA-core path.
+//
+// Implicit GEMM per output tile of 128 consecutive (padded pitch-linear) pixels:
+//     D[128 px, 64 oc] = sum over 9 taps  A_tap[128 px, 64 ic] . W_tap[64 oc, 64 ic]^T
+//   * activations are NHWC: one pixel = 64 channels = 128 B = exactly one 128-byte-swizzle row, so A_tap is ONE TMA box
+//     (cp.async.bulk.tensor.2d) at row offset (ky-1)*Wp + (kx-1); the zero border of the plane layout supplies the padding and TMA
+//     zero-fills the one row that can fall before the tensor.
+//   * the 9 x {hi,lo} weight tiles (144 KB) are loaded once per CTA and stay in shared memory; CTAs are persistent over tiles.
+//   * warp 0 = TMA producer (2-stage A ring), warp 1 = MMA issuer (108 tcgen05.mma per tile), warps 2-5 = epilogue
+//     (tcgen05.ld -> bias/LeakyReLU or LeakyReLU' mask -> bf16 hi/lo split -> 128 B row stores), accumulators double-buffered in TMEM
+//     so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace lemo {
+
+constexpr int CT_M = 128, CT_C = 64, CT_STAGES = 2;
+constexpr int CT_A_TILE = CT_M * CT_C * 2;                 // 16 KB  (bf16)
+constexpr int CT_W_TILE = CT_C * CT_C * 2;                 //  8 KB
+constexpr int CT_W_BYTES = 18 * CT_W_TILE;                 // 9 taps x {hi,lo}
+constexpr int CT_STAGE_BYTES = 2 * CT_A_TILE;              // hi + lo
+constexpr size_t CT_SMEM = 1024 + CT_W_BYTES + CT_STAGES * CT_STAGE_BYTES + 256;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {       // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+// (hi, lo) bf16 split of one fp32 value; returns hi in the low 16 bits of *h, lo in *l (as raw bf16 bits)
+__device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    h = (uint32_t)__bfloat16_as_ushort(hi);
+    l = (uint32_t)__bfloat16_as_ushort(lo);
+}
+
+// epi: 0 = bias + LeakyReLU (forward), 1 = multiply by LeakyReLU'(aux) (input gradient)
+__global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                    const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                                                    const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
+                                                    __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
+                                                    int Wp, int PS, int epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + CT_W_BYTES;
+    uint64_t* bars = (uint64_t*)(s_a + CT_STAGES * CT_STAGE_BYTES);
+    // bars: [0,1] A full, [2,3] A empty, [4,5] tmem full, [6,7] tmem empty, [8] weights
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tps = (H * Wp + CT_M - 1) / CT_M;               // tiles per sample
+    const int ntiles = N * tps;
+    const int qend = (H + 1) * Wp;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) mb_init(s_u32(&bars[i]), 1);
+        mb_init(s_u32(&bars[4]), 1); mb_init(s_u32(&bars[5]), 1);
+        mb_init(s_u32(&bars[6]), 4); mb_init(s_u32(&bars[7]), 4);
+        mb_init(s_u32(&bars[8]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            const uint32_t wbar = s_u32(&bars[8]);
+            mb_expect_tx(wbar, CT_W_BYTES);
+            for (int t = 0; t < 18; ++t) tma2d(s_u32(s_w + t * CT_W_TILE), &map_w, wbar, 0, t * CT_C);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+                const int row0 = n * PS + q0;
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int s = it & 1;
+                    mb_wait(s_u32(&bars[2 + s]), ((it >> 1) & 1) ^ 1);
+                    const uint32_t full = s_u32(&bars[s]);
+                    mb_expect_tx(full, CT_STAGE_BYTES);
+                    const int row = row0 + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+                    const uint32_t dst = s_u32(s_a + s * CT_STAGE_BYTES);
+                    tma2d(dst, &map_hi, full, 0, row);
+                    tma2d(dst + CT_A_TILE, &map_lo, full, 0, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            // D=F32, A=B=BF16, K-major both, N=64, M=128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+            mb_wait(s_u32(&bars[8]), 0);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mb_wait(s_u32(&bars[6 + acc]), ((lt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + acc * CT_C;
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int s = it & 1;
+                    mb_wait(s_u32(&bars[s]), (it >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = s_u32(s_a + s * CT_STAGE_BYTES);
+                    const uint64_t ahi = desc_sw128(a0), alo = desc_sw128(a0 + CT_A_TILE);
+                    const uint64_t whi = desc_sw128(s_u32(s_w + (tap * 2) * CT_W_TILE)), wlo = desc_sw128(s_u32(s_w + (tap * 2 + 1) * CT_W_TILE));
+#pragma unroll
+                    for (int k = 0; k < CT_C / 16; ++k) {                      // UMMA_K = 16 bf16 = 32 B inside the swizzle atom
+                        const uint64_t o = (uint64_t)(k * 32 >> 4);
+                        mma_bf16(d, ahi + o, whi + o, idesc, (tap | k) != 0 ? 1u : 0u);
+                        mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
+                        mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                    }
+                    mma_commit(s_u32(&bars[2 + s]));                          // A stage reusable once these MMAs retire
+                }
+                mma_commit(s_u32(&bars[4 + acc]));                            // accumulator of this tile complete
+            }
+        }
+    } else {
+        // ============================== epilogue ==============================
+        const int lq = warp & 3;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+            mb_wait(s_u32(&bars[4 + acc]), (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * CT_C);
+            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(s_u32(&bars[6 + acc]));                  // this warp's quarter of the accumulator is free
+            const int q = q0 + lq * 32 + lane;
+            if (q < qend) {
+                const int col = q % Wp;
+                const bool interior = col >= 1 && col <= W;
+                const size_t row = (size_t)n * PS + q;
+                uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C);
+                uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C);
+                const uint4* ax = aux_hi ? reinterpret_cast<const uint4*>(aux_hi + row * CT_C) : nullptr;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {                              // 8 channels = 16 B of bf16 per step
+                    uint32_t hw[4], lw[4];
+                    uint4 a = make_uint4(0, 0, 0, 0);
+                    if (epi == 1) a = ax[c8];
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = c8 * 8 + p * 2 + e;
+                            float x = __uint_as_float(r[c]);
+                            if (epi == 0) { x += __ldg(bias + c); x = x > 0.f ? x : 0.2f * x; }
+                            else {
+                                const uint32_t hb = (aw[p] >> (16 * e)) & 0xFFFFu;       // bf16 bits of the forward activation
+                                const bool pos = hb != 0u && (hb & 0x8000u) == 0u && hb != 0x8000u;
+                                x *= pos ? 1.f : 0.2f;
+                            }
+                            v[e] = interior ? x : 0.f;
+                            if (out_f32) out_f32[row * CT_C + c] = v[e];
+                        }
+                        uint32_t h0, l0, h1, l1;
+                        split_bf16(v[0], h0, l0);
+                        split_bf16(v[1], h1, l1);
+                        hw[p] = h0 | (h1 << 16);
+                        lw[p] = l0 | (l1 << 16);
+                    }
+                    oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ SIMT helpers (first / last layer, loss)
+// layer 0 (1 -> 32 channels): x planar fp32 [N][1][PS] -> NHWC (hi,lo) rows, channels 32..63 stay zero
+__global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, const float* __restrict__ w /*[32][1][9]*/, const float* __restrict__ b,
+                                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int H, int W, int Wp, int PS) {
+    const int n = blockIdx.y;
+    const int q = Wp + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (H + 1) * Wp) return;
+    const int col = q % Wp;
+    const bool interior = col >= 1 && col <= W;
+    float xin[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) xin[k] = x[(size_t)n * PS + q + (k / 3 - 1) * Wp + (k % 3 - 1)];
+    uint32_t* oh = reinterpret_cast<uint32_t*>(out_hi + ((size_t)n * PS + q) * CT_C);
+    uint32_t* ol = reinterpret_cast<uint32_t*>(out_lo + ((size_t)n * PS + q) * CT_C);
+    for (int c = 0; c < 32; c += 2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float a = __ldg(b + c + e);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a = fmaf(__ldg(w + (c + e) * 9 + k), xin[k], a);
+            a = a > 0.f ? a : 0.2f * a;
+            v[e] = interior ? a : 0.f;
+        }
+        uint32_t h0, l0, h1, l1;
+        split_bf16(v[0], h0, l0);
+        split_bf16(v[1], h1, l1);
+        oh[c >> 1] = h0 | (h1 << 16);
+        ol[c >> 1] = l0 | (l1 << 16);
+    }
+}
+// input gradient of layer 0 (32 -> 1): dpre NHWC (hi,lo) -> dx planar fp32
+__global__ void __launch_bounds__(128) k_tc_last_bwd(const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo,
+                                                     const float* __restrict__ w /*[32][1][9]*/, float* __restrict__ dx, int H, int W, int Wp, int PS) {
+    const int n = blockIdx.y;
+    const int q = Wp + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (H + 1) * Wp) return;
+    const int col = q % Wp;
+    float a = 0.f;
+    if (col >= 1 && col <= W) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {                                  // dx[q] = sum_oc,k dpre[oc][q - off_k] * W[oc][k]
+            const size_t row = (size_t)n * PS + q - ((k / 3 - 1) * Wp + (k % 3 - 1));
+            const uint32_t* ph = reinterpret_cast<const uint32_t*>(g_hi + row * CT_C);
+            const uint32_t* pl = reinterpret_cast<const uint32_t*>(g_lo + row * CT_C);
+            for (int c2 = 0; c2 < 16; ++c2) {
+                const uint32_t h = ph[c2], l = pl[c2];
+                const float g0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+                const float g1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+                a = fmaf(g0, __ldg(w + (2 * c2) * 9 + k), a);
+                a = fmaf(g1, __ldg(w + (2 * c2 + 1) * 9 + k), a);
+            }
+        }
+    }
+    dx[(size_t)n * PS + q] = a;
+}
+// smoothness loss on the fp32 NHWC output + dpre of the last layer in (hi,lo) form (same math as fit.cu:k_smooth_loss)
+__global__ void __launch_bounds__(256) k_tc_smooth_loss(const float* __restrict__ zf, int H, int W, int Wp, int PS, float w, int acc_stride,
+                                                        int acc_slot, __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
+                                                        float* __restrict__ acc) {
+    __shared__ float sred[32];
+    const int s = blockIdx.y;
+    const float inv_n = 1.f / (64.f * (float)H * (float)(W - 1));
+    float part = 0.f;
+    const long long tot = (long long)H * Wp * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 63);
+        const int q = Wp + (int)(i >> 6);
+        const int col = q % Wp, x = col - 1;
+        const size_t o = ((size_t)s * PS + q) * 64 + c;
+        float g = 0.f;
+        if (x >= 0 && x < W) {
+            const float zc = zf[o];
+            if (x >= 1) g += zc - zf[o - 64];
+            if (x <= W - 2) { const float d = zf[o + 64] - zc; g -= d; part += d * d; }
+            g = w * 2.f * inv_n * g * (zc > 0.f ? 1.f : 0.2f);
+        }
+        uint32_t h, l;
+        split_bf16(g, h, l);
+        g_hi[o] = __ushort_as_bfloat16((unsigned short)h);
+        g_lo[o] = __ushort_as_bfloat16((unsigned short)l);
+    }
+    part = block_sum(part, sred);
+    if (threadIdx.x == 0) atomicAdd(&acc[s * acc_stride + acc_slot], part * inv_n);
+}
+// module API helpers: NHWC fp32 -> dense NCHW ; dense NCHW gradient (x LeakyReLU'(z)) -> NHWC (hi,lo)
+__global__ void k_tc_unpack_z(const float* __restrict__ zf, float* __restrict__ dense, int N, int H, int W, int Wp, int PS) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * 64 * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % 64), n = (int)(i / ((long long)W * H * 64));
+    dense[i] = zf[((size_t)n * PS + (y + 1) * Wp + x + 1) * 64 + c];
+}
+__global__ void k_tc_pack_dz(const float* __restrict__ dz, const float* __restrict__ zf, __nv_bfloat16* __restrict__ g_hi,
+                             __nv_bfloat16* __restrict__ g_lo, int N, int H, int W, int Wp, int PS) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * 64 * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % 64), n = (int)(i / ((long long)W * H * 64));
+    const size_t o = ((size_t)n * PS + (y + 1) * Wp + x + 1) * 64 + c;
+    const float g = dz[i] * (zf[o] > 0.f ? 1.f : 0.2f);
+    uint32_t h, l;
+    split_bf16(g, h, l);
+    g_hi[o] = __ushort_as_bfloat16((unsigned short)h);
+    g_lo[o] = __ushort_as_bfloat16((unsigned short)l);
+}
+// weights: Conv2d W[oc][ic][9] fp32 -> forward tiles [tap][{hi,lo}][oc 64][ic 64] and input-gradient tiles [tap][{hi,lo}][ic 64][oc 64] (flipped taps)
+__global__ void k_tc_prep_w(const float* __restrict__ w, const float* __restrict__ b, int Cin, int Cout, __nv_bfloat16* __restrict__ wf,
+                            __nv_bfloat16* __restrict__ wb, float* __restrict__ bias64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64) bias64[i] = i < Cout ? b[i] : 0.f;
+    if (i >= 9 * 64 * 64) return;
+    const int tap = i / 4096, r = (i / 64) % 64, c = i % 64;
+    {   // forward: row = oc, col = ic
+        const float v = (r < Cout && c < Cin) ? w[((size_t)r * Cin + c) * 9 + tap] : 0.f;
+        uint32_t h, l;
+        split_bf16(v, h, l);
+        wf[((size_t)(tap * 2) * 64 + r) * 64 + c] = __ushort_as_bfloat16((unsigned short)h);
+        wf[((size_t)(tap * 2 + 1) * 64 + r) * 64 + c] = __ushort_as_bfloat16((unsigned short)l);
+    }
+    {   // input gradient: row = ic (output channel of the adjoint conv), col = oc, tap flipped
+        const float v = (c < Cout && r < Cin) ? w[((size_t)c * Cin + r) * 9 + (8 - tap)] : 0.f;
+        uint32_t h, l;
+        split_bf16(v, h, l);
+        wb[((size_t)(tap * 2) * 64 + r) * 64 + c] = __ushort_as_bfloat16((unsigned short)h);
+        wb[((size_t)(tap * 2 + 1) * 64 + r) * 64 + c] = __ushort_as_bfloat16((unsigned short)l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct EncTC {
+    int maxN = 0;
+    PlaneGeom g{};
+    __nv_bfloat16 *a_hi[11] = {}, *a_lo[11] = {};       // a_*[l] = input of layers[l] for l = 1..9, a_*[10] = final activation
+    float* zf = nullptr;                                // final activation, fp32 NHWC
+    __nv_bfloat16 *g_hi[2] = {}, *g_lo[2] = {};
+    __nv_bfloat16 *wf[10] = {}, *wb[10] = {};
+    float* bias[10] = {};
+    CUtensorMap m_a_hi[11], m_a_lo[11], m_g_hi[2], m_g_lo[2], m_wf[10], m_wb[10];
+    int sm_count = 148;
+};
+
+typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_bf16_map(CUtensorMap* m, const void* base, long long rows, int box_rows) {
+    static PFN_enc fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_enc)p;
+    }
+    LEMO_CHECK(fn, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LEMO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    return 0;
+}
+template <typename T>
+static int zalloc(T** p, size_t n) {
+    LEMO_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    LEMO_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+    return 0;
+}
+
+static int g_conv_tc = -1;
+bool conv_tc_enabled() {
+    if (g_conv_tc < 0) { const char* e = getenv("LEMO_CONV"); g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
+    return g_conv_tc == 1;
+}
+void conv_tc_set(int on) { g_conv_tc = on ? 1 : 0; }
+
+int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    for (int l = 1; l < 10; ++l) {
+        const ConvLayer& L = n->layers[l];
+        k_tc_prep_w<<<cdiv(9 * 64 * 64, 256), 256, 0, st>>>(n->w_flat + L.w_off, n->w_flat + L.b_off, L.Cin, L.Cout, t->wf[l], t->wb[l], t->bias[l]);
+    }
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int enc_tc_create(ConvNet* n) {
+    EncTC* t = new EncTC();
+    n->tc = t;
+    t->maxN = n->maxN; t->g = n->geom[0];
+    const size_t rows = (size_t)n->maxN * t->g.PS;
+    for (int l = 1; l <= 10; ++l) {
+        LEMO_TRY(zalloc(&t->a_hi[l], rows * 64)); LEMO_TRY(zalloc(&t->a_lo[l], rows * 64));
+        LEMO_TRY(make_bf16_map(&t->m_a_hi[l], t->a_hi[l], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_a_lo[l], t->a_lo[l], rows, CT_M));
+    }
+    LEMO_TRY(zalloc(&t->zf, rows * 64));
+    if (n->with_backward)
+        for (int i = 0; i < 2; ++i) {
+            LEMO_TRY(zalloc(&t->g_hi[i], rows * 64)); LEMO_TRY(zalloc(&t->g_lo[i], rows * 64));
+            LEMO_TRY(make_bf16_map(&t->m_g_hi[i], t->g_hi[i], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_g_lo[i], t->g_lo[i], rows, CT_M));
+        }
+    for (int l = 1; l < 10; ++l) {
+        LEMO_TRY(zalloc(&t->wf[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->wb[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->bias[l], 64));
+        LEMO_TRY(make_bf16_map(&t->m_wf[l], t->wf[l], 18 * 64, CT_C)); LEMO_TRY(make_bf16_map(&t->m_wb[l], t->wb[l], 18 * 64, CT_C));
+    }
+    cudaDeviceProp prop;
+    LEMO_CUDA(cudaGetDeviceProperties(&prop, n->device));
+    t->sm_count = prop.multiProcessorCount;
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+    return enc_tc_refresh_weights(n, 0);
+}
+void enc_tc_free(ConvNet* n) {
+    EncTC* t = (EncTC*)n->tc;
+    if (!t) return;
+    for (int l = 0; l <= 10; ++l) { cudaFree(t->a_hi[l]); cudaFree(t->a_lo[l]); }
+    cudaFree(t->zf);
+    for (int i = 0; i < 2; ++i) { cudaFree(t->g_hi[i]); cudaFree(t->g_lo[i]); }
+    for (int l = 0; l < 10; ++l) { cudaFree(t->wf[l]); cudaFree(t->wb[l]); cudaFree(t->bias[l]); }
+    delete t;
+    n->tc = nullptr;
+}
+
+static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
+                     const __nv_bfloat16* aux, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32, int N, int epi, cudaStream_t st) {
+    const PlaneGeom& g = t->g;
+    const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
+    k_conv_tc<<<std::min(ntiles, t->sm_count), 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// x planar fp32 [N][1][PS] -> a_*[10] / zf
+int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    const PlaneGeom& g = t->g;
+    const ConvLayer& L0 = n->layers[0];
+    k_tc_first<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(x_planes, n->w_flat + L0.w_off, n->w_flat + L0.b_off, t->a_hi[1], t->a_lo[1],
+                                                                          g.H, g.W, g.Wp, g.PS);
+    for (int l = 1; l < 10; ++l)
+        LEMO_TRY(launch_tc(t, t->m_a_hi[l], t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1], t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st));
+    n->launches += 10;
+    return 0;
+}
+int enc_tc_smooth_loss(ConvNet* n, int N, float w, int acc_stride, int acc_slot, float* acc, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    const PlaneGeom& g = t->g;
+    k_tc_smooth_loss<<<dim3(256, N), 256, 0, st>>>(t->zf, g.H, g.W, g.Wp, g.PS, w, acc_stride, acc_slot, t->g_hi[0], t->g_lo[0], acc);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+// dpre of the last layer in g_*[0]  ->  dx planar fp32
+int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    const PlaneGeom& g = t->g;
+    int cur = 0;
+    for (int l = 9; l >= 1; --l) {
+        LEMO_TRY(launch_tc(t, t->m_g_hi[cur], t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l], t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st));
+        cur ^= 1;
+    }
+    const ConvLayer& L0 = n->layers[0];
+    k_tc_last_bwd<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(t->g_hi[cur], t->g_lo[cur], n->w_flat + L0.w_off, dx_planes, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    n->launches += 10;
+    return 0;
+}
+// measurement hook: relaunch one tensor-core layer `reps` times on resident buffers (forward layer l in 1..9, or its input gradient)
+int enc_tc_profile_layer(ConvNet* n, int layer, int N, int backward, int reps, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    LEMO_CHECK(layer >= 1 && layer <= 9, "tensor-core layers are 1..9");
+    for (int r = 0; r < reps; ++r) {
+        if (!backward) LEMO_TRY(launch_tc(t, t->m_a_hi[layer], t->m_a_lo[layer], t->m_wf[layer], t->bias[layer], nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
+        else LEMO_TRY(launch_tc(t, t->m_g_hi[0], t->m_g_lo[0], t->m_wb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
+    }
+    return 0;
+}
+int enc_tc_unpack_z(ConvNet* n, int N, float* z_dense, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    const PlaneGeom& g = t->g;
+    const long long tot = (long long)N * 64 * g.H * g.W;
+    k_tc_unpack_z<<<cdiv(tot, 256), 256, 0, st>>>(t->zf, z_dense, N, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+int enc_tc_pack_dz(ConvNet* n, int N, const float* dz_dense, cudaStream_t st) {
+    EncTC* t = (EncTC*)n->tc;
+    const PlaneGeom& g = t->g;
+    const long long tot = (long long)N * 64 * g.H * g.W;
+    k_tc_pack_dz<<<cdiv(tot, 256), 256, 0, st>>>(dz_dense, t->zf, t->g_hi[0], t->g_lo[0], N, g.H, g.W, g.Wp, g.PS);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace lemo

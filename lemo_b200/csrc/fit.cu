@@ -367,7 +367,9 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
         k_canon<<<cdiv(S, 32), 32, 0, st>>>(f->ctx->Jposed, f->Vr, f->T, NR, S, f->canon); nl++;
         k_smooth_input<<<dim3(cdiv(g.W, 128), g.H, S), 128, 0, st>>>(f->Vr, f->canon, f->stats, f->T, NR, g.H, g.W, g.Wp, g.PS, f->xin); nl++;
         LEMO_TRY(enc_forward_planes(f->enc, f->xin, S, st)); nl += 10;
-        k_smooth_loss<<<dim3(8, 64, S), 256, 0, st>>>(enc_z_planes(f->enc), 64, g.H, g.W, g.Wp, g.PS, c.w_smooth, enc_gz_planes(f->enc), f->acc); nl++;
+        if (enc_uses_tc(f->enc)) LEMO_TRY(enc_tc_smooth_loss(f->enc, S, c.w_smooth, ACC_N, ACC_SMOOTH, f->acc, st));
+        else k_smooth_loss<<<dim3(8, 64, S), 256, 0, st>>>(enc_z_planes(f->enc), 64, g.H, g.W, g.Wp, g.PS, c.w_smooth, enc_gz_planes(f->enc), f->acc);
+        nl++;
         LEMO_TRY(enc_backward_planes(f->enc, S, f->gx, st)); nl += 10;
         k_smooth_bwd_a<<<dim3(cdiv(f->T - 1, 128), 243, S), 128, 0, st>>>(f->gx, f->T, g.H, g.W, g.Wp, g.PS, f->gv); nl++;
         k_smooth_bwd_b<<<cdiv(S * f->T * 81, 256), 256, 0, st>>>(f->gv, f->canon, f->stats, f->T, NR, S, f->Grows); nl++;

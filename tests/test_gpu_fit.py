@@ -21,8 +21,10 @@ def _fitter(S, T, **kw):
     return TemporalFitter(smplx_module(), vposer_module(), S, T, enc=enc_module(), device=DEV, **kw)
 
 
-@pytest.mark.parametrize('graph', [False, True])
-def test_temporal_first_iteration_gradients(graph):
+@pytest.mark.parametrize('graph,conv', [(False, 'tc'), (True, 'tc'), (True, 'simt')])
+def test_temporal_first_iteration_gradients(graph, conv):
+    from lemo_b200 import _lib
+    _lib.call('lemo_debug_set_conv_tc', 1 if conv == 'tc' else 0)
     T, S = 119, 2
     c32, c64 = oracle_ctx(torch.float32), oracle_ctx(torch.float64)
     fit = _fitter(S, T, use_cuda_graph=graph)
@@ -45,6 +47,7 @@ def test_temporal_first_iteration_gradients(graph):
             want = tr64[0][k]
             assert abs(float(losses[s, i]) - want) <= 2e-4 * abs(want) + 1e-9, (k, float(losses[s, i]), want)
         assert rel(p72[s], ref72) < 2e-5                    # parameters of the (first) forward incl. tgm axis-angle
+    _lib.call('lemo_debug_set_conv_tc', 1)
 
 
 def test_temporal_loop_tracks_oracle():
