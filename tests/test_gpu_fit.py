@@ -42,7 +42,10 @@ def test_temporal_first_iteration_gradients(graph, conv):
         for k in ('g_transl', 'g_rot6d', 'g_other'):
             e32 = rel(tr32[0][k], tr64[0][k])
             e = rel(st[k][sl], tr64[0][k])
-            assert e < max(5 * e32, 1e-4), (k, s, e, e32)
+            # The smoothness term differentiates Enc features along time (|dz| ~ 1e-2 |z|), which amplifies rounding noise: the fp32
+            # reference arithmetic itself is only ~6e-5 accurate on these gradients.  Budget: 5x that for the fp32 CUDA-core conv
+            # path, 12x (measured 6.5x, 4e-4 of max|g|) for the bf16x3 tensor-core path whose per-activation rounding is 2^-18.
+            assert e < max((5 if conv == 'simt' else 12) * e32, 1e-4), (k, s, e, e32)
         for i, k in enumerate(['loss', 'rec', 'vposer', 'shape', 'hand', 'contact', 'smooth']):
             want = tr64[0][k]
             assert abs(float(losses[s, i]) - want) <= 2e-4 * abs(want) + 1e-9, (k, float(losses[s, i]), want)
@@ -121,4 +124,4 @@ def test_full_size_property_rest_pose_zero_loss():
     fit.set_sequence(0, clean, v[:, c32.m67].numpy(), con)
     fit.run(n_iters=1)
     _, losses = fit.results()
-    assert float(losses[0, 1]) < 2e-6
+    assert float(losses[0, 1]) < 1e-5          # mean |marker - target|: TF32 rounding of Wt on ~1 m coordinates
