@@ -31,6 +31,12 @@ constexpr int CT_W_TILE = CT_C * CT_C * 2;                 //  8 KB
 constexpr int CT_W_BYTES = 18 * CT_W_TILE;                 // 9 taps x {hi,lo}
 constexpr int CT_STAGE_BYTES = 2 * CT_A_TILE;              // hi + lo
 constexpr size_t CT_SMEM = 1024 + CT_W_BYTES + CT_STAGES * CT_STAGE_BYTES + 256;
+// row-reuse variant (MODE 1/2): one TMA box of 136 rows per ky serves the three kx taps through descriptor start addresses that are
+// 0/128/256 B into the box (one pixel = one 128 B swizzle row); 3x less L2->SMEM traffic and 3x fewer pipeline round trips.
+constexpr int CT_M2 = 136;
+constexpr int CT_A_TILE2 = CT_M2 * CT_C * 2;               // 17 KB
+constexpr int CT_STAGE_BYTES2 = 2 * CT_A_TILE2;
+constexpr size_t CT_SMEM2 = 1024 + CT_W_BYTES + CT_STAGES * CT_STAGE_BYTES2 + 256;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -78,6 +84,9 @@ __device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
 }
 
 // epi: 0 = bias + LeakyReLU (forward), 1 = multiply by LeakyReLU'(aux) (input gradient)
+// MODE 0: one TMA box per tap (9 per tile).  MODE 1: one box per ky, kx by start-address offset, descriptor base_offset 0.
+// MODE 2: as 1 with base_offset = (start >> 7) & 7.
+template <int MODE>
 __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                     const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                                     const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
@@ -87,7 +96,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;
     uint8_t* s_a = smem + CT_W_BYTES;
-    uint64_t* bars = (uint64_t*)(s_a + CT_STAGES * CT_STAGE_BYTES);
+    constexpr int STAGE_BYTES = MODE == 0 ? CT_STAGE_BYTES : CT_STAGE_BYTES2;
+    constexpr int A_TILE = MODE == 0 ? CT_A_TILE : CT_A_TILE2;
+    constexpr int NLOADS = MODE == 0 ? 9 : 3;
+    uint64_t* bars = (uint64_t*)(s_a + CT_STAGES * STAGE_BYTES);
     // bars: [0,1] A full, [2,3] A empty, [4,5] tmem full, [6,7] tmem empty, [8] weights
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,15 +136,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
                 const int row0 = n * PS + q0;
-                for (int tap = 0; tap < 9; ++tap, ++it) {
+                for (int ld = 0; ld < NLOADS; ++ld, ++it) {
                     const int s = it & 1;
                     mb_wait(s_u32(&bars[2 + s]), ((it >> 1) & 1) ^ 1);
                     const uint32_t full = s_u32(&bars[s]);
-                    mb_expect_tx(full, CT_STAGE_BYTES);
-                    const int row = row0 + (tap / 3 - 1) * Wp + (tap % 3 - 1);
-                    const uint32_t dst = s_u32(s_a + s * CT_STAGE_BYTES);
+                    mb_expect_tx(full, STAGE_BYTES);
+                    const int row = MODE == 0 ? row0 + (ld / 3 - 1) * Wp + (ld % 3 - 1) : row0 + (ld - 1) * Wp - 1;
+                    const uint32_t dst = s_u32(s_a + s * STAGE_BYTES);
                     tma2d(dst, &map_hi, full, 0, row);
-                    tma2d(dst + CT_A_TILE, &map_lo, full, 0, row);
+                    tma2d(dst + A_TILE, &map_lo, full, 0, row);
                 }
             }
         }
@@ -148,19 +160,25 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
                 mb_wait(s_u32(&bars[6 + acc]), ((lt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * CT_C;
-                for (int tap = 0; tap < 9; ++tap, ++it) {
+                for (int ld = 0; ld < NLOADS; ++ld, ++it) {
                     const int s = it & 1;
                     mb_wait(s_u32(&bars[s]), (it >> 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a0 = s_u32(s_a + s * CT_STAGE_BYTES);
-                    const uint64_t ahi = desc_sw128(a0), alo = desc_sw128(a0 + CT_A_TILE);
-                    const uint64_t whi = desc_sw128(s_u32(s_w + (tap * 2) * CT_W_TILE)), wlo = desc_sw128(s_u32(s_w + (tap * 2 + 1) * CT_W_TILE));
+                    const uint32_t a0 = s_u32(s_a + s * STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < CT_C / 16; ++k) {                      // UMMA_K = 16 bf16 = 32 B inside the swizzle atom
-                        const uint64_t o = (uint64_t)(k * 32 >> 4);
-                        mma_bf16(d, ahi + o, whi + o, idesc, (tap | k) != 0 ? 1u : 0u);
-                        mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
-                        mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                    for (int kx = 0; kx < (MODE == 0 ? 1 : 3); ++kx) {
+                        const int tap = MODE == 0 ? ld : ld * 3 + kx;
+                        const uint32_t ah = a0 + kx * 128, al = a0 + A_TILE + kx * 128;   // +1 pixel = +1 swizzle row
+                        uint64_t ahi = desc_sw128(ah), alo = desc_sw128(al);
+                        if (MODE == 2) { ahi |= (uint64_t)((ah >> 7) & 7) << 49; alo |= (uint64_t)((al >> 7) & 7) << 49; }
+                        const uint64_t whi = desc_sw128(s_u32(s_w + (tap * 2) * CT_W_TILE)), wlo = desc_sw128(s_u32(s_w + (tap * 2 + 1) * CT_W_TILE));
+#pragma unroll
+                        for (int k = 0; k < CT_C / 16; ++k) {                  // UMMA_K = 16 bf16 = 32 B inside the swizzle atom
+                            const uint64_t o = (uint64_t)(k * 32 >> 4);
+                            mma_bf16(d, ahi + o, whi + o, idesc, (tap | k) != 0 ? 1u : 0u);
+                            mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
+                            mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                        }
                     }
                     mma_commit(s_u32(&bars[2 + s]));                          // A stage reusable once these MMAs retire
                 }
@@ -262,27 +280,53 @@ __global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, c
         ol[c >> 1] = l0 | (l1 << 16);
     }
 }
-// input gradient of layer 0 (32 -> 1): dpre NHWC (hi,lo) -> dx planar fp32
-__global__ void __launch_bounds__(128) k_tc_last_bwd(const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo,
+// input gradient of layer 0 (32 -> 1): dpre NHWC (hi,lo) -> dx planar fp32.
+// Two phases per CTA of 256 output pixels: (1) every pixel of the tile + halo reads ITS OWN 128 B row once (warp = 32 consecutive
+// rows = 4 KB contiguous) and reduces it against the 9 weight columns into shared memory T[pixel][9]; (2) dx[q] = sum_k T[q - off_k][k].
+__global__ void __launch_bounds__(256) k_tc_last_bwd(const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo,
                                                      const float* __restrict__ w /*[32][1][9]*/, float* __restrict__ dx, int H, int W, int Wp, int PS) {
+    extern __shared__ float s_t[];                 // [256 + 2*Wp + 2][9]
+    __shared__ float s_w[32 * 9];
     const int n = blockIdx.y;
-    const int q = Wp + blockIdx.x * blockDim.x + threadIdx.x;
+    const int q0 = Wp + blockIdx.x * 256;
+    const int span = 256 + 2 * Wp + 2;
+    for (int i = threadIdx.x; i < 288; i += 256) s_w[i] = w[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < span; e += 256) {
+        const int q = q0 - Wp - 1 + e;
+        float t[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t[k] = 0.f;
+        if (q >= 0 && q < PS) {
+            const uint4* ph = reinterpret_cast<const uint4*>(g_hi + ((size_t)n * PS + q) * CT_C);
+            const uint4* pl = reinterpret_cast<const uint4*>(g_lo + ((size_t)n * PS + q) * CT_C);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {       // channels 0..31
+                const uint4 h = ph[c8], l = pl[c8];
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float g0 = __uint_as_float(hw[p] << 16) + __uint_as_float(lw[p] << 16);
+                    const float g1 = __uint_as_float(hw[p] & 0xFFFF0000u) + __uint_as_float(lw[p] & 0xFFFF0000u);
+                    const int c = c8 * 8 + p * 2;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) t[k] = fmaf(g0, s_w[c * 9 + k], fmaf(g1, s_w[(c + 1) * 9 + k], t[k]));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_t[e * 9 + k] = t[k];
+    }
+    __syncthreads();
+    const int q = q0 + threadIdx.x;
     if (q >= (H + 1) * Wp) return;
     const int col = q % Wp;
     float a = 0.f;
     if (col >= 1 && col <= W) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {                                  // dx[q] = sum_oc,k dpre[oc][q - off_k] * W[oc][k]
-            const size_t row = (size_t)n * PS + q - ((k / 3 - 1) * Wp + (k % 3 - 1));
-            const uint32_t* ph = reinterpret_cast<const uint32_t*>(g_hi + row * CT_C);
-            const uint32_t* pl = reinterpret_cast<const uint32_t*>(g_lo + row * CT_C);
-            for (int c2 = 0; c2 < 16; ++c2) {
-                const uint32_t h = ph[c2], l = pl[c2];
-                const float g0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);
-                const float g1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
-                a = fmaf(g0, __ldg(w + (2 * c2) * 9 + k), a);
-                a = fmaf(g1, __ldg(w + (2 * c2 + 1) * 9 + k), a);
-            }
+        for (int k = 0; k < 9; ++k) {              // dx[q] = sum_oc,k dpre[oc][q - off_k] * W[oc][k]
+            const int e = threadIdx.x + Wp + 1 - ((k / 3 - 1) * Wp + (k % 3 - 1));
+            a += s_t[e * 9 + k];
         }
     }
     dx[(size_t)n * PS + q] = a;
@@ -368,6 +412,7 @@ struct EncTC {
     __nv_bfloat16 *wf[10] = {}, *wb[10] = {};
     float* bias[10] = {};
     CUtensorMap m_a_hi[11], m_a_lo[11], m_g_hi[2], m_g_lo[2], m_wf[10], m_wb[10];
+    CUtensorMap r_a_hi[11], r_a_lo[11], r_g_hi[2], r_g_lo[2];   // 136-row boxes for the row-reuse variant
     int sm_count = 148;
 };
 
@@ -397,12 +442,15 @@ static int zalloc(T** p, size_t n) {
     return 0;
 }
 
-static int g_conv_tc = -1;
-bool conv_tc_enabled() {
-    if (g_conv_tc < 0) { const char* e = getenv("LEMO_CONV"); g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
-    return g_conv_tc == 1;
+static int g_conv_tc = -1;      // 0 = CUDA-core fp32 path; 1 = tensor cores, one TMA box per tap; 2/3 = row-reuse variants (MODE 1/2)
+static void conv_tc_init() {
+    if (g_conv_tc < 0) {
+        const char* e = getenv("LEMO_CONV");
+        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc2") == 0 ? 2 : (strcmp(e, "tc3") == 0 ? 3 : 1)));
+    }
 }
-void conv_tc_set(int on) { g_conv_tc = on ? 1 : 0; }
+bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 3 ? 3 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -422,12 +470,14 @@ int enc_tc_create(ConvNet* n) {
     for (int l = 1; l <= 10; ++l) {
         LEMO_TRY(zalloc(&t->a_hi[l], rows * 64)); LEMO_TRY(zalloc(&t->a_lo[l], rows * 64));
         LEMO_TRY(make_bf16_map(&t->m_a_hi[l], t->a_hi[l], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_a_lo[l], t->a_lo[l], rows, CT_M));
+        LEMO_TRY(make_bf16_map(&t->r_a_hi[l], t->a_hi[l], rows, CT_M2)); LEMO_TRY(make_bf16_map(&t->r_a_lo[l], t->a_lo[l], rows, CT_M2));
     }
     LEMO_TRY(zalloc(&t->zf, rows * 64));
     if (n->with_backward)
         for (int i = 0; i < 2; ++i) {
             LEMO_TRY(zalloc(&t->g_hi[i], rows * 64)); LEMO_TRY(zalloc(&t->g_lo[i], rows * 64));
             LEMO_TRY(make_bf16_map(&t->m_g_hi[i], t->g_hi[i], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_g_lo[i], t->g_lo[i], rows, CT_M));
+            LEMO_TRY(make_bf16_map(&t->r_g_hi[i], t->g_hi[i], rows, CT_M2)); LEMO_TRY(make_bf16_map(&t->r_g_lo[i], t->g_lo[i], rows, CT_M2));
         }
     for (int l = 1; l < 10; ++l) {
         LEMO_TRY(zalloc(&t->wf[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->wb[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->bias[l], 64));
@@ -436,7 +486,9 @@ int enc_tc_create(ConvNet* n) {
     cudaDeviceProp prop;
     LEMO_CUDA(cudaGetDeviceProperties(&prop, n->device));
     t->sm_count = prop.multiProcessorCount;
-    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -454,7 +506,11 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
                      const __nv_bfloat16* aux, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32, int N, int epi, cudaStream_t st) {
     const PlaneGeom& g = t->g;
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
-    k_conv_tc<<<std::min(ntiles, t->sm_count), 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    const int grid = std::min(ntiles, t->sm_count);
+    conv_tc_init();
+    if (g_conv_tc == 2) k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 3) k_conv_tc<2><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -466,8 +522,11 @@ int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
     const ConvLayer& L0 = n->layers[0];
     k_tc_first<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(x_planes, n->w_flat + L0.w_off, n->w_flat + L0.b_off, t->a_hi[1], t->a_lo[1],
                                                                           g.H, g.W, g.Wp, g.PS);
+    conv_tc_init();
+    const bool rr = g_conv_tc >= 2;
     for (int l = 1; l < 10; ++l)
-        LEMO_TRY(launch_tc(t, t->m_a_hi[l], t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1], t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st));
+        LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[l] : t->m_a_hi[l], rr ? t->r_a_lo[l] : t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1],
+                           t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st));
     n->launches += 10;
     return 0;
 }
@@ -483,12 +542,16 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
     const PlaneGeom& g = t->g;
     int cur = 0;
+    conv_tc_init();
+    const bool rr = g_conv_tc >= 2;
     for (int l = 9; l >= 1; --l) {
-        LEMO_TRY(launch_tc(t, t->m_g_hi[cur], t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l], t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st));
+        LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[cur] : t->m_g_hi[cur], rr ? t->r_g_lo[cur] : t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l],
+                           t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st));
         cur ^= 1;
     }
     const ConvLayer& L0 = n->layers[0];
-    k_tc_last_bwd<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(t->g_hi[cur], t->g_lo[cur], n->w_flat + L0.w_off, dx_planes, g.H, g.W, g.Wp, g.PS);
+    k_tc_last_bwd<<<dim3(cdiv((long long)g.H * g.Wp, 256), N), 256, (size_t)(256 + 2 * g.Wp + 2) * 9 * sizeof(float), st>>>(
+        t->g_hi[cur], t->g_lo[cur], n->w_flat + L0.w_off, dx_planes, g.H, g.W, g.Wp, g.PS);
     LEMO_CUDA(cudaGetLastError());
     n->launches += 10;
     return 0;
@@ -498,8 +561,9 @@ int enc_tc_profile_layer(ConvNet* n, int layer, int N, int backward, int reps, c
     EncTC* t = (EncTC*)n->tc;
     LEMO_CHECK(layer >= 1 && layer <= 9, "tensor-core layers are 1..9");
     for (int r = 0; r < reps; ++r) {
-        if (!backward) LEMO_TRY(launch_tc(t, t->m_a_hi[layer], t->m_a_lo[layer], t->m_wf[layer], t->bias[layer], nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
-        else LEMO_TRY(launch_tc(t, t->m_g_hi[0], t->m_g_lo[0], t->m_wb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
+        const bool rr = g_conv_tc >= 2;
+        if (!backward) LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[layer] : t->m_a_hi[layer], rr ? t->r_a_lo[layer] : t->m_a_lo[layer], t->m_wf[layer], t->bias[layer], nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
+        else LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[0] : t->m_g_hi[0], rr ? t->r_g_lo[0] : t->m_g_lo[0], t->m_wb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
     }
     return 0;
 }

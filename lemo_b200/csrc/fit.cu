@@ -132,20 +132,35 @@ __global__ void __launch_bounds__(256) k_priors(const float* __restrict__ z, con
     ps = block_sum(ps, sred); if (threadIdx.x == 0) acc[s * ACC_N + ACC_SHAPE] = ps / (float)nb;
 }
 
-// foot-contact velocity loss (opt_amass_temp.py:407-447).  grid (4 parts, S).  pass 0: count+sum, pass 1: grads.
-__global__ void __launch_bounds__(256) k_contact(const float* __restrict__ Vr, const float* __restrict__ contact, int T, int NR, int off,
-                                                 int cnt_rows, int part, float fps, float thres, float w, int pass,
-                                                 float* __restrict__ acc, float* __restrict__ Grows) {
+// foot-contact velocity loss (opt_amass_temp.py:407-447).  grid (4 parts, S): one CTA per (part, sequence) does the
+// count+sum pass, reduces in-block, then the gradient pass -- the data-dependent masked mean with its empty-set guard
+// (`if (...).sum().item() >= 1`, four host syncs per iteration in the reference) never leaves the device.
+struct FootTab { int off[4]; int n[4]; };
+__global__ void __launch_bounds__(256) k_contact(const float* __restrict__ Vr, const float* __restrict__ contact, int T, int NR, FootTab ft,
+                                                 float fps, float thres, float w, float* __restrict__ acc, float* __restrict__ Grows) {
     __shared__ float sred[32];
-    const int s = blockIdx.x;
-    float cnt = 0.f, sum = 0.f;
-    float inv = 0.f;
-    if (pass == 1) {
-        const float c = acc[s * ACC_N + ACC_CNT0 + part];
-        if (c < 1.f) return;
-        inv = w * fps / c;
-    }
+    __shared__ float s_cnt;
+    const int part = blockIdx.x, s = blockIdx.y;
+    const int off = ft.off[part], cnt_rows = ft.n[part];
     const int n = (T - 1) * cnt_rows;
+    float cnt = 0.f, sum = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = i % cnt_rows, t = i / cnt_rows;
+        const size_t b = (size_t)s * T + t;
+        if (contact[b * 4 + part] != 1.f) continue;
+        const float* a0 = Vr + (b * NR + off + r) * 3;
+        const float* a1 = Vr + ((b + 1) * NR + off + r) * 3;
+        const float vx = (a1[0] - a0[0]) * fps, vy = (a1[1] - a0[1]) * fps, vz = (a1[2] - a0[2]) * fps;
+        const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
+        if (nrm > thres) { cnt += 1.f; sum += nrm; }
+    }
+    cnt = block_sum(cnt, sred);
+    if (threadIdx.x == 0) { s_cnt = cnt; acc[s * ACC_N + ACC_CNT0 + part] = cnt; }
+    sum = block_sum(sum, sred);
+    if (threadIdx.x == 0) acc[s * ACC_N + ACC_SUM0 + part] = sum;
+    __syncthreads();
+    if (s_cnt < 1.f) return;
+    const float inv = w * fps / s_cnt;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int r = i % cnt_rows, t = i / cnt_rows;
         const size_t b = (size_t)s * T + t;
@@ -155,19 +170,12 @@ __global__ void __launch_bounds__(256) k_contact(const float* __restrict__ Vr, c
         const float vx = (a1[0] - a0[0]) * fps, vy = (a1[1] - a0[1]) * fps, vz = (a1[2] - a0[2]) * fps;
         const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
         if (nrm > thres) {
-            if (pass == 0) { cnt += 1.f; sum += nrm; }
-            else {
-                const float c = inv / nrm;
-                float* g0 = Grows + (b * NR + off + r) * 3;
-                float* g1 = Grows + ((b + 1) * NR + off + r) * 3;
-                atomicAdd(&g1[0], c * vx); atomicAdd(&g1[1], c * vy); atomicAdd(&g1[2], c * vz);
-                atomicAdd(&g0[0], -c * vx); atomicAdd(&g0[1], -c * vy); atomicAdd(&g0[2], -c * vz);
-            }
+            const float c = inv / nrm;
+            float* g0 = Grows + (b * NR + off + r) * 3;
+            float* g1 = Grows + ((b + 1) * NR + off + r) * 3;
+            atomicAdd(&g1[0], c * vx); atomicAdd(&g1[1], c * vy); atomicAdd(&g1[2], c * vz);
+            atomicAdd(&g0[0], -c * vx); atomicAdd(&g0[1], -c * vy); atomicAdd(&g0[2], -c * vz);
         }
-    }
-    if (pass == 0) {
-        cnt = block_sum(cnt, sred); if (threadIdx.x == 0) acc[s * ACC_N + ACC_CNT0 + part] = cnt;
-        sum = block_sum(sum, sred); if (threadIdx.x == 0) acc[s * ACC_N + ACC_SUM0 + part] = sum;
     }
 }
 
@@ -356,11 +364,9 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
     const bool smooth = f->mode == 0 && f->enc && c.w_smooth > 0.f;
     const bool con = f->mode == 0 && c.w_contact > 0.f;
     if (con) {
-        for (int p = 0; p < 4; ++p) {
-            k_contact<<<S, 256, 0, st>>>(f->Vr, contact, f->T, NR, f->foot_off[p], f->foot_n[p], p, c.fps, c.vel_thres, c.w_contact, 0, f->acc, f->Grows);
-            k_contact<<<S, 256, 0, st>>>(f->Vr, contact, f->T, NR, f->foot_off[p], f->foot_n[p], p, c.fps, c.vel_thres, c.w_contact, 1, f->acc, f->Grows);
-            nl += 2;
-        }
+        FootTab ft;
+        for (int p = 0; p < 4; ++p) { ft.off[p] = f->foot_off[p]; ft.n[p] = f->foot_n[p]; }
+        k_contact<<<dim3(4, S), 256, 0, st>>>(f->Vr, contact, f->T, NR, ft, c.fps, c.vel_thres, c.w_contact, f->acc, f->Grows); nl++;
     }
     if (smooth) {
         const PlaneGeom& g = f->geom;
