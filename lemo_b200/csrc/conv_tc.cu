@@ -84,8 +84,10 @@ __device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
 }
 
 // epi: 0 = bias + LeakyReLU (forward), 1 = multiply by LeakyReLU'(aux) (input gradient)
-// MODE 0: one TMA box per tap (9 per tile).  MODE 1: one box per ky, kx by start-address offset, descriptor base_offset 0.
-// MODE 2: as 1 with base_offset = (start >> 7) & 7.
+// MODE 1 (default): one TMA box of 136 rows per ky; the three kx taps are descriptor start addresses 0/128/256 B into it.  The 128 B
+//   swizzle is a function of the ABSOLUTE shared-memory address, so a start address that is not 1024 B aligned needs NO base_offset
+//   (measured on B200: base_offset = 0 reproduces the per-tap result bit for bit, base_offset = (addr >> 7) & 7 gives garbage).
+// MODE 0: one TMA box per tap (9 per tile) -- kept as the A/B reference for that experiment (tools/diag_conv_modes.py).
 template <int MODE>
 __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                     const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
@@ -169,8 +171,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
                     for (int kx = 0; kx < (MODE == 0 ? 1 : 3); ++kx) {
                         const int tap = MODE == 0 ? ld : ld * 3 + kx;
                         const uint32_t ah = a0 + kx * 128, al = a0 + A_TILE + kx * 128;   // +1 pixel = +1 swizzle row
-                        uint64_t ahi = desc_sw128(ah), alo = desc_sw128(al);
-                        if (MODE == 2) { ahi |= (uint64_t)((ah >> 7) & 7) << 49; alo |= (uint64_t)((al >> 7) & 7) << 49; }
+                        const uint64_t ahi = desc_sw128(ah), alo = desc_sw128(al);
                         const uint64_t whi = desc_sw128(s_u32(s_w + (tap * 2) * CT_W_TILE)), wlo = desc_sw128(s_u32(s_w + (tap * 2 + 1) * CT_W_TILE));
 #pragma unroll
                         for (int k = 0; k < CT_C / 16; ++k) {                  // UMMA_K = 16 bf16 = 32 B inside the swizzle atom
@@ -442,15 +443,15 @@ static int zalloc(T** p, size_t n) {
     return 0;
 }
 
-static int g_conv_tc = -1;      // 0 = CUDA-core fp32 path; 1 = tensor cores, one TMA box per tap; 2/3 = row-reuse variants (MODE 1/2)
+static int g_conv_tc = -1;      // 0 = CUDA-core fp32 path; 1 = tensor cores, row-reuse (default); 2 = tensor cores, one TMA box per tap
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc2") == 0 ? 2 : (strcmp(e, "tc3") == 0 ? 3 : 1)));
+        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : 1));
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 3 ? 3 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 2 ? 2 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -488,7 +489,6 @@ int enc_tc_create(ConvNet* n) {
     t->sm_count = prop.multiProcessorCount;
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
-    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -508,9 +508,8 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 2) k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else if (g_conv_tc == 3) k_conv_tc<2><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -523,7 +522,7 @@ int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
     k_tc_first<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(x_planes, n->w_flat + L0.w_off, n->w_flat + L0.b_off, t->a_hi[1], t->a_lo[1],
                                                                           g.H, g.W, g.Wp, g.PS);
     conv_tc_init();
-    const bool rr = g_conv_tc >= 2;
+    const bool rr = g_conv_tc != 2;
     for (int l = 1; l < 10; ++l)
         LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[l] : t->m_a_hi[l], rr ? t->r_a_lo[l] : t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1],
                            t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st));
@@ -543,7 +542,7 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
     const PlaneGeom& g = t->g;
     int cur = 0;
     conv_tc_init();
-    const bool rr = g_conv_tc >= 2;
+    const bool rr = g_conv_tc != 2;
     for (int l = 9; l >= 1; --l) {
         LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[cur] : t->m_g_hi[cur], rr ? t->r_g_lo[cur] : t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l],
                            t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st));
@@ -561,7 +560,7 @@ int enc_tc_profile_layer(ConvNet* n, int layer, int N, int backward, int reps, c
     EncTC* t = (EncTC*)n->tc;
     LEMO_CHECK(layer >= 1 && layer <= 9, "tensor-core layers are 1..9");
     for (int r = 0; r < reps; ++r) {
-        const bool rr = g_conv_tc >= 2;
+        const bool rr = g_conv_tc != 2;
         if (!backward) LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[layer] : t->m_a_hi[layer], rr ? t->r_a_lo[layer] : t->m_a_lo[layer], t->m_wf[layer], t->bias[layer], nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
         else LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[0] : t->m_g_hi[0], rr ? t->r_g_lo[0] : t->m_g_lo[0], t->m_wb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
     }
