@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--cpu-iters', type=int, default=8, help='timed CPU-baseline iterations (bounded sample)')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-perframe', action='store_true')
     return ap.parse_args()
 
 
@@ -311,6 +312,26 @@ def main():
                     'traffic': traffic.get('lbs_forward'), 'ms': lbs_ms, 'verts_per_sec': T * Vn / (lbs_ms * 1e-3),
                     'peak_source': ('measured' if 'hbm_gbs' in peaks else 'fallback') + ' copy bandwidth (MEASURED_PEAKS.json)'}
 
+    # ---------------- secondary: per-frame stage (BASELINE configs[1]: B=1 chains, warm start), rank 0 only, reported not headline
+    perframe = None
+    if rank == 0 and not a.skip_perframe:
+        from lemo_b200.fit import PerFrameFitter
+        Tp, it_pf = 60, 100
+        pf = PerFrameFitter(body, vp, S, Tp, device=dev, use_cuda_graph=not a.no_graph)
+        for i in range(S):
+            pf.set_sequence(i, inits[i][0, 6:16].numpy(), mrecs[i][:Tp])
+        pf.run(n_iters=2)
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        pf.run(n_iters=it_pf)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        pf_ms = c0.elapsed_time(c1)
+        perframe = {'workload': 'opt_amass_perframe: %d sequences x %d frames x %d Adam iterations, B=1 chains side by side' % (S, Tp, it_pf),
+                    'frame_iterations_per_sec': S * Tp * it_pf / (pf_ms * 1e-3), 'us_per_iteration': 1e3 * pf_ms / (Tp * it_pf),
+                    'clips_per_sec': S / (pf_ms * 1e-3)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,7 +343,7 @@ def main():
             'data': 'synthetic', 'config': workload_config(a, world), 'clocks': clocks,
             'e2e': {'value': e2e_rate, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(h_loss.numel() + h_par.numel()) * 4},
             'gpu_launches': int(launches), 'roofline': roof, 'roofline_lbs': roof_lbs,
-            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'],
+            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'], 'perframe': perframe,
             'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}}
     print(json.dumps(line), flush=True)
     if world > 1:

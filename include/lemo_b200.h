@@ -169,6 +169,22 @@ int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* 
                           int64_t xyz2_batch_stride, const float* g_dist1, const float* g_dist2,
                           const int32_t* idx1, const int32_t* idx2, float* d_xyz1, float* d_xyz2, void* stream);
 
+/* ---------------------------------------------------------------- PROX scene terms (temp_prox/fitting_temp_slide.py) --- */
+/* PerspectiveCamera.forward (temp_prox/camera.py:93-116): img = f * (R p + t).xy / (R p + t).z + c.  points [n,3] -> out [n,2].
+ * h_R [9] / h_t [3] are HOST arrays (the camera is fixed in the shipped configs, S2.yaml camera_mode 'fixed'); NULL = identity / zero. */
+int lemo_camera_project(const float* points, int64_t n, const float* h_R, const float* h_t, float fx, float fy, float cx, float cy,
+                        float* out, void* stream);
+int lemo_camera_project_backward(const float* points, int64_t n, const float* h_R, const float* h_t, float fx, float fy, float cx,
+                                 float cy, const float* d_out, float* d_points, void* stream);
+/* camera -> world: out = R p + t (fitting_temp_slide.py:677-678); adjoint = 1 computes R^T g (the gradient) */
+int lemo_rigid_transform(const float* points, int64_t n, const float* h_R, const float* h_t, int32_t adjoint, float* out, void* stream);
+/* F.grid_sample(sdf, norm_vertices[:, :, [2,1,0]], padding_mode='border') (fitting_temp_slide.py:684-687): trilinear lookup of a
+ * [dim,dim,dim] signed-distance volume (indexed [x][y][z], shared by the batch) at world points [n,3]; align_corners=False. */
+int lemo_sdf_sample(const float* points, int64_t n, const float* sdf, int32_t dim, const float* h_grid_min, const float* h_grid_max,
+                    float* values, void* stream);
+int lemo_sdf_sample_backward(const float* points, int64_t n, const float* sdf, int32_t dim, const float* h_grid_min,
+                             const float* h_grid_max, const float* d_values, float* d_points, void* stream);
+
 /* ---------------------------------------------------------------- optimiser (torch.optim.Adam.step) ----- */
 /* p,g,m,v [n]; t = 1-based step; bias-corrected, no weight decay / amsgrad (opt_amass_temp.py:345,455) */
 int lemo_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,

@@ -110,6 +110,11 @@ SIGNATURES = {
     'lemo_ae_finetune_step': (C.c_int, [_P, _P, _P, _I, _I, _D, _I, _P, _P]),
     'lemo_chamfer_forward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P]),
     'lemo_chamfer_backward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    'lemo_camera_project': (C.c_int, [_P, _L, _P, _P, _F, _F, _F, _F, _P, _P]),
+    'lemo_camera_project_backward': (C.c_int, [_P, _L, _P, _P, _F, _F, _F, _F, _P, _P, _P]),
+    'lemo_rigid_transform': (C.c_int, [_P, _L, _P, _P, _I, _P, _P]),
+    'lemo_sdf_sample': (C.c_int, [_P, _L, _P, _I, _P, _P, _P, _P]),
+    'lemo_sdf_sample_backward': (C.c_int, [_P, _L, _P, _I, _P, _P, _P, _P, _P]),
     'lemo_adam_step': (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _P]),
     'lemo_fit_create': (C.c_int, [_P, _P, _P, _P, C.POINTER(LemoFitConfigC), C.c_int, C.POINTER(_P)]),
     'lemo_fit_destroy': (C.c_int, [_P]),
