@@ -83,6 +83,61 @@ __device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
     l = (uint32_t)__bfloat16_as_ushort(lo);
 }
 
+// per-tile epilogue shared by the kernel variants: TMEM -> registers -> bias/LeakyReLU or LeakyReLU' mask -> (hi,lo) rows
+__device__ __forceinline__ void conv_tc_epilogue(uint32_t tmem_base, int acc, uint32_t empty_bar, int lq, int lane, int n, int q0, int qend,
+                                                 int W, int Wp, int PS, int epi, const float* __restrict__ bias,
+                                                 const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
+                                                 __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
+    uint32_t r[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * CT_C);
+            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(empty_bar);                  // this warp's quarter of the accumulator is free
+            const int q = q0 + lq * 32 + lane;
+            if (q < qend) {
+                const int col = q % Wp;
+                const bool interior = col >= 1 && col <= W;
+                const size_t row = (size_t)n * PS + q;
+                uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C);
+                uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C);
+                const uint4* ax = aux_hi ? reinterpret_cast<const uint4*>(aux_hi + row * CT_C) : nullptr;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {                              // 8 channels = 16 B of bf16 per step
+                    uint32_t hw[4], lw[4];
+                    uint4 a = make_uint4(0, 0, 0, 0);
+                    if (epi == 1) a = ax[c8];
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = c8 * 8 + p * 2 + e;
+                            float x = __uint_as_float(r[c]);
+                            if (epi == 0) { x += __ldg(bias + c); x = x > 0.f ? x : 0.2f * x; }
+                            else {
+                                const uint32_t hb = (aw[p] >> (16 * e)) & 0xFFFFu;       // bf16 bits of the forward activation
+                                const bool pos = hb != 0u && (hb & 0x8000u) == 0u && hb != 0x8000u;
+                                x *= pos ? 1.f : 0.2f;
+                            }
+                            v[e] = interior ? x : 0.f;
+                            if (out_f32) out_f32[row * CT_C + c] = v[e];
+                        }
+                        uint32_t h0, l0, h1, l1;
+                        split_bf16(v[0], h0, l0);
+                        split_bf16(v[1], h1, l1);
+                        hw[p] = h0 | (h1 << 16);
+                        lw[p] = l0 | (l1 << 16);
+                    }
+                    oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+}
+
 // epi: 0 = bias + LeakyReLU (forward), 1 = multiply by LeakyReLU'(aux) (input gradient)
 // MODE 1 (default): one TMA box of 136 rows per ky; the three kx taps are descriptor start addresses 0/128/256 B into it.  The 128 B
 //   swizzle is a function of the ABSOLUTE shared-memory address, so a start address that is not 1024 B aligned needs NO base_offset
@@ -195,54 +250,118 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
             const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
             mb_wait(s_u32(&bars[4 + acc]), (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * CT_C);
-            tmem_ld32(taddr, r);
-            tmem_ld32(taddr + 32, r + 32);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mb_arrive(s_u32(&bars[6 + acc]));                  // this warp's quarter of the accumulator is free
-            const int q = q0 + lq * 32 + lane;
-            if (q < qend) {
-                const int col = q % Wp;
-                const bool interior = col >= 1 && col <= W;
-                const size_t row = (size_t)n * PS + q;
-                uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C);
-                uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C);
-                const uint4* ax = aux_hi ? reinterpret_cast<const uint4*>(aux_hi + row * CT_C) : nullptr;
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {                              // 8 channels = 16 B of bf16 per step
-                    uint32_t hw[4], lw[4];
-                    uint4 a = make_uint4(0, 0, 0, 0);
-                    if (epi == 1) a = ax[c8];
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        float v[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int c = c8 * 8 + p * 2 + e;
-                            float x = __uint_as_float(r[c]);
-                            if (epi == 0) { x += __ldg(bias + c); x = x > 0.f ? x : 0.2f * x; }
-                            else {
-                                const uint32_t hb = (aw[p] >> (16 * e)) & 0xFFFFu;       // bf16 bits of the forward activation
-                                const bool pos = hb != 0u && (hb & 0x8000u) == 0u && hb != 0x8000u;
-                                x *= pos ? 1.f : 0.2f;
-                            }
-                            v[e] = interior ? x : 0.f;
-                            if (out_f32) out_f32[row * CT_C + c] = v[e];
-                        }
-                        uint32_t h0, l0, h1, l1;
-                        split_bf16(v[0], h0, l0);
-                        split_bf16(v[1], h1, l1);
-                        hw[p] = h0 | (h1 << 16);
-                        lw[p] = l0 | (l1 << 16);
-                    }
-                    oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            conv_tc_epilogue(tmem_base, acc, s_u32(&bars[6 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi, out_hi, out_lo, out_f32);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ deeper-pipeline variant
+// Same math as k_conv_tc<1>, different shared-memory budget: ncu on k_conv_tc<1> shows the tensor pipe only 30-39 % active with L2 at
+// 35 % and DRAM at 12 % -- the kernel waits on TMA->MMA round trips because 144 KB of resident weights leave room for just two A
+// stages.  Here the weights of ONE ky row (3 taps x {hi,lo} = 48 KB) travel with each step through a 2-slot ring (they stay L2
+// resident: 144 KB per layer), which frees shared memory for THREE 34 KB A stages.
+constexpr int CW_NA = 3, CW_NW = 2;
+constexpr int CW_WSLOT = 6 * CT_W_TILE;                                       // 48 KB
+constexpr size_t CW_SMEM = 1024 + CW_NW * CW_WSLOT + CW_NA * CT_STAGE_BYTES2 + 256;
+__global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                       const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
+                                                       __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
+                                                       int Wp, int PS, int epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + CW_NW * CW_WSLOT;
+    uint64_t* bars = (uint64_t*)(s_a + CW_NA * CT_STAGE_BYTES2);
+    // bars: [0..2] step full (A stage + weight slot), [3..5] A empty, [6,7] W empty, [8,9] tmem full, [10,11] tmem empty
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tps = (H * Wp + CT_M - 1) / CT_M;
+    const int ntiles = N * tps;
+    const int qend = (H + 1) * Wp;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 10; ++i) mb_init(s_u32(&bars[i]), 1);
+        mb_init(s_u32(&bars[10]), 4); mb_init(s_u32(&bars[11]), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+                const int row0 = n * PS + q0;
+                for (int ky = 0; ky < 3; ++ky, ++it) {
+                    const int sa = it % CW_NA, sw = it % CW_NW;
+                    mb_wait(s_u32(&bars[3 + sa]), ((it / CW_NA) & 1) ^ 1);
+                    mb_wait(s_u32(&bars[6 + sw]), ((it / CW_NW) & 1) ^ 1);
+                    const uint32_t full = s_u32(&bars[sa]);
+                    mb_expect_tx(full, CT_STAGE_BYTES2 + CW_WSLOT);
+                    const int row = row0 + (ky - 1) * Wp - 1;
+                    const uint32_t dst = s_u32(s_a + sa * CT_STAGE_BYTES2);
+                    tma2d(dst, &map_hi, full, 0, row);
+                    tma2d(dst + CT_A_TILE2, &map_lo, full, 0, row);
+                    const uint32_t wdst = s_u32(s_w + sw * CW_WSLOT);
+                    for (int t = 0; t < 6; ++t) tma2d(wdst + t * CT_W_TILE, &map_w, full, 0, (ky * 6 + t) * CT_C);   // taps ky*3+kx, {hi,lo}
                 }
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mb_wait(s_u32(&bars[10 + acc]), ((lt >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + acc * CT_C;
+                for (int ky = 0; ky < 3; ++ky, ++it) {
+                    const int sa = it % CW_NA, sw = it % CW_NW;
+                    mb_wait(s_u32(&bars[sa]), (it / CW_NA) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = s_u32(s_a + sa * CT_STAGE_BYTES2), w0 = s_u32(s_w + sw * CW_WSLOT);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const uint64_t ahi = desc_sw128(a0 + kx * 128), alo = desc_sw128(a0 + CT_A_TILE2 + kx * 128);
+                        const uint64_t whi = desc_sw128(w0 + (kx * 2) * CT_W_TILE), wlo = desc_sw128(w0 + (kx * 2 + 1) * CT_W_TILE);
+#pragma unroll
+                        for (int k = 0; k < CT_C / 16; ++k) {
+                            const uint64_t o = (uint64_t)(k * 32 >> 4);
+                            mma_bf16(d, ahi + o, whi + o, idesc, (ky | kx | k) != 0 ? 1u : 0u);
+                            mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
+                            mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                        }
+                    }
+                    mma_commit(s_u32(&bars[3 + sa]));
+                    mma_commit(s_u32(&bars[6 + sw]));
+                }
+                mma_commit(s_u32(&bars[8 + acc]));
+            }
+        }
+    } else {
+        const int lq = warp & 3;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+            mb_wait(s_u32(&bars[8 + acc]), (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            conv_tc_epilogue(tmem_base, acc, s_u32(&bars[10 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi, out_hi, out_lo, out_f32);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -443,15 +562,15 @@ static int zalloc(T** p, size_t n) {
     return 0;
 }
 
-static int g_conv_tc = -1;      // 0 = CUDA-core fp32 path; 1 = tensor cores, row-reuse (default); 2 = tensor cores, one TMA box per tap
+static int g_conv_tc = -1;      // 0 = CUDA-core fp32; 1 = tensor cores, row-reuse (default); 2 = one TMA box per tap; 3 = row-reuse + streamed weights
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : 1));
+        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : 1)));
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 2 ? 2 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 3 ? 3 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -489,6 +608,7 @@ int enc_tc_create(ConvNet* n) {
     t->sm_count = prop.multiProcessorCount;
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -508,7 +628,8 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 3) k_conv_tc_ws<<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
     return 0;
