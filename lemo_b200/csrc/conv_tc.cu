@@ -84,14 +84,25 @@ __device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
 }
 
 // per-tile epilogue shared by the kernel variants: TMEM -> registers -> bias/LeakyReLU or LeakyReLU' mask -> (hi,lo) rows
+template <bool STACK = false>
 __device__ __forceinline__ void conv_tc_epilogue(uint32_t tmem_base, int acc, uint32_t empty_bar, int lq, int lane, int n, int q0, int qend,
                                                  int W, int Wp, int PS, int epi, const float* __restrict__ bias,
                                                  const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
                                                  __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
     uint32_t r[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * CT_C);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * (STACK ? 2 * CT_C : CT_C));
             tmem_ld32(taddr, r);
             tmem_ld32(taddr + 32, r + 32);
+            if (STACK) {                      // columns [64,128) hold the hi*lo product of the stacked-weights MMA: fold them in
+                uint32_t t2[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(taddr + 64 + 32 * h, t2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[32 * h + j] = __float_as_uint(__uint_as_float(r[32 * h + j]) + __uint_as_float(t2[j]));
+                }
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -266,6 +277,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ CUte
 constexpr int CW_NA = 3, CW_NW = 2;
 constexpr int CW_WSLOT = 6 * CT_W_TILE;                                       // 48 KB
 constexpr size_t CW_SMEM = 1024 + CW_NW * CW_WSLOT + CW_NA * CT_STAGE_BYTES2 + 256;
+// STACK: the MMA atom M128 x N64 x K16 reads 6 KB of shared memory for 32 cycles of math (128 B/clk => 48 cycles): operand-bandwidth
+// bound.  Stacking [W_hi ; W_lo] (adjacent 64-row tiles = one 128-row K-major operand) turns the two products that share A_hi into ONE
+// N=128 MMA whose halves [hi*hi | hi*lo] are summed in the epilogue: A_hi is read once instead of twice (14 KB instead of 18 KB per K step).
+template <bool STACK>
 __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                        const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                                        const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(STACK ? 256 : 128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -324,12 +339,13 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+            constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
             uint32_t it = 0, lt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
                 const int acc = lt & 1;
                 mb_wait(s_u32(&bars[10 + acc]), ((lt >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem_base + acc * CT_C;
+                const uint32_t d = tmem_base + acc * (STACK ? 2 * CT_C : CT_C);
                 for (int ky = 0; ky < 3; ++ky, ++it) {
                     const int sa = it % CW_NA, sw = it % CW_NW;
                     mb_wait(s_u32(&bars[sa]), (it / CW_NA) & 1);
@@ -342,9 +358,14 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
 #pragma unroll
                         for (int k = 0; k < CT_C / 16; ++k) {
                             const uint64_t o = (uint64_t)(k * 32 >> 4);
-                            mma_bf16(d, ahi + o, whi + o, idesc, (ky | kx | k) != 0 ? 1u : 0u);
-                            mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
-                            mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                            if (STACK) {
+                                mma_bf16(d, ahi + o, whi + o, idesc128, (ky | kx | k) != 0 ? 1u : 0u);   // [hi*W_hi | hi*W_lo], N = 128
+                                mma_bf16(d, alo + o, whi + o, idesc, 1u);                               // lo*W_hi into columns [0,64)
+                            } else {
+                                mma_bf16(d, ahi + o, whi + o, idesc, (ky | kx | k) != 0 ? 1u : 0u);
+                                mma_bf16(d, ahi + o, wlo + o, idesc, 1u);
+                                mma_bf16(d, alo + o, whi + o, idesc, 1u);
+                            }
                         }
                     }
                     mma_commit(s_u32(&bars[3 + sa]));
@@ -361,12 +382,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
             const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
             mb_wait(s_u32(&bars[8 + acc]), (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            conv_tc_epilogue(tmem_base, acc, s_u32(&bars[10 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi, out_hi, out_lo, out_f32);
+            conv_tc_epilogue<STACK>(tmem_base, acc, s_u32(&bars[10 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi, out_hi, out_lo, out_f32);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(STACK ? 256 : 128) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ SIMT helpers (first / last layer, loss)
@@ -566,11 +587,11 @@ static int g_conv_tc = -1;      // 0 = CUDA-core fp32; 1 = tensor cores, row-reu
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : 1)));
+        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : (strcmp(e, "tc_stack") == 0 ? 4 : 1))));
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 3 ? 3 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 4 ? 4 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -608,7 +629,8 @@ int enc_tc_create(ConvNet* n) {
     t->sm_count = prop.multiProcessorCount;
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
-    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -628,7 +650,8 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 3) k_conv_tc_ws<<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 4) k_conv_tc_ws<true><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 3) k_conv_tc_ws<false><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
