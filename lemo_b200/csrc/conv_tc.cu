@@ -84,69 +84,71 @@ __device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
 }
 
 // per-tile epilogue shared by the kernel variants: TMEM -> registers -> bias/LeakyReLU or LeakyReLU' mask -> (hi,lo) rows
-template <bool STACK = false>
+// per-tile epilogue shared by the kernel variants: TMEM -> registers -> bias/LeakyReLU or LeakyReLU' mask -> (hi,lo) rows.
+// NCH channels per thread starting at c0 (64: one warp per TMEM lane quarter; 32: two warps per quarter, each half the channels).
+template <bool STACK = false, int NCH = 64>
 __device__ __forceinline__ void conv_tc_epilogue(uint32_t tmem_base, int acc, uint32_t empty_bar, int lq, int lane, int n, int q0, int qend,
                                                  int W, int Wp, int PS, int epi, const float* __restrict__ bias,
                                                  const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
-                                                 __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
-    uint32_t r[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * (STACK ? 2 * CT_C : CT_C));
-            tmem_ld32(taddr, r);
-            tmem_ld32(taddr + 32, r + 32);
-            if (STACK) {                      // columns [64,128) hold the hi*lo product of the stacked-weights MMA: fold them in
-                uint32_t t2[32];
+                                                 __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int c0 = 0) {
+    uint32_t r[NCH];
+    const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * (STACK ? 2 * CT_C : CT_C)) + (uint32_t)c0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tmem_ld32(taddr + 64 + 32 * h, t2);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int h = 0; h < NCH / 32; ++h) tmem_ld32(taddr + 32 * h, r + 32 * h);
+    if (STACK) {                      // columns [64,128) hold the hi*lo product of the stacked-weights MMA: fold them in
+        uint32_t t2[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[32 * h + j] = __float_as_uint(__uint_as_float(r[32 * h + j]) + __uint_as_float(t2[j]));
-                }
-            }
+        for (int h = 0; h < NCH / 32; ++h) {
+            tmem_ld32(taddr + 64 + 32 * h, t2);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mb_arrive(empty_bar);                  // this warp's quarter of the accumulator is free
-            const int q = q0 + lq * 32 + lane;
-            if (q < qend) {
-                const int col = q % Wp;
-                const bool interior = col >= 1 && col <= W;
-                const size_t row = (size_t)n * PS + q;
-                uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C);
-                uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C);
-                const uint4* ax = aux_hi ? reinterpret_cast<const uint4*>(aux_hi + row * CT_C) : nullptr;
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {                              // 8 channels = 16 B of bf16 per step
-                    uint32_t hw[4], lw[4];
-                    uint4 a = make_uint4(0, 0, 0, 0);
-                    if (epi == 1) a = ax[c8];
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            for (int j = 0; j < 32; ++j) r[32 * h + j] = __float_as_uint(__uint_as_float(r[32 * h + j]) + __uint_as_float(t2[j]));
+        }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mb_arrive(empty_bar);                  // this warp's share of the accumulator is free
+    const int q = q0 + lq * 32 + lane;
+    if (q < qend) {
+        const int col = q % Wp;
+        const bool interior = col >= 1 && col <= W;
+        const size_t row = (size_t)n * PS + q;
+        uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C + c0);
+        uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C + c0);
+        const uint4* ax = aux_hi ? reinterpret_cast<const uint4*>(aux_hi + row * CT_C + c0) : nullptr;
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        float v[2];
+        for (int c8 = 0; c8 < NCH / 8; ++c8) {                              // 8 channels = 16 B of bf16 per step
+            uint32_t hw[4], lw[4];
+            uint4 a = make_uint4(0, 0, 0, 0);
+            if (epi == 1) a = ax[c8];
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int c = c8 * 8 + p * 2 + e;
-                            float x = __uint_as_float(r[c]);
-                            if (epi == 0) { x += __ldg(bias + c); x = x > 0.f ? x : 0.2f * x; }
-                            else {
-                                const uint32_t hb = (aw[p] >> (16 * e)) & 0xFFFFu;       // bf16 bits of the forward activation
-                                const bool pos = hb != 0u && (hb & 0x8000u) == 0u && hb != 0x8000u;
-                                x *= pos ? 1.f : 0.2f;
-                            }
-                            v[e] = interior ? x : 0.f;
-                            if (out_f32) out_f32[row * CT_C + c] = v[e];
-                        }
-                        uint32_t h0, l0, h1, l1;
-                        split_bf16(v[0], h0, l0);
-                        split_bf16(v[1], h1, l1);
-                        hw[p] = h0 | (h1 << 16);
-                        lw[p] = l0 | (l1 << 16);
+            for (int p = 0; p < 4; ++p) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = c8 * 8 + p * 2 + e;
+                    float x = __uint_as_float(r[c]);
+                    if (epi == 0) { x += __ldg(bias + c0 + c); x = x > 0.f ? x : 0.2f * x; }
+                    else {
+                        const uint32_t hb = (aw[p] >> (16 * e)) & 0xFFFFu;       // bf16 bits of the forward activation
+                        const bool pos = hb != 0u && (hb & 0x8000u) == 0u;
+                        x *= pos ? 1.f : 0.2f;
                     }
-                    oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    v[e] = interior ? x : 0.f;
+                    if (out_f32) out_f32[row * CT_C + c0 + c] = v[e];
                 }
+                uint32_t h0, l0, h1, l1;
+                split_bf16(v[0], h0, l0);
+                split_bf16(v[1], h1, l1);
+                hw[p] = h0 | (h1 << 16);
+                lw[p] = l0 | (l1 << 16);
             }
+            oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+    }
 }
 
 // epi: 0 = bias + LeakyReLU (forward), 1 = multiply by LeakyReLU'(aux) (input gradient)
@@ -280,8 +282,10 @@ constexpr size_t CW_SMEM = 1024 + CW_NW * CW_WSLOT + CW_NA * CT_STAGE_BYTES2 + 2
 // STACK: the MMA atom M128 x N64 x K16 reads 6 KB of shared memory for 32 cycles of math (128 B/clk => 48 cycles): operand-bandwidth
 // bound.  Stacking [W_hi ; W_lo] (adjacent 64-row tiles = one 128-row K-major operand) turns the two products that share A_hi into ONE
 // N=128 MMA whose halves [hi*hi | hi*lo] are summed in the epilogue: A_hi is read once instead of twice (14 KB instead of 18 KB per K step).
-template <bool STACK>
-__global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+// NEPI epilogue warps (4: one per TMEM lane quarter; 8: two per quarter, 32 channels each -- with 4, every SM sub-partition runs ONE
+// epilogue warp with no latency hiding and the ~800-instruction epilogue, not the MMAs, paces the tile).
+template <bool STACK, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_ws(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                        const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                                        const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
                                                        __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 10; ++i) mb_init(s_u32(&bars[i]), 1);
-        mb_init(s_u32(&bars[10]), 4); mb_init(s_u32(&bars[11]), 4);
+        mb_init(s_u32(&bars[10]), NEPI); mb_init(s_u32(&bars[11]), NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
@@ -376,13 +380,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_ws(const __grid_constant__ C
         }
     } else {
         const int lq = warp & 3;
+        const int c0 = NEPI == 8 ? ((warp - 2) >> 2) * 32 : 0;
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int acc = lt & 1;
             const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
             mb_wait(s_u32(&bars[8 + acc]), (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            conv_tc_epilogue<STACK>(tmem_base, acc, s_u32(&bars[10 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi, out_hi, out_lo, out_f32);
+            conv_tc_epilogue<STACK, NEPI == 8 ? 32 : 64>(tmem_base, acc, s_u32(&bars[10 + acc]), lq, lane, n, q0, qend, W, Wp, PS, epi, bias, aux_hi,
+                                                          out_hi, out_lo, out_f32, c0);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -587,11 +593,11 @@ static int g_conv_tc = -1;      // 0 = CUDA-core fp32; 1 = tensor cores, row-reu
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : (strcmp(e, "tc_stack") == 0 ? 4 : 1))));
+        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : (strcmp(e, "tc_stack") == 0 ? 4 : (strcmp(e, "tc_epi8") == 0 ? 5 : 1)))));
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 4 ? 4 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 5 ? 5 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -629,8 +635,9 @@ int enc_tc_create(ConvNet* n) {
     t->sm_count = prop.multiProcessorCount;
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
-    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
-    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -650,8 +657,9 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 4) k_conv_tc_ws<true><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else if (g_conv_tc == 3) k_conv_tc_ws<false><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 5) k_conv_tc_ws<true, 8><<<grid, 320, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 4) k_conv_tc_ws<true, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 3) k_conv_tc_ws<false, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
