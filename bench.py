@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--cpu-iters', type=int, default=8, help='timed CPU-baseline iterations (bounded sample)')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-perframe', action='store_true')
+    ap.add_argument('--skip-prox', action='store_true')
     return ap.parse_args()
 
 
@@ -332,6 +333,51 @@ def main():
                     'frame_iterations_per_sec': S * Tp * it_pf / (pf_ms * 1e-3), 'us_per_iteration': 1e3 * pf_ms / (Tp * it_pf),
                     'clips_per_sec': S / (pf_ms * 1e-3)}
 
+    # ---------------- secondary: PROX stage-2 iteration (BASELINE configs[3] + contact on): B=100 window, full mesh, 256^3 SDF, 100k scene points
+    prox = None
+    if rank == 0 and not a.skip_prox:
+        from lemo_b200.temp_prox.camera import PerspectiveCamera
+        from lemo_b200.temp_prox.fitting_temp_slide import SMPLifyLoss
+        Bp = 100
+        Pp, cfgp = synth.make_prox_problem(Bp, D=256, m_scene=100000, seed=3)
+        body.joint_mapper = None
+        Rc, tc_, fx, fy, cc = cfgp['camera']
+        cam = PerspectiveCamera(rotation=Rc[None].repeat(Bp, 1, 1), translation=tc_[None].repeat(Bp, 1), focal_length_x=fx, focal_length_y=fy,
+                                batch_size=Bp, center=cc[None].repeat(Bp, 1)).to(dev)
+        lossf = SMPLifyLoss(cfgp['w'], cam, cfgp['cam2world'], cfgp['sdf'].to(dev), cfgp['grid_min'], cfgp['grid_max'], cfgp['fric_ids'].to(dev),
+                            cfgp['contact_ids'].to(dev), cfgp['scene_v'].to(dev), torch.from_numpy(tables['markers81']).long().to(dev), enc,
+                            torch.from_numpy(tables['smooth_Xmean']).view(1, 1, 243).to(dev), torch.from_numpy(tables['smooth_Xstd']).to(dev),
+                            cfgp['joint_weights'].to(dev))
+        keys = ['transl', 'global_orient', 'pose_embedding', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression']
+        Pg = {k: torch.from_numpy(v).to(dev).requires_grad_(k in keys) for k, v in Pp.items()}
+        opt = torch.optim.Adam([Pg[k] for k in keys], lr=0.005)
+        jmap = cfgp['joint_map'].to(dev)
+        gtj, gtc = cfgp['gt_joints'].to(dev), cfgp['joints_conf'].to(dev)
+
+        def prox_iter():
+            opt.zero_grad()
+            Rb = vp.decode(Pg['pose_embedding'], 'matrot').reshape(Bp, 21, 9)
+            kw = {k: Pg[k] for k in ('transl', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression', 'betas')}
+            out = body(return_verts=True, return_full_pose=True, R_body=Rb, **kw)
+            raw = out.joints
+            out = out._replace(joints=raw[:, jmap])
+            tot, _ = lossf(out, raw, gtj, gtc, Pg['pose_embedding'])
+            tot.backward()
+            opt.step()
+        for _ in range(3):
+            prox_iter()
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            prox_iter()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        pms = c0.elapsed_time(c1) / 10
+        prox = {'workload': 'PROXD_temp_S2-shaped window: B=100, full mesh, keypoints + priors + SDF 256^3 penetration + friction + Chamfer contact '
+                            '(1121 x 100k, shared scene) + Enc smoothness, Adam; SMPL-X evaluated once', 'ms_per_iteration': pms,
+                'iterations_per_sec': 1e3 / pms, 'note': 'operators = lemo kernels; loss glue + optimizer still PyTorch (DESIGN.md section 7)'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -343,7 +389,7 @@ def main():
             'data': 'synthetic', 'config': workload_config(a, world), 'clocks': clocks,
             'e2e': {'value': e2e_rate, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(h_loss.numel() + h_par.numel()) * 4},
             'gpu_launches': int(launches), 'roofline': roof, 'roofline_lbs': roof_lbs,
-            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'], 'perframe': perframe,
+            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'], 'perframe': perframe, 'prox': prox,
             'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}}
     print(json.dumps(line), flush=True)
     if world > 1:

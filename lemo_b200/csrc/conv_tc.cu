@@ -589,11 +589,14 @@ static int zalloc(T** p, size_t n) {
     return 0;
 }
 
-static int g_conv_tc = -1;      // 0 = CUDA-core fp32; 1 = tensor cores, row-reuse (default); 2 = one TMA box per tap; 3 = row-reuse + streamed weights
+// 0 = CUDA-core fp32 path (conv.cu).  Tensor-core variants, in the order they were developed and measured on B200 (64->64 layer,
+// S=8, T=120; tools/diag_conv_modes.py): 2 = one TMA box per tap, resident weights (92.6 us); 3 = row reuse (76.7 us);
+// 4 = + streamed weights, 3 A stages (71.2 us); 5 = + stacked [W_hi;W_lo] N=128 MMA (68.9 us); 1 = DEFAULT = + 8 epilogue warps (61.8 us).
+static int g_conv_tc = -1;
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = !e ? 1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc_pertap") == 0 ? 2 : (strcmp(e, "tc_ws") == 0 ? 3 : (strcmp(e, "tc_stack") == 0 ? 4 : (strcmp(e, "tc_epi8") == 0 ? 5 : 1)))));
+        g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
@@ -657,11 +660,11 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 5) k_conv_tc_ws<true, 8><<<grid, 320, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else if (g_conv_tc == 4) k_conv_tc_ws<true, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else if (g_conv_tc == 3) k_conv_tc_ws<false, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 5) k_conv_tc_ws<true, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 4) k_conv_tc_ws<false, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else if (g_conv_tc == 3) k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else k_conv_tc_ws<true, 8><<<grid, 320, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }

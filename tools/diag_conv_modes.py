@@ -10,7 +10,7 @@ enc = load_smooth_prior().to(dev)
 x = torch.from_numpy(g['enc_full_x']).to(dev).repeat(8, 1, 1, 1).contiguous()
 ref = torch.from_numpy(g['enc_full_z_sub'])
 net = enc.net(torch.device(dev), 8, 245, 134)
-for mode, name in ((0, 'simt'), (2, 'tc per-tap'), (1, 'tc row-reuse (default)'), (3, 'tc row-reuse + streamed weights, 3 stages'), (4, 'tc ... + stacked [Whi;Wlo] N=128'), (5, 'tc ... + 8 epilogue warps')):
+for mode, name in ((0, 'simt fp32'), (2, 'tc per-tap'), (3, 'tc row-reuse'), (4, 'tc + streamed weights, 3 stages'), (5, 'tc + stacked [Whi;Wlo] N=128'), (1, 'tc + 8 epilogue warps (default)')):
     _lib.call('lemo_debug_set_conv_tc', mode)
     z = enc(x)[0]
     torch.cuda.synchronize()
