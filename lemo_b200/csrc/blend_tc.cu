@@ -23,6 +23,7 @@ constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_B_BYTES;     // X_hi block, X
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_OUT_PITCH = TC_BN + 1;
 constexpr size_t TC_SMEM = 1024 /*align slack*/ + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/;
+static_assert(2 * (TC_STAGE_BYTES + TC_B_BYTES) <= TC_STAGES * TC_STAGE_BYTES, "the 3-term variant (2 stages of 88 KB) must fit in the same buffer");
 static_assert((size_t)TC_BM * TC_OUT_PITCH * 4 <= (size_t)TC_STAGES * TC_STAGE_BYTES, "epilogue staging reuses the pipeline buffers");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,10 +67,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// The same kernel is the generic TF32 GEMM of the library: C[M,N] = epi( [A_hi | A_lo][M, lo_col + K] . B[N,K]^T ), used for the VPoser
+// MLP and its adjoint (vposer.cu) with bias / LeakyReLU / LeakyReLU' epilogues and an optional (hi|lo)-split copy of the result that
+// feeds the next layer's A operand.
+// three != 0: a second B tensor map_wlo = B - rn_tf32(B) is loaded next to every B block and a third MMA (A_hi . B_lo) is issued,
+// i.e. the full 3-term split A_hi B_hi + A_lo B_hi + A_hi B_lo (fp32-grade; used where the result is not diluted by a larger term).
 __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                                                       float* __restrict__ VP, int B, int N, int K) {
+                                                       const __grid_constant__ CUtensorMap map_wlo, float* __restrict__ VP, int B, int N, int K,
+                                                       int lo_col, int three, TcEpi ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
+    const int stage_bytes = three ? TC_STAGE_BYTES + TC_B_BYTES : TC_STAGE_BYTES;
+    const int nstages = three ? 2 : TC_STAGES;                                         // 2 x 88 KB or 3 x 60 KB
     uint64_t* bars = (uint64_t*)(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
     // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full, then the TMEM base address slot
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
@@ -97,14 +106,15 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
         // ===================== TMA producer =====================
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+                const int s = kb % nstages;
+                const uint32_t ph = (kb / nstages) & 1;
                 mbar_wait(smem_u32(&bars[TC_STAGES + s]), ph ^ 1);                  // slot free (first pass returns immediately)
                 const uint32_t full = smem_u32(&bars[s]);
-                mbar_expect_tx(full, TC_STAGE_BYTES);
-                const uint32_t a_dst = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+                mbar_expect_tx(full, stage_bytes);
+                const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+                if (three) tma_load_2d(a_dst + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, full, kb * TC_BK, n0);
                 tma_load_2d(a_dst, &map_x, full, kb * TC_BK, m0);                   // X_hi block
-                tma_load_2d(a_dst + TC_A_BYTES, &map_x, full, K + kb * TC_BK, m0);  // X_lo block
+                tma_load_2d(a_dst + TC_A_BYTES, &map_x, full, lo_col + kb * TC_BK, m0);  // X_lo block
                 tma_load_2d(a_dst + 2 * TC_A_BYTES, &map_w, full, kb * TC_BK, n0);
             }
         }
@@ -113,11 +123,12 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+                const int s = kb % nstages;
+                const uint32_t ph = (kb / nstages) & 1;
                 mbar_wait(smem_u32(&bars[s]), ph);                                  // TMA bytes have landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t blo = umma_desc_sw128(a_addr + 2 * TC_A_BYTES + TC_B_BYTES);
                 const uint64_t ahi = umma_desc_sw128(a_addr), alo = umma_desc_sw128(a_addr + TC_A_BYTES);
                 const uint64_t bdesc = umma_desc_sw128(a_addr + 2 * TC_A_BYTES);
 #pragma unroll
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
                     const uint64_t off = (uint64_t)(k * TC_UMMA_K * 4 >> 4);
                     umma_tf32(tmem_base, ahi + off, bdesc + off, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_tf32(tmem_base, alo + off, bdesc + off, idesc, 1u);
+                    if (three) umma_tf32(tmem_base, ahi + off, blo + off, idesc, 1u);
                 }
                 umma_commit(smem_u32(&bars[TC_STAGES + s]));                        // frees the smem slot when these MMAs retire
             }
@@ -159,9 +171,21 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
             const int gr = m0 + lq * 32 + rr;
             if (gr >= B) break;
             const float* src = s_out + (lq * 32 + rr) * TC_OUT_PITCH;
-            float* dst = VP + (size_t)gr * N + n0;
-            for (int c = lane; c < TC_BN; c += 32)
-                if (n0 + c < N) dst[c] = src[c];
+            const long long ldc = ep.ldc ? ep.ldc : N;
+            for (int c = lane; c < TC_BN; c += 32) {
+                const int gc = n0 + c;
+                if (gc >= N) continue;
+                float v = src[c];
+                if (ep.bias) v += ep.bias[gc];
+                if (ep.act == 1) v = v > 0.f ? v : 0.2f * v;
+                else if (ep.act == 2) v *= ep.mask_src[(size_t)gr * ldc + gc] > 0.f ? 1.f : 0.2f;
+                if (VP) VP[(size_t)gr * ldc + gc] = v;
+                if (ep.split_out) {               // (hi|lo) TF32 split of the result = A operand of the next GEMM
+                    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                    ep.split_out[(size_t)gr * ep.split_ld + gc] = hi;
+                    ep.split_out[(size_t)gr * ep.split_ld + ep.split_lo + gc] = v - hi;
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -202,14 +226,41 @@ int make_kmajor_map(void* out_map /*CUtensorMap, 128 B*/, const float* base, lon
 int blend_tc_map_x(const float* X2, int maxB, void* map_x) { return make_kmajor_map(map_x, X2, maxB, 2 * XK, TC_BM); }
 int blend_tc_map_w(const float* WtT, int N, void* map_w) { return make_kmajor_map(map_w, WtT, N, XK, TC_BN); }
 
-int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st) {
+int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N, int K, int lo_col, const TcEpi& ep, cudaStream_t st,
+                   const void* map_b_lo) {
     static bool configured = false;
     if (!configured) {
         LEMO_CUDA(cudaFuncSetAttribute(k_blend_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         configured = true;
     }
-    dim3 grid(cdiv(N, TC_BN), cdiv(B, TC_BM));
-    k_blend_tf32<<<grid, 192, TC_SMEM, st>>>(*(const CUtensorMap*)map_x, *(const CUtensorMap*)map_w, VP, B, N, XK);
+    LEMO_CHECK(K % TC_BK == 0 && K > 0, "tc_gemm: K must be a positive multiple of 32");
+    dim3 grid(cdiv(N, TC_BN), cdiv(M, TC_BM));
+    k_blend_tf32<<<grid, 192, TC_SMEM, st>>>(*(const CUtensorMap*)map_a, *(const CUtensorMap*)map_b,
+                                             *(const CUtensorMap*)(map_b_lo ? map_b_lo : map_b), C, M, N, K, lo_col, map_b_lo ? 1 : 0, ep);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st) {
+    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, TcEpi{}, st, nullptr);
+}
+int tc_map_a(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BM); }
+int tc_map_b(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BN); }
+
+// dst[n][kpad] = rn_tf32(src) with optional transpose: src is [rows_src][cols_src] row-major; transpose=0: dst[n=r][k=c]; 1: dst[n=c][k=r]
+__global__ void k_tc_prep_b(const float* __restrict__ src, int rows_src, int cols_src, int transpose, int kpad, float* __restrict__ dst,
+                            float* __restrict__ dst_lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_src * cols_src) return;
+    const int r = i / cols_src, c = i - r * cols_src;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(src[i]));
+    const float v = __uint_as_float(t);
+    const size_t o = !transpose ? (size_t)r * kpad + c : (size_t)c * kpad + r;
+    dst[o] = v;
+    if (dst_lo) dst_lo[o] = src[i] - v;
+}
+int tc_prep_b(const float* src, int rows_src, int cols_src, int transpose, int kpad, float* dst, cudaStream_t st, float* dst_lo) {
+    k_tc_prep_b<<<cdiv(rows_src * cols_src, 256), 256, 0, st>>>(src, rows_src, cols_src, transpose, kpad, dst, dst_lo);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }

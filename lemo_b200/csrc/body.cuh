@@ -107,6 +107,20 @@ int body_grad_begin(BodyCtx* pose_src, int B, cudaStream_t st);
 int body_skin_backward(BodyCtx* c, BodyCtx* pose_src, int B, const float* d_verts, const float* d_joints, cudaStream_t st);
 int body_pose_backward(BodyCtx* c, const PoseIn& in, int B, const PoseGrad& g, cudaStream_t st);
 
+// generic TF32 tensor-core GEMM (blend_tc.cu): epilogue options
+struct TcEpi {
+    const float* bias = nullptr;       // [N]
+    const float* mask_src = nullptr;   // act == 2: [M, ldc], factor = mask_src > 0 ? 1 : 0.2
+    int act = 0;                       // 0 none, 1 LeakyReLU(0.2), 2 LeakyReLU' mask
+    long long ldc = 0;                 // row pitch of C / mask_src (0 = N)
+    float* split_out = nullptr;        // optional [M, split_ld]: hi at column n, lo at column split_lo + n
+    long long split_ld = 0, split_lo = 0;
+};
+int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N, int K, int lo_col, const TcEpi& ep, cudaStream_t st,
+                   const void* map_b_lo = nullptr);   // map_b_lo: B - rn_tf32(B) => fp32-grade 3-term product
+int tc_map_a(void* map, const float* base, long long rows, int cols);     // A operand [rows, cols], 128-row boxes
+int tc_map_b(void* map, const float* base, long long rows, int cols);     // B operand [rows = N, cols = K], 224-row boxes
+int tc_prep_b(const float* src, int rows_src, int cols_src, int transpose, int kpad, float* dst, cudaStream_t st, float* dst_lo = nullptr);
 // tcgen05 blend GEMM (blend_tc.cu)
 int blend_tc_map_x(const float* X2, int maxB, void* map_x);
 int blend_tc_map_w(const float* WtT, int N, void* map_w);
