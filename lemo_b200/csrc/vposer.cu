@@ -7,6 +7,8 @@
 #include "gemm.cuh"
 #include "vposer.cuh"
 #include "body.cuh"
+#include <cstdlib>
+#include <cstring>
 #include "../../include/lemo_b200.h"
 
 namespace lemo {
@@ -102,9 +104,19 @@ void vposer_free(VPoser* v) {
     delete v;
 }
 
+// The TF32 tensor-core path is OFF by default (LEMO_VPOSER=tc enables it): measured on B200 it is both slower at the fit's shapes
+// (M = 960, N = 512 gives 24 CTAs of 128x224 against 120 CTAs for the CUDA-core GEMM: 2.24 vs 2.03 ms per fitting step) and less
+// accurate (R_body 4e-5 vs 1e-6 of max even with the exact 3-term split -- the tensor core's fp32 accumulation itself is only good to
+// ~1e-5 over K = 512), and the rotations it produces are NOT diluted by a larger term the way blend-shape offsets are.
+static bool vposer_tc_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("LEMO_VPOSER"); on = (e && strcmp(e, "tc") == 0) ? 1 : 0; }
+    return on == 1;
+}
+
 int vposer_decode(VPoser* v, const float* z, int B, float* R_body, float* aa, cudaStream_t st) {
     LEMO_CHECK(v && z && R_body && B > 0 && B <= v->maxB, "bad arguments / batch exceeds handle size");
-    if (v->has_tc && blend_tc_enabled()) {
+    if (v->has_tc && vposer_tc_enabled()) {
         // TF32 tensor-core MLP: A operands are exact (hi|lo) splits, weights are rounded once to TF32
         k_vp_split<<<cdiv(B * 32, 256), 256, 0, st>>>(z, B, 32, 32, v->zs);
         TcEpi e1; e1.bias = v->b1; e1.act = 1; e1.split_out = v->h1s; e1.split_ld = 1024; e1.split_lo = 512;
@@ -128,7 +140,7 @@ int vposer_decode(VPoser* v, const float* z, int B, float* R_body, float* aa, cu
 int vposer_decode_backward(VPoser* v, const float* z, int B, const float* dR_body, float* dz, cudaStream_t st) {
     LEMO_CHECK(v && dR_body && dz && B > 0 && B <= v->maxB, "bad arguments / batch exceeds handle size");
     (void)z;
-    const bool tc = v->has_tc && blend_tc_enabled();
+    const bool tc = v->has_tc && vposer_tc_enabled();
     k_vp_gs_bwd<<<cdiv(B * NBODY, 128), 128, 0, st>>>(v->o, dR_body, B * NBODY, v->d_o, tc ? v->dos : nullptr);
     LEMO_CUDA(cudaGetLastError());
     if (tc) {
