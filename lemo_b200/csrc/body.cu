@@ -419,13 +419,15 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
     __shared__ float sdJ[NJ][3];      // dL/dJrest
     __shared__ float sC[NJ][15];      // per-joint contribution to its parent: dG (12) + dJrest[parent] (3)
     __shared__ int spar[NJ];
+    __shared__ float sG[NJ][12];      // global transforms of this frame (parents are read from here, not from HBM, inside the level loop)
+    __shared__ float sJr[NJ][3];
     const int b = blockIdx.x, j = threadIdx.x;
     float r[9], gl[12], Jr[3];
     int par = -1, dep = 0;
     if (j < NJ) {
         for (int k = 0; k < 9; ++k) r[k] = R[((size_t)b * NJ + j) * 9 + k];
-        for (int k = 0; k < 12; ++k) gl[k] = G[((size_t)b * NJ + j) * 12 + k];
-        for (int k = 0; k < 3; ++k) Jr[k] = Jrest[((size_t)b * NJ + j) * 3 + k];
+        for (int k = 0; k < 12; ++k) sG[j][k] = gl[k] = G[((size_t)b * NJ + j) * 12 + k];
+        for (int k = 0; k < 3; ++k) sJr[j][k] = Jr[k] = Jrest[((size_t)b * NJ + j) * 3 + k];
         par = parents[j]; dep = depth[j];
         const float* da = dA + (size_t)j * B * 12 + (size_t)b * 12;
         float dAt[3] = {da[3], da[7], da[11]};
@@ -439,15 +441,19 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
     }
     if (j < NJ) spar[j] = par;
     __syncthreads();
+    unsigned long long kids = 0ull;   // children of joint j as a bit mask, walked in ascending order below
+    if (j < NJ)
+        for (int c = j + 1; c < NJ; ++c)
+            if (spar[c] == j) kids |= 1ull << c;
     // children -> parent accumulation in a FIXED order (no shared-memory atomics): results are bitwise reproducible,
     // which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same parameters).
     for (int lev = max_depth; lev >= 1; --lev) {
         if (j < NJ && dep == lev) {
-            const float* gp = G + ((size_t)b * NJ + par) * 12;        // parent's global transform
+            const float* gp = sG[par];                                // parent's global transform
             float gpR[9] = {gp[0], gp[1], gp[2], gp[4], gp[5], gp[6], gp[8], gp[9], gp[10]};
             float dGr[9] = {sdG[j][0], sdG[j][1], sdG[j][2], sdG[j][4], sdG[j][5], sdG[j][6], sdG[j][8], sdG[j][9], sdG[j][10]};
             float dGt[3] = {sdG[j][3], sdG[j][7], sdG[j][11]};
-            const float* Jp = Jrest + ((size_t)b * NJ + par) * 3;
+            const float* Jp = sJr[par];
             const float t[3] = {Jr[0] - Jp[0], Jr[1] - Jp[1], Jr[2] - Jp[2]};
             float dr[9], dpr[9], dt[3];
             m3_mul_at(gpR, dGr, dr);               // dR_j = Gp.R^T dG_j.R
@@ -465,8 +471,8 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
         }
         __syncthreads();
         if (j < NJ && dep == lev - 1) {
-            for (int c = j + 1; c < NJ; ++c) {
-                if (spar[c] != j) continue;
+            for (unsigned long long m = kids; m; m &= m - 1) {
+                const int c = __ffsll((long long)m) - 1;
                 for (int k = 0; k < 12; ++k) sdG[j][k] += sC[c][k];
                 for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
             }

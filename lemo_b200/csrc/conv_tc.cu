@@ -397,9 +397,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_ws(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ SIMT helpers (first / last layer, loss)
-// layer 0 (1 -> 32 channels): x planar fp32 [N][1][PS] -> NHWC (hi,lo) rows, channels 32..63 stay zero
+// layer 0 (1 -> 32 channels): x planar fp32 [N][1][PS] -> NHWC (hi,lo) rows, channels 32..63 stay zero.
+// One thread per pixel; weights in shared memory; the 32 outputs leave as 4 + 4 16-byte stores (64 B of hi, 64 B of lo per pixel).
 __global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, const float* __restrict__ w /*[32][1][9]*/, const float* __restrict__ b,
                                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int H, int W, int Wp, int PS) {
+    __shared__ float s_w[32 * 9 + 32];
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) s_w[i] = w[i];
+    if (threadIdx.x < 32) s_w[288 + threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
     const int n = blockIdx.y;
     const int q = Wp + blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (H + 1) * Wp) return;
@@ -408,23 +413,31 @@ __global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, c
     float xin[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) xin[k] = x[(size_t)n * PS + q + (k / 3 - 1) * Wp + (k % 3 - 1)];
-    uint32_t* oh = reinterpret_cast<uint32_t*>(out_hi + ((size_t)n * PS + q) * CT_C);
-    uint32_t* ol = reinterpret_cast<uint32_t*>(out_lo + ((size_t)n * PS + q) * CT_C);
-    for (int c = 0; c < 32; c += 2) {
-        float v[2];
+    uint4* oh = reinterpret_cast<uint4*>(out_hi + ((size_t)n * PS + q) * CT_C);
+    uint4* ol = reinterpret_cast<uint4*>(out_lo + ((size_t)n * PS + q) * CT_C);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float a = __ldg(b + c + e);
+    for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t hw[4], lw[4];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a = fmaf(__ldg(w + (c + e) * 9 + k), xin[k], a);
-            a = a > 0.f ? a : 0.2f * a;
-            v[e] = interior ? a : 0.f;
+        for (int p = 0; p < 4; ++p) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = c8 * 8 + p * 2 + e;
+                float a = s_w[288 + c];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a = fmaf(s_w[c * 9 + k], xin[k], a);
+                a = a > 0.f ? a : 0.2f * a;
+                v[e] = interior ? a : 0.f;
+            }
+            uint32_t h0, l0, h1, l1;
+            split_bf16(v[0], h0, l0);
+            split_bf16(v[1], h1, l1);
+            hw[p] = h0 | (h1 << 16);
+            lw[p] = l0 | (l1 << 16);
         }
-        uint32_t h0, l0, h1, l1;
-        split_bf16(v[0], h0, l0);
-        split_bf16(v[1], h1, l1);
-        oh[c >> 1] = h0 | (h1 << 16);
-        ol[c >> 1] = l0 | (l1 << 16);
+        oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
 }
 // input gradient of layer 0 (32 -> 1): dpre NHWC (hi,lo) -> dx planar fp32.
@@ -478,7 +491,8 @@ __global__ void __launch_bounds__(256) k_tc_last_bwd(const __nv_bfloat16* __rest
     }
     dx[(size_t)n * PS + q] = a;
 }
-// smoothness loss on the fp32 NHWC output + dpre of the last layer in (hi,lo) form (same math as fit.cu:k_smooth_loss)
+// smoothness loss on the fp32 NHWC output + dpre of the last layer in (hi,lo) form (same math as fit.cu:k_smooth_loss).
+// One thread per (pixel, 8 channels): float4 loads of z[q-1], z[q], z[q+1], one 16-byte store per plane.
 __global__ void __launch_bounds__(256) k_tc_smooth_loss(const float* __restrict__ zf, int H, int W, int Wp, int PS, float w, int acc_stride,
                                                         int acc_slot, __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
                                                         float* __restrict__ acc) {
@@ -486,23 +500,40 @@ __global__ void __launch_bounds__(256) k_tc_smooth_loss(const float* __restrict_
     const int s = blockIdx.y;
     const float inv_n = 1.f / (64.f * (float)H * (float)(W - 1));
     float part = 0.f;
-    const long long tot = (long long)H * Wp * 64;
+    const long long tot = (long long)H * Wp * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i & 63);
-        const int q = Wp + (int)(i >> 6);
+        const int c8 = (int)(i & 7);
+        const int q = Wp + (int)(i >> 3);
         const int col = q % Wp, x = col - 1;
-        const size_t o = ((size_t)s * PS + q) * 64 + c;
-        float g = 0.f;
+        const size_t o = ((size_t)s * PS + q) * 64 + c8 * 8;
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
         if (x >= 0 && x < W) {
-            const float zc = zf[o];
-            if (x >= 1) g += zc - zf[o - 64];
-            if (x <= W - 2) { const float d = zf[o + 64] - zc; g -= d; part += d * d; }
-            g = w * 2.f * inv_n * g * (zc > 0.f ? 1.f : 0.2f);
+            float zc[8], zl[8], zr[8];
+            *reinterpret_cast<float4*>(zc) = *reinterpret_cast<const float4*>(zf + o);
+            *reinterpret_cast<float4*>(zc + 4) = *reinterpret_cast<const float4*>(zf + o + 4);
+            if (x >= 1) { *reinterpret_cast<float4*>(zl) = *reinterpret_cast<const float4*>(zf + o - 64); *reinterpret_cast<float4*>(zl + 4) = *reinterpret_cast<const float4*>(zf + o - 60); }
+            if (x <= W - 2) { *reinterpret_cast<float4*>(zr) = *reinterpret_cast<const float4*>(zf + o + 64); *reinterpret_cast<float4*>(zr + 4) = *reinterpret_cast<const float4*>(zf + o + 68); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+                if (x >= 1) a += zc[j] - zl[j];
+                if (x <= W - 2) { const float d = zr[j] - zc[j]; a -= d; part += d * d; }
+                g[j] = w * 2.f * inv_n * a * (zc[j] > 0.f ? 1.f : 0.2f);
+            }
         }
-        uint32_t h, l;
-        split_bf16(g, h, l);
-        g_hi[o] = __ushort_as_bfloat16((unsigned short)h);
-        g_lo[o] = __ushort_as_bfloat16((unsigned short)l);
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t h0, l0, h1, l1;
+            split_bf16(g[2 * p], h0, l0);
+            split_bf16(g[2 * p + 1], h1, l1);
+            hw[p] = h0 | (h1 << 16);
+            lw[p] = l0 | (l1 << 16);
+        }
+        *reinterpret_cast<uint4*>(g_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(g_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
     part = block_sum(part, sred);
     if (threadIdx.x == 0) atomicAdd(&acc[s * acc_stride + acc_slot], part * inv_n);
