@@ -215,6 +215,9 @@ int lemo_fit_destroy(LemoFit* fit);
  * target markers [T,67,3], contact labels [T,4].  Temporal mode.  (opt_amass_temp.py:253,329-341) */
 int lemo_fit_set_sequence(LemoFit* fit, int32_t s, const float* init72, const float* markers_rec, const float* contact,
                           void* stream);
+/* all S sequences of the handle in one call: init72 [S,T,72], markers_rec [S,T,67,3], contact [S,T,4] (device pointers); two copies and
+ * one kernel instead of 3 S launches -- the batched form of the per-sequence loads of opt_amass_temp.py:253,329-341.  Temporal mode. */
+int lemo_fit_set_sequences(LemoFit* fit, const float* init72, const float* markers_rec, const float* contact, void* stream);
 /* n_iters Adam iterations with the script's LR schedule (lr0 until step>lr_switch, then lr1).
  * Entirely on device: no host synchronisation inside. */
 int lemo_fit_run(LemoFit* fit, int32_t n_iters, float lr0, float lr1, int32_t lr_switch, void* stream);

@@ -119,6 +119,7 @@ SIGNATURES = {
     'lemo_fit_create': (C.c_int, [_P, _P, _P, _P, C.POINTER(LemoFitConfigC), C.c_int, C.POINTER(_P)]),
     'lemo_fit_destroy': (C.c_int, [_P]),
     'lemo_fit_set_sequence': (C.c_int, [_P, _I, _P, _P, _P, _P]),
+    'lemo_fit_set_sequences': (C.c_int, [_P, _P, _P, _P, _P]),
     'lemo_fit_run': (C.c_int, [_P, _I, _F, _F, _I, _P]),
     'lemo_fit_run_perframe': (C.c_int, [_P, _I, _P]),
     'lemo_fit_get': (C.c_int, [_P, _P, _P, _P]),

@@ -108,7 +108,7 @@ __device__ __forceinline__ void conv_tc_epilogue(uint32_t tmem_base, int acc, ui
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
-    if (lane == 0) mb_arrive(empty_bar);                  // this warp's share of the accumulator is free
+    if (lane == 0 && empty_bar) mb_arrive(empty_bar);     // this warp's share of the accumulator is free (0: caller arrives later)
     const int q = q0 + lq * 32 + lane;
     if (q < qend) {
         const int col = q % Wp;
@@ -396,6 +396,234 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_ws(const __grid_c
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(STACK ? 256 : 128) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ pair variant
+// ncu on k_conv_tc_ws<1,8> (profiles/r01_ncu_full_summary.md): tensor pipe 47 % active, operand reads 51 %, L2 45 % -- nothing saturated;
+// the warp-stall samples sit in the EPILOGUE warps (only 13 % of their samples wait for an accumulator): the ~1000-instruction epilogue
+// (runtime `epi` switch, per-channel bias LDGs, scalar F2F conversions, aux loads issued after the wait) paces the tile, the MMA warp
+// waits for a free accumulator.  This variant attacks both ends:
+//   * one 48 KB weight slot serves TWO consecutive 128-pixel tiles (per ky step: W(ky) + A(ky, tile 0), then A(ky, tile 1)); the four
+//     stacked accumulators (2 tiles x 2 buffers x 128 columns) fill TMEM's 512 columns exactly; L2->SMEM traffic per tile drops from
+//     246 KB to 174 KB;
+//   * EPI / F32OUT are template parameters, the bias lives in registers, the forward activation bits (aux) are fetched BEFORE the wait
+//     on the accumulator, the (hi,lo) split uses the packed F2FP conversion (2 values per instruction) and every accumulator half has its
+//     own full/empty barrier so the epilogue of tile 0 starts while tile 1 still runs.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// two fp32 values -> packed bf16 hi pair and packed bf16 lo pair (bit-identical to two split_bf16 calls)
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hw, uint32_t& lw) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    hw = *reinterpret_cast<const uint32_t*>(&h2);
+    const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xFFFF0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+    lw = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
+template <int NEPI, int EPI, bool F32OUT>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_pair(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                         const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                                                         const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
+                                                         __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
+                                                         int Wp, int PS, int dbg) {
+    constexpr int NCH = 256 / NEPI;                       // channels per epilogue thread: 32 (8 warps) or 16 (16 warps)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + CW_NW * CW_WSLOT;
+    uint64_t* bars = (uint64_t*)(s_a + CW_NA * CT_STAGE_BYTES2);
+    // bars: [0..2] A stage full (+ weight slot on the first half), [3..5] A empty, [6,7] W empty, [8..11] accumulator full (buffer*2 + half),
+    //       [12..15] accumulator empty
+    uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tps = (H * Wp + CT_M - 1) / CT_M;
+    const int ntiles = N * tps;
+    const int npairs = (ntiles + 1) >> 1;
+    const int qend = (H + 1) * Wp;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 12; ++i) mb_init(s_u32(&bars[i]), 1);
+        for (int i = 12; i < 16; ++i) mb_init(s_u32(&bars[i]), NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // Warps 0 and 1 run their loops CONVERGED (all 32 lanes wait on the barriers and compute the same addresses) and elect one lane
+    // only around the TMA / tcgen05 instructions: descriptors then live in uniform registers and every UTCHMMA issues back to back.
+    // With the whole loop under `if (lane == 0)` the compiler wrapped EACH UTCHMMA in an ELECT/R2UR/BRA.U.ANY "waterfall" loop --
+    // ~90 cycles of issue per MMA, which (not the tensor pipe, not shared memory, not L2) paced the earlier variants
+    // (tools/diag_conv_modes.py --experiments: time independent of the MMA shapes issued, halved by halving the MMA count).
+    if (warp == 0) {
+        uint32_t ia = 0, iw = 0;
+        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+            const int nh = 2 * pr + 1 < ntiles ? 2 : 1;
+            for (int ky = 0; ky < 3; ++ky, ++iw) {
+                const int sw = iw % CW_NW;
+                for (int h = 0; h < nh; ++h, ++ia) {
+                    const int tile = 2 * pr + h;
+                    const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+                    const int sa = ia % CW_NA;
+                    mb_wait(s_u32(&bars[3 + sa]), ((ia / CW_NA) & 1) ^ 1);
+                    if (h == 0) mb_wait(s_u32(&bars[6 + sw]), ((iw / CW_NW) & 1) ^ 1);
+                    const uint32_t full = s_u32(&bars[sa]);
+                    const int row = n * PS + q0 + (ky - 1) * Wp - 1;
+                    const uint32_t dst = s_u32(s_a + sa * CT_STAGE_BYTES2);
+                    const uint32_t wdst = s_u32(s_w + sw * CW_WSLOT);
+                    if (elect_one()) {
+                        if (dbg & 1) mb_arrive(full);                    // timing experiment: no loads
+                        else {
+                            mb_expect_tx(full, h == 0 ? CT_STAGE_BYTES2 + CW_WSLOT : CT_STAGE_BYTES2);
+                            tma2d(dst, &map_hi, full, 0, row);
+                            tma2d(dst + CT_A_TILE2, &map_lo, full, 0, row);
+                            if (h == 0)
+                                for (int t = 0; t < 6; ++t) tma2d(wdst + t * CT_W_TILE, &map_w, full, 0, (ky * 6 + t) * CT_C);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+        constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * CT_C >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+        uint32_t ia = 0, iw = 0, lt = 0;
+        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++lt) {
+            const int nh = 2 * pr + 1 < ntiles ? 2 : 1;
+            const int buf = lt & 1;
+            for (int ky = 0; ky < 3; ++ky, ++iw) {
+                const int sw = iw % CW_NW;
+                const uint32_t w0 = s_u32(s_w + sw * CW_WSLOT);
+                for (int h = 0; h < nh; ++h, ++ia) {
+                    const int sa = ia % CW_NA;
+                    const uint32_t d = tmem_base + (uint32_t)((buf * 2 + h) * 2 * CT_C);
+                    if (ky == 0) mb_wait(s_u32(&bars[12 + buf * 2 + h]), ((lt >> 1) & 1) ^ 1);
+                    mb_wait(s_u32(&bars[sa]), (ia / CW_NA) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = s_u32(s_a + sa * CT_STAGE_BYTES2);
+                    if (elect_one()) {
+                        const int reps = (dbg & 128) ? 2 : (dbg & 256) ? 4 : 1;      // timing experiment: repeat the step's MMAs
+                        if (!(dbg & 2)) for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint64_t ahi = desc_sw128(a0 + kx * 128), alo = desc_sw128(a0 + CT_A_TILE2 + kx * 128);
+                                const uint64_t whi = desc_sw128(w0 + (kx * 2) * CT_W_TILE);
+#pragma unroll
+                                for (int k = 0; k < CT_C / 16; ++k) {
+                                    const uint64_t o = (uint64_t)(k * 32 >> 4);
+                                    if (dbg >= 8) {                       // timing experiments on the tensor pipe (tools/diag_conv_modes.py)
+                                        constexpr uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+                                        const uint64_t a1 = (dbg & 16) ? desc_sw128(a0) + o : ahi + o;
+                                        // 512: rotate the destination over 4 accumulator blocks (independent accumulate chains)
+                                        const uint32_t dd = (dbg & 512) ? tmem_base + (uint32_t)(((kx + k) & 3) * 128) : d;
+                                        if (dbg & 32) mma_bf16(tmem_base + (uint32_t)(((dbg & 512) ? (k & 1) : buf) * 256), a1, desc_sw128(w0) + o, idesc256, 1u);
+                                        else {
+                                            if (!(dbg & 64)) mma_bf16(dd, a1, whi + o, idesc128, 1u);
+                                            if (!(dbg & 8)) mma_bf16((dbg & 512) ? dd + 64 : dd, (dbg & 16) ? desc_sw128(a0 + CT_A_TILE2) + o : alo + o, whi + o, idesc, 1u);
+                                        }
+                                        continue;
+                                    }
+                                    mma_bf16(d, ahi + o, whi + o, idesc128, (ky | kx | k) != 0 ? 1u : 0u);   // [hi*W_hi | hi*W_lo], N = 128
+                                    mma_bf16(d, alo + o, whi + o, idesc, 1u);                               // lo*W_hi into columns [0,64)
+                                }
+                            }
+                        }
+                        mma_commit(s_u32(&bars[3 + sa]));
+                        if (ky == 2) mma_commit(s_u32(&bars[8 + buf * 2 + h]));
+                        if (h == nh - 1) mma_commit(s_u32(&bars[6 + sw]));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int lq = warp & 3;
+        const int c0 = ((warp - 2) >> 2) * NCH;
+        float breg[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) breg[c] = EPI == 0 ? __ldg(bias + c0 + c) : 0.f;
+        uint32_t lt = 0;
+        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++lt) {
+            const int nh = 2 * pr + 1 < ntiles ? 2 : 1;
+            const int buf = lt & 1;
+            for (int h = 0; h < nh; ++h) {
+                const int tile = 2 * pr + h;
+                const int n = tile / tps, q0 = Wp + (tile - n * tps) * CT_M;
+                const int q = q0 + lq * 32 + lane;
+                const bool live = q < qend;
+                const int col = q % Wp;
+                const bool interior = live && col >= 1 && col <= W;
+                const size_t row = (size_t)n * PS + q;
+                uint4 ax[NCH / 8];
+                if (EPI == 1) {                               // forward activation bits: issued before the wait, consumed after it
+                    const uint4* axp = reinterpret_cast<const uint4*>(aux_hi + row * CT_C + c0);
+#pragma unroll
+                    for (int i = 0; i < NCH / 8; ++i) ax[i] = live ? __ldg(axp + i) : make_uint4(0, 0, 0, 0);
+                }
+                mb_wait(s_u32(&bars[8 + buf * 2 + h]), (lt >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r[NCH], t2[NCH];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + h) * 2 * CT_C + c0);
+                if (NCH == 32) { tmem_ld32(taddr, r); tmem_ld32(taddr + 64, t2); }
+                else { tmem_ld16(taddr, r); tmem_ld16(taddr + 64, t2); }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mb_arrive(s_u32(&bars[12 + buf * 2 + h]));     // this warp's share of the accumulator is free
+                if (!live || (dbg & 4)) continue;
+                uint4* oh = reinterpret_cast<uint4*>(out_hi + row * CT_C + c0);
+                uint4* ol = reinterpret_cast<uint4*>(out_lo + row * CT_C + c0);
+#pragma unroll
+                for (int c8 = 0; c8 < NCH / 8; ++c8) {
+                    uint32_t hw[4], lw[4];
+                    float v[8];
+                    const uint32_t aw[4] = {ax[c8].x, ax[c8].y, ax[c8].z, ax[c8].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c8 * 8 + e;
+                        float x = __uint_as_float(r[c]) + __uint_as_float(t2[c]);
+                        if (EPI == 0) { x += breg[c]; x = fmaxf(x, 0.2f * x); }
+                        else {
+                            const uint32_t hb = (aw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;    // bf16 bits of the forward activation
+                            x *= (hb - 1u < 0x7FFFu) ? 1.f : 0.2f;                            // positive and non-zero
+                        }
+                        v[e] = interior ? x : 0.f;
+                    }
+                    if (F32OUT) {
+                        float4* of = reinterpret_cast<float4*>(out_f32 + row * CT_C + c0 + c8 * 8);
+                        of[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        of[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+#pragma unroll
+                    for (int p2 = 0; p2 < 4; ++p2) split_bf16x2(v[2 * p2], v[2 * p2 + 1], hw[p2], lw[p2]);
+                    oh[c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    ol[c8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ SIMT helpers (first / last layer, loss)
 // layer 0 (1 -> 32 channels): x planar fp32 [N][1][PS] -> NHWC (hi,lo) rows, channels 32..63 stay zero.
 // One thread per pixel; weights in shared memory; the 32 outputs leave as 4 + 4 16-byte stores (64 B of hi, 64 B of lo per pixel).
@@ -622,16 +850,18 @@ static int zalloc(T** p, size_t n) {
 
 // 0 = CUDA-core fp32 path (conv.cu).  Tensor-core variants, in the order they were developed and measured on B200 (64->64 layer,
 // S=8, T=120; tools/diag_conv_modes.py): 2 = one TMA box per tap, resident weights (92.6 us); 3 = row reuse (76.7 us);
-// 4 = + streamed weights, 3 A stages (71.2 us); 5 = + stacked [W_hi;W_lo] N=128 MMA (68.9 us); 1 = DEFAULT = + 8 epilogue warps (61.8 us).
+// 4 = + streamed weights, 3 A stages (71.2 us); 5 = + stacked [W_hi;W_lo] N=128 MMA (68.9 us); 6 = + 8 epilogue warps (61.8 us);
+// 1 = DEFAULT = pair kernel: weight slot shared by two tiles, lean epilogue, converged MMA/TMA issue (57.7 us); 7 = same with 16 epilogue warps.
+// >= 8: timing experiments on the pair kernel (bit mask, see tools/diag_conv_modes.py) -- results are garbage by construction.
 static int g_conv_tc = -1;
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+        g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : 1;
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 5 ? 5 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 4095 ? 4095 : on); }
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
@@ -672,6 +902,12 @@ int enc_tc_create(ConvNet* n) {
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<8, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<8, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -691,11 +927,18 @@ static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& m
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 5) k_conv_tc_ws<true, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    if (g_conv_tc == 1 || g_conv_tc >= 7) {
+        const int dbg = g_conv_tc >= 8 ? g_conv_tc - 8 : 0;      // 8 + bit mask: timing experiments (tools/diag_conv_modes.py), results invalid
+        const int pg = std::min((ntiles + 1) / 2, t->sm_count);
+#define LEMO_PAIR(NE, E, F) k_conv_tc_pair<NE, E, F><<<pg, 64 + 32 * NE, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, dbg)
+        if (g_conv_tc != 7) { if (epi == 1) LEMO_PAIR(8, 1, false); else if (of32) LEMO_PAIR(8, 0, true); else LEMO_PAIR(8, 0, false); }
+        else { if (epi == 1) LEMO_PAIR(16, 1, false); else if (of32) LEMO_PAIR(16, 0, true); else LEMO_PAIR(16, 0, false); }
+#undef LEMO_PAIR
+    } else if (g_conv_tc == 5) k_conv_tc_ws<true, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 4) k_conv_tc_ws<false, 4><<<grid, 192, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 3) k_conv_tc<1><<<grid, 192, CT_SMEM2, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
     else if (g_conv_tc == 2) k_conv_tc<0><<<grid, 192, CT_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
-    else k_conv_tc_ws<true, 8><<<grid, 320, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);
+    else k_conv_tc_ws<true, 8><<<grid, 320, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, epi);    // 6
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }

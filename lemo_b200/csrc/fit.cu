@@ -546,6 +546,19 @@ int lemo_fit_set_sequence(LemoFit* h, int32_t s, const float* init72, const floa
     return 0;
 }
 
+int lemo_fit_set_sequences(LemoFit* h, const float* init72, const float* markers_rec, const float* contact, void* stream) {
+    LEMO_CHECK(h && init72 && markers_rec && contact, "bad arguments");
+    Fit* f = &h->f;
+    LEMO_CHECK(f->mode == 0, "lemo_fit_set_sequences is the temporal-mode loader");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = f->S * f->T;                       // sequence s owns rows [s T, (s+1) T) of every per-frame array
+    LEMO_CUDA(cudaMemcpyAsync(f->mrec, markers_rec, (size_t)B * 201 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    LEMO_CUDA(cudaMemcpyAsync(f->contact, contact, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    k_split72<<<cdiv(B, 64), 64, 0, st>>>(init72, B, f->tr(), f->r6(), f->betas, f->zz(), f->lh(), f->rh());
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int fit_begin_run(Fit* f, float lr0, float lr1, float lr2, int sw1, int sw2, int frame, cudaStream_t st) {
     // fresh optimiser (optim.Adam(final_params, lr=init_lr): opt_amass_temp.py:344-345, opt_amass_perframe.py:319)
     LEMO_CUDA(cudaMemsetAsync(f->M1, 0, (size_t)f->B * 65 * sizeof(float), st));

@@ -133,8 +133,9 @@ class TemporalFitter(_Fitter):
         """All S sequences at once from [S,T,72], [S,T,67,3], [S,T,4] (host or device); no host synchronisation."""
         S, T = self.S, self.T
         a, b, c = self._dev(init72, (S, T, 72)), self._dev(markers_rec, (S, T, 67, 3)), self._dev(contact, (S, T, 4))
-        for s in range(S):
-            self.set_sequence(s, a[s], b[s], c[s], sync=False)
+        _lib.call('lemo_fit_set_sequences', self.handle, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.cur_stream(self.device))
+        for t in (a, b, c):
+            t.record_stream(torch.cuda.current_stream(self.device))
 
     def run(self, n_iters=100, lr0=0.01, lr1=0.005, lr_switch=60):
         """total_steps=100, lr .01 -> .005 after step 60 (opt_amass_temp.py:343-352).  Asynchronous."""

@@ -80,10 +80,16 @@ def test_temporal_deterministic_across_slots_and_runs():
             fit.set_sequence(s, init, mrec, con)
         fit.run(n_iters=5)
         outs.append(fit.state())
-    a, b = outs
+    # third run: the batched loader (lemo_fit_set_sequences) must stage exactly what the per-sequence loader stages
+    fit = _fitter(2, T)
+    fit.set_sequences(np.stack([init, init]), np.stack([mrec, mrec]), np.stack([con, con]))
+    fit.run(n_iters=5)
+    outs.append(fit.state())
+    a, b, c = outs
     for k in ('transl', 'rot6d', 'other'):
         assert torch.equal(a[k][:T], a[k][T:])
         assert torch.equal(a[k], b[k])
+        assert torch.equal(a[k], c[k])
 
 
 def test_perframe_tracks_oracle():
