@@ -208,7 +208,6 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
     if (with_backward) {
         LEMO_TRY(dev_alloc(&c->Gv, B * 3 * V));
         LEMO_TRY(dev_alloc(&c->DVP, B * 3 * V));
-        LEMO_TRY(dev_alloc(&c->DT, V * B * 12));
         LEMO_TRY(dev_alloc(&c->dA, (size_t)NJ * B * 12));
         LEMO_TRY(dev_alloc(&c->dX, B * XK));
         LEMO_TRY(dev_alloc(&c->dR, B * NJ * 9));
@@ -222,7 +221,7 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
 void bodyctx_free(BodyCtx* c) {
     if (!c) return;
     cudaSetDevice(c->m->device);
-    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->DT, c->dA, c->dX, c->dR, c->dJp, c->dtr};
+    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->dA, c->dX, c->dR, c->dJp, c->dtr};
     for (float* p : ptrs) cudaFree(p);
     delete c;
 }
@@ -533,47 +532,85 @@ __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ A, c
     o[2] = T[8] * p0 + T[9] * p1 + T[10] * p2 + T[11] + t2;
 }
 
-// adjoint per (frame, vertex): dvp = T.R^T g ; dT = g (x) [vp;1] ; dtransl += g
+// adjoint per (frame, vertex): dvp = T.R^T g ; dT = g (x) [vp;1] ; dtransl += g, fused with the contraction over vertices
+// dA[j][b][12] += sum_v w[j][v] dT[v][b][12]  (the first version wrote dT [V, B*12] to HBM -- 48 B per (frame, vertex) at a 46 KB stride --
+// and ran a separate split-K GEMM over it: 56 + 28 us per fitting iteration).  One CTA = one frame x `tiles` tiles of 256 vertices:
+// per tile, phase A computes dvp and parks dT in shared memory, phase B lets thread t accumulate outputs t, t+256, t+512 of the 660
+// (joint, 3x4 entry) pairs over the tile.  A CTA that owns all vertices of its frame (the loss-row sub-models: V = 253) adds in a fixed
+// order => bitwise reproducible; several CTAs per frame (full mesh) combine with atomicAdd like the split-K GEMM did.
+constexpr int SKB_TV = 256;
 __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, const float* __restrict__ w_jm,
-                                                  const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B,
-                                                  float* __restrict__ DVP, float* __restrict__ DT, float* __restrict__ dtr) {
+                                                  const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B, int tiles,
+                                                  float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr) {
     __shared__ float sA[NJ * 12];
+    __shared__ float s_dt[SKB_TV * 12];
     __shared__ float sred[32];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < NJ * 12; i += blockDim.x) sA[i] = A[(size_t)b * NJ * 12 + i];
-    __syncthreads();
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (v < V) {
-        float T[9];
+    float o[3] = {0.f, 0.f, 0.f};
+    float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f;
+    const int t0 = blockIdx.x * tiles;
+    for (int tl = 0; tl < tiles; ++tl) {
+        const int v0 = (t0 + tl) * SKB_TV;
+        if (v0 >= V) break;
+        __syncthreads();                                   // sA ready / previous tile's s_dt consumed
+        const int v = v0 + threadIdx.x;
+        float dt[12];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) T[k] = 0.f;
-        for (int j = 0; j < NJ; ++j) {
-            const float w = w_jm[(size_t)j * V + v];
+        for (int k = 0; k < 12; ++k) dt[k] = 0.f;
+        if (v < V) {
+            float T[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) T[k] = 0.f;
+            for (int j = 0; j < NJ; ++j) {
+                const float w = w_jm[(size_t)j * V + v];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) T[i * 3 + c] = fmaf(w, sA[j * 12 + i * 4 + c], T[i * 3 + c]);
+            }
+            const float* g = Gv + ((size_t)b * V + v) * 3;
+            const float g0 = g[0], g1 = g[1], g2 = g[2];
+            gs0 += g0; gs1 += g1; gs2 += g2;
+            const float* vp = VP + ((size_t)b * V + v) * 3;
+            const float p[4] = {vp[0], vp[1], vp[2], 1.f};
+            float* dvp = DVP + ((size_t)b * V + v) * 3;
+            dvp[0] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+            dvp[1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+            dvp[2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+            const float gg[3] = {g0, g1, g2};
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) T[i * 3 + c] = fmaf(w, sA[j * 12 + i * 4 + c], T[i * 3 + c]);
+                for (int c = 0; c < 4; ++c) dt[i * 4 + c] = gg[i] * p[c];
         }
-        const float* g = Gv + ((size_t)b * V + v) * 3;
-        g0 = g[0]; g1 = g[1]; g2 = g[2];
-        const float* vp = VP + ((size_t)b * V + v) * 3;
-        const float p[4] = {vp[0], vp[1], vp[2], 1.f};
-        float* dvp = DVP + ((size_t)b * V + v) * 3;
-        dvp[0] = T[0] * g0 + T[3] * g1 + T[6] * g2;
-        dvp[1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
-        dvp[2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
-        float* dt = DT + (size_t)v * B * 12 + (size_t)b * 12;
-        const float gg[3] = {g0, g1, g2};
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int k4 = 0; k4 < 3; ++k4)
+            *reinterpret_cast<float4*>(&s_dt[threadIdx.x * 12 + k4 * 4]) = make_float4(dt[k4 * 4], dt[k4 * 4 + 1], dt[k4 * 4 + 2], dt[k4 * 4 + 3]);
+        __syncthreads();
+        const int nv = min(SKB_TV, V - v0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dt[i * 4 + c] = gg[i] * p[c];
+        for (int r = 0; r < 3; ++r) {
+            const int t = threadIdx.x + r * 256;
+            if (t >= NJ * 12) break;
+            const int j = t / 12, k = t - j * 12;
+            const float* wj = w_jm + (size_t)j * V + v0;
+            float acc = o[r];
+            for (int u = 0; u < nv; ++u) acc = fmaf(__ldg(wj + u), s_dt[u * 12 + k], acc);
+            o[r] = acc;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int t = threadIdx.x + r * 256;
+        if (t >= NJ * 12) break;
+        const int j = t / 12, k = t - j * 12;
+        atomicAdd(&dA[(size_t)j * B * 12 + (size_t)b * 12 + k], o[r]);
     }
     float s;
-    s = block_sum(g0, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3], s);
-    s = block_sum(g1, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 1], s);
-    s = block_sum(g2, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 2], s);
+    s = block_sum(gs0, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3], s);
+    s = block_sum(gs1, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 1], s);
+    s = block_sum(gs2, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 2], s);
 }
 
 // =============================================================================================
@@ -702,7 +739,12 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
         k_joints_bwd<<<cdiv(B * nout, 128), 128, 0, st>>>(d_joints, m->extra_vids, m->n_extra, m->lmk_tri, m->lmk_bary, m->n_lmk, V, B,
                                                             c->Gv, ps->dJp, ps->dtr);
     }
-    k_skin_bwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, c->DVP, c->DT, ps->dtr);
+    {
+        // vertex tiles per CTA: everything in one CTA per frame while that still fills the GPU (sub-models), else ~6 CTAs per frame
+        const int ntile = cdiv(V, SKB_TV);
+        const int tiles = ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 720)));
+        k_skin_bwd<<<dim3(cdiv(ntile, tiles), B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr);
+    }
     LEMO_CUDA(cudaGetLastError());
     // dX[B,512] += DVP[B,3V] . Wt^T        (contraction over 3V: split-K with atomics)
     {
@@ -711,15 +753,6 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
         g.M = B; g.N = XK; g.K = 3 * V;
         g.sAm = 3 * V; g.sAk = 1; g.sBk = 1; g.sBn = 3 * V; g.sCm = XK; g.sCn = 1;
         g.splitk = 1; g.nz = std::max(1, std::min(64, (3 * V) / 2048));   // loss-row sub-models: one slice => deterministic
-        LEMO_TRY(gemm_launch(g, st));
-    }
-    // dA[55, B*12] += w_jm[55,V] . DT[V, B*12]   (contraction over V)
-    {
-        GemmP g{};
-        g.A = m->w_jm; g.B = c->DT; g.C = ps->dA; g.bias = nullptr;
-        g.M = NJ; g.N = B * 12; g.K = V;
-        g.sAm = V; g.sAk = 1; g.sBk = (long long)B * 12; g.sBn = 1; g.sCm = (long long)B * 12; g.sCn = 1;
-        g.splitk = 1; g.nz = std::max(1, std::min(32, V / 1024));
         LEMO_TRY(gemm_launch(g, st));
     }
     return 0;

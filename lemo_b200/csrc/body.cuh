@@ -82,7 +82,6 @@ struct BodyCtx {
     // backward scratch
     float* Gv = nullptr;         // [B,V,3]   dL/dverts working copy
     float* DVP = nullptr;        // [B,3V]
-    float* DT = nullptr;         // [V, B*12]
     float* dA = nullptr;         // [55, B*12]  joint-major
     float* dX = nullptr;         // [B,512]
     float* dR = nullptr;         // [B,55,9]

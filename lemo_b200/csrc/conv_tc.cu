@@ -669,15 +669,17 @@ __global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, c
     }
 }
 // input gradient of layer 0 (32 -> 1): dpre NHWC (hi,lo) -> dx planar fp32.
-// Two phases per CTA of 256 output pixels: (1) every pixel of the tile + halo reads ITS OWN 128 B row once (warp = 32 consecutive
-// rows = 4 KB contiguous) and reduces it against the 9 weight columns into shared memory T[pixel][9]; (2) dx[q] = sum_k T[q - off_k][k].
+// Two phases per CTA of LB_TILE output pixels: (1) every pixel of the tile + halo reads ITS OWN 128 B row once and reduces it against the
+// 9 weight columns into shared memory T[pixel][9]; (2) dx[q] = sum_k T[q - off_k][k].  The halo is 2 Wp + 2 pixels whatever the tile, so
+// the tile is large (1024 pixels = 8 image rows at Wp = 128: 25 % redundant rows; the first version used 256 pixels = 100 %).
+constexpr int LB_TILE = 1024;
 __global__ void __launch_bounds__(256) k_tc_last_bwd(const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo,
                                                      const float* __restrict__ w /*[32][1][9]*/, float* __restrict__ dx, int H, int W, int Wp, int PS) {
-    extern __shared__ float s_t[];                 // [256 + 2*Wp + 2][9]
+    extern __shared__ float s_t[];                 // [LB_TILE + 2*Wp + 2][9]
     __shared__ float s_w[32 * 9];
     const int n = blockIdx.y;
-    const int q0 = Wp + blockIdx.x * 256;
-    const int span = 256 + 2 * Wp + 2;
+    const int q0 = Wp + blockIdx.x * LB_TILE;
+    const int span = LB_TILE + 2 * Wp + 2;
     for (int i = threadIdx.x; i < 288; i += 256) s_w[i] = w[i];
     __syncthreads();
     for (int e = threadIdx.x; e < span; e += 256) {
@@ -706,18 +708,20 @@ __global__ void __launch_bounds__(256) k_tc_last_bwd(const __nv_bfloat16* __rest
         for (int k = 0; k < 9; ++k) s_t[e * 9 + k] = t[k];
     }
     __syncthreads();
-    const int q = q0 + threadIdx.x;
-    if (q >= (H + 1) * Wp) return;
-    const int col = q % Wp;
-    float a = 0.f;
-    if (col >= 1 && col <= W) {
+    for (int o = threadIdx.x; o < LB_TILE; o += 256) {
+        const int q = q0 + o;
+        if (q >= (H + 1) * Wp) break;
+        const int col = q % Wp;
+        float a = 0.f;
+        if (col >= 1 && col <= W) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {              // dx[q] = sum_oc,k dpre[oc][q - off_k] * W[oc][k]
-            const int e = threadIdx.x + Wp + 1 - ((k / 3 - 1) * Wp + (k % 3 - 1));
-            a += s_t[e * 9 + k];
+            for (int k = 0; k < 9; ++k) {          // dx[q] = sum_oc,k dpre[oc][q - off_k] * W[oc][k]
+                const int e = o + Wp + 1 - ((k / 3 - 1) * Wp + (k % 3 - 1));
+                a += s_t[e * 9 + k];
+            }
         }
+        dx[(size_t)n * PS + q] = a;
     }
-    dx[(size_t)n * PS + q] = a;
 }
 // smoothness loss on the fp32 NHWC output + dpre of the last layer in (hi,lo) form (same math as fit.cu:k_smooth_loss).
 // One thread per (pixel, 8 channels): float4 loads of z[q-1], z[q], z[q+1], one 16-byte store per plane.
@@ -897,6 +901,7 @@ int enc_tc_create(ConvNet* n) {
     cudaDeviceProp prop;
     LEMO_CUDA(cudaGetDeviceProperties(&prop, n->device));
     t->sm_count = prop.multiProcessorCount;
+    LEMO_CUDA(cudaFuncSetAttribute(k_tc_last_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM2));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_ws<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
@@ -978,7 +983,9 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
         cur ^= 1;
     }
     const ConvLayer& L0 = n->layers[0];
-    k_tc_last_bwd<<<dim3(cdiv((long long)g.H * g.Wp, 256), N), 256, (size_t)(256 + 2 * g.Wp + 2) * 9 * sizeof(float), st>>>(
+    const size_t lb_smem = (size_t)(LB_TILE + 2 * g.Wp + 2) * 9 * sizeof(float);
+    LEMO_CHECK(lb_smem <= 200 * 1024, "plane pitch too wide for k_tc_last_bwd");
+    k_tc_last_bwd<<<dim3(cdiv((long long)g.H * g.Wp, LB_TILE), N), 256, lb_smem, st>>>(
         t->g_hi[cur], t->g_lo[cur], n->w_flat + L0.w_off, dx_planes, g.H, g.W, g.Wp, g.PS);
     LEMO_CUDA(cudaGetLastError());
     n->launches += 10;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_marker_l1(const float* __restrict__ Vr,
 }
 
 // L2 priors (opt_amass_temp.py:397-404): mean(z^2), mean(betas^2), mean(hand^2); adds their grads
-__global__ void __launch_bounds__(256) k_priors(const float* __restrict__ z, const float* __restrict__ lh, const float* __restrict__ rh,
+__global__ void __launch_bounds__(1024) k_priors(const float* __restrict__ z, const float* __restrict__ lh, const float* __restrict__ rh,
                                                 const float* __restrict__ betas, int Tb, float w_vp, float w_hand,
                                                 float* __restrict__ gz, float* __restrict__ glh, float* __restrict__ grh,
                                                 float* __restrict__ acc) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_priors(const float* __restrict__ z, con
 // count+sum pass, reduces in-block, then the gradient pass -- the data-dependent masked mean with its empty-set guard
 // (`if (...).sum().item() >= 1`, four host syncs per iteration in the reference) never leaves the device.
 struct FootTab { int off[4]; int n[4]; };
-__global__ void __launch_bounds__(256) k_contact(const float* __restrict__ Vr, const float* __restrict__ contact, int T, int NR, FootTab ft,
+__global__ void __launch_bounds__(1024) k_contact(const float* __restrict__ Vr, const float* __restrict__ contact, int T, int NR, FootTab ft,
                                                  float fps, float thres, float w, float* __restrict__ acc, float* __restrict__ Grows) {
     __shared__ float sred[32];
     __shared__ float s_cnt;
@@ -366,7 +366,7 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
     if (con) {
         FootTab ft;
         for (int p = 0; p < 4; ++p) { ft.off[p] = f->foot_off[p]; ft.n[p] = f->foot_n[p]; }
-        k_contact<<<dim3(4, S), 256, 0, st>>>(f->Vr, contact, f->T, NR, ft, c.fps, c.vel_thres, c.w_contact, f->acc, f->Grows); nl++;
+        k_contact<<<dim3(4, S), 1024, 0, st>>>(f->Vr, contact, f->T, NR, ft, c.fps, c.vel_thres, c.w_contact, f->acc, f->Grows); nl++;
     }
     if (smooth) {
         const PlaneGeom& g = f->geom;
@@ -383,13 +383,13 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
     LEMO_CUDA(cudaGetLastError());
     // ---------------- backward through the body model
     LEMO_TRY(body_grad_begin(f->ctx, B, st));
-    LEMO_TRY(body_skin_backward(f->ctx, f->ctx, B, f->Grows, nullptr, st)); nl += 3;
+    LEMO_TRY(body_skin_backward(f->ctx, f->ctx, B, f->Grows, nullptr, st)); nl += 2;
     PoseGrad pg;
     pg.transl = f->g_tr(); pg.R_global = f->dRg; pg.R_body = f->dRb; pg.lhand = f->g_lh(); pg.rhand = f->g_rh();
     LEMO_TRY(body_pose_backward(f->ctx, in, B, pg, st)); nl += 3;
     LEMO_TRY(lemo_rot6d_to_rotmat_backward(f->r6(), f->dRg, B, f->g_r6(), st)); nl++;
     LEMO_TRY(vposer_decode_backward(f->vp, f->zz(), B, f->dRb, f->g_zz(), st)); nl += 4;
-    k_priors<<<S, 256, 0, st>>>(f->zz(), f->lh(), f->rh(), f->betas, Tb, c.w_vposer, c.w_hand, f->g_zz(), f->g_lh(), f->g_rh(), f->acc); nl++;
+    k_priors<<<S, 1024, 0, st>>>(f->zz(), f->lh(), f->rh(), f->betas, Tb, c.w_vposer, c.w_hand, f->g_zz(), f->g_lh(), f->g_rh(), f->acc); nl++;
     // ---------------- Adam
     k_adam_dev<<<cdiv(B * 65, 256), 256, 0, st>>>(f->P, f->Gp, f->M1, f->M2, B * 65, f->sched); nl++;
     LEMO_CUDA(cudaGetLastError());
