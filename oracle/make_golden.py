@@ -141,5 +141,56 @@ def main():
           '%.1f KB' % (os.path.getsize(os.path.join(OUT, 'reference_golden.npz')) / 1024))
 
 
+def synth_marker_clip(seed, T=120):
+    """A moving, turning 68-point body (pelvis + 67 markers, z up) with float32 coordinates and 0/1 contact labels."""
+    g = np.random.default_rng(seed)
+    base = g.standard_normal((68, 3)) * np.array([0.25, 0.12, 0.45]) + np.array([0.0, 0.0, 0.9])
+    base[[27, 57], 0] += np.array([-0.2, 0.2])          # shoulders / hips apart along x so that `across` is well defined
+    base[[28, 58], 0] += np.array([-0.15, 0.15])
+    t = np.arange(T) / 30.0
+    yaw = 0.6 * np.sin(0.7 * t) + 0.3 * t
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    R = np.stack([np.stack([c, -s_, 0 * c], -1), np.stack([s_, c, 0 * c], -1), np.stack([0 * c, 0 * c, 1 + 0 * c], -1)], -2)
+    pos = np.stack([0.8 * t + 0.1 * np.sin(2 * t), 0.3 * np.sin(0.9 * t), 0.02 * np.sin(5 * t)], -1)
+    body = np.einsum('tij,kj->tki', R, base) + pos[:, None] + 0.01 * g.standard_normal((T, 68, 3))
+    contact = (g.random((T, 4)) > 0.5).astype(np.float32)
+    return body.astype(np.float32), contact
+
+
+def make_infill_golden():
+    """Pin oracle/ref_infill.py against the reference's own get_local_markers_4chan / reconstruct_global_body.  utils/utils.py imports
+    torchgeometry (absent here) at module level for unrelated functions: an empty stub module lets the import through."""
+    import types
+    sys.modules.setdefault('torchgeometry', types.ModuleType('torchgeometry'))
+    sys.path.insert(0, REF)
+    import utils.utils as U
+    from oracle import ref_infill as ri
+    gold = {}
+    for tag, seed in (('a', 5), ('b', 6)):
+        body, contact = synth_marker_clip(seed)
+        ref_repr, ref_rot0 = U.get_local_markers_4chan(body.copy(), contact.copy())
+        my_repr, my_rot0 = ri.get_local_markers_4chan(body, contact)
+        e = np.abs(my_repr - ref_repr).max()
+        print('get_local_markers_4chan[%s]: oracle vs reference max abs err %.3e, rot0 err %.3e' % (tag, e, np.abs(my_rot0 - ref_rot0).max()))
+        assert e < 1e-12 and np.abs(my_rot0 - ref_rot0).max() < 1e-12
+        # inverse: zero reference + local part + (vx, vy, r) trajectory, as opt_amass_temp.py:306-312 assembles it
+        T = ref_repr.shape[1]
+        local = ref_repr[0, :, 0:-4].reshape(T, 68, 3)
+        traj = np.stack([ref_repr[1, :, 0], ref_repr[2, :, 0], ref_repr[3, :, 0]], -1)[:, None]
+        packed = np.concatenate([np.zeros((T, 1, 3)), local, traj], axis=1)
+        ref_glob = U.reconstruct_global_body(packed.copy(), ref_rot0)
+        my_glob = ri.reconstruct_global_body(packed, ref_rot0)
+        e = np.abs(my_glob - ref_glob).max()
+        print('reconstruct_global_body[%s]: oracle vs reference max abs err %.3e' % (tag, e))
+        assert e < 1e-12
+        gold.update({'body_' + tag: body, 'contact_' + tag: contact, 'repr_' + tag: ref_repr, 'rot0_' + tag: ref_rot0,
+                     'packed_' + tag: packed, 'global_' + tag: ref_glob})
+    np.savez_compressed(os.path.join(OUT, 'reference_golden_infill.npz'), **gold)
+
+
 if __name__ == '__main__':
-    main()
+    if 'infill' in sys.argv[1:]:
+        make_infill_golden()
+    else:
+        main()
+        make_infill_golden()

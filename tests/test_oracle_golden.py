@@ -71,3 +71,34 @@ def test_rotation_round_trips():
     x6 = rb.convert_to_6D_all(aa)
     assert torch.allclose(rb.gram_schmidt_6d(x6), rb.tgm_aa_to_rotmat(aa), atol=2e-6)
     assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(64, 3, 3), atol=1e-5)
+
+
+def test_infill_repr_and_reconstruction_match_reference():
+    """oracle/ref_infill.py vs outputs of the reference's own get_local_markers_4chan / reconstruct_global_body
+    (tests/golden/reference_golden_infill.npz, written by oracle/make_golden.py), plus the round trip body -> repr -> body."""
+    import os
+    from oracle import ref_infill as ri
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden_infill.npz')))
+    for tag in ('a', 'b'):
+        rep, rot0 = ri.get_local_markers_4chan(g['body_' + tag], g['contact_' + tag])
+        assert np.abs(rep - g['repr_' + tag]).max() < 1e-12 and np.abs(rot0 - g['rot0_' + tag]).max() < 1e-12
+        glob = ri.reconstruct_global_body(g['packed_' + tag], g['rot0_' + tag])
+        assert np.abs(glob - g['global_' + tag]).max() < 1e-12
+        # size-independent property: reconstruction inverts the representation up to the floor shift, the frame-0 pelvis (x, y)
+        # origin and the dropped last frame
+        body = g['body_' + tag].astype(np.float64)
+        body[:, :, 2] -= np.float64(g['body_' + tag][:, :, 2].min())
+        body[:, :, 0:2] -= body[0, 0, 0:2].copy()
+        assert np.abs(glob - body[:-1]).max() < 1e-6
+
+
+def test_infill_mask_rows_and_padding():
+    from oracle import ref_infill as ri
+    masked, loss_rows = ri.mask_rows(208)
+    assert masked.shape == (66,) and masked.min() == 9 and masked.max() == 185 and len(set(masked.tolist())) == 66
+    assert loss_rows.shape == (210 - 66 - 5,) and loss_rows[0] == 0 and loss_rows[-1] == 204
+    x = np.arange(4 * 208 * 30, dtype=np.float32).reshape(4, 208, 30) + 1.0
+    p = ri.prepare_input(x)
+    assert p.shape == (4, 210, 46)
+    assert np.all(p[0, masked + 1, :] == 0.0) and np.all(p[0, 205:209, :] == 0.0)
+    assert np.array_equal(p[1, 1:-1, 8:-8], x[1]) and np.array_equal(p[1, 0, 8:-8], x[1, 1]) and np.array_equal(p[2, 5, 0:8], x[2, 4, 8:0:-1])

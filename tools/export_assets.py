@@ -6,6 +6,7 @@ outputs are integer index tables, float statistics and network weights.
 
   lemo_b200/assets/lemo_tables.npz   marker / foot-vertex index tables + smooth/infill stats
   lemo_b200/assets/enc_smooth_15217.npz   Enc weights of runs/15217/Enc_last_model.pkl
+  lemo_b200/assets/ae_infill_59547.npz    AE (infill prior) weights of runs/59547/AE_last_model.pkl
   tests/golden/seed_clips.npz        the ten shipped [119,72] result clips + contact labels
 
 Index provenance (all under /root/reference):
@@ -39,12 +40,14 @@ def main():
     tabs['smooth_Xstd'] = st['Xstd'].reshape(243).astype(np.float32)
     st = np.load(os.path.join(REF, 'preprocess_stats/preprocess_stats_infill_local_markers_4chan.npz'))
     for k in st.files:
-        tabs['infill_' + k] = np.asarray(st[k], np.float32)
+        tabs['infill_' + k] = np.asarray(st[k], np.float64)     # float64 like the file: the de-normalisation runs in numpy float64
     np.savez(os.path.join(OUT_A, 'lemo_tables.npz'), **tabs)
     print({k: v.shape for k, v in tabs.items()})
 
     w = torch.load(os.path.join(REF, 'runs/15217/Enc_last_model.pkl'), map_location='cpu')
     np.savez(os.path.join(OUT_A, 'enc_smooth_15217.npz'), **{k: v.numpy() for k, v in w.items()})
+    w = torch.load(os.path.join(REF, 'runs/59547/AE_last_model.pkl'), map_location='cpu')
+    np.savez_compressed(os.path.join(OUT_A, 'ae_infill_59547.npz'), **{k: v.numpy() for k, v in w.items()})
 
     clips = {}
     for stage in ('perframe', 'temp'):
