@@ -157,6 +157,28 @@ int lemo_ae_backward_weights(LemoConvNet* net, const float* d_rec, int32_t N, fl
 int lemo_ae_finetune_step(LemoConvNet* net, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr,
                           int32_t t, float* loss_out, void* stream);
 
+/* ---------------------------------------------------------------- infill pre-stage --- */
+/* Body representation of one clip (utils/utils.py:209-265 get_local_markers_4chan + the loader's normalisation and layout,
+ * loader/optimize_loader_amass_new.py:359-361,376-377).  body [T,68,3] = pelvis joint + the 67 SSM2 markers, world z up; contact [T,4].
+ * repr: float32 [4, 208, T-1] (channel, row, frame) = what the dataset hands to the AE; d_stats (device, nullable) = 420 doubles
+ * {Xmean_local[208], Xstd_local[208], Xmean_global_xy, Xstd_global_xy, Xmean_global_r, Xstd_global_r}: NULL leaves the values
+ * un-normalised.  rot_0_pivot: device double[1].  workspace: device, >= 8*T doubles.  Arithmetic in double like the numpy reference. */
+int lemo_repr_local_markers_4chan(const float* body, const float* contact, int32_t T, const double* d_stats, float* repr,
+                                  double* rot_0_pivot, double* workspace, void* stream);
+/* utils/utils.py:180-203 reconstruct_global_body on its own: packed [T,70,3] = zero reference joint, local pelvis + 67 markers, one
+ * trajectory row (vx, vy, r); rot_0_pivot device double[1]; out [T,68,3] world positions.  workspace: >= 8*T doubles. */
+int lemo_reconstruct_global_body(const float* packed, const double* rot_0_pivot, int32_t T, float* out, double* workspace, void* stream);
+/* clip [4,d,T] (d must be 208) -> x_pad [4,d+2,T+16]: upper-body marker rows and the contact rows of channel 0 zeroed, then reflect
+ * padding (8,8,1,1) (opt_amass_temp.py:164-184).  row_mask (device [d+2], nullable) receives 1 on the rows of the fine-tune loss
+ * (opt_amass_temp.py:196-200) for lemo_ae_finetune_step; *n_rows_selected (host, nullable) their count. */
+int lemo_infill_prepare_input(const float* clip, int32_t d, int32_t T, float* x_pad, float* row_mask, int32_t* n_rows_selected,
+                              void* stream);
+/* AE output on the padded clip rec_pad [d+2,T+16] + the clip itself -> infilled markers in world coordinates markers_rec [T,67,3],
+ * contact labels [T,4] (sigmoid > .5), and optionally the same reconstruction of the un-infilled input markers_input [T,67,3]:
+ * crop, de-normalise, reconstruct_global_body (opt_amass_temp.py:205-325, utils/utils.py:180-203).  workspace: >= 8*T doubles. */
+int lemo_infill_finalize(const float* rec_pad, const float* clip, const double* d_stats, const double* rot_0_pivot, int32_t d, int32_t T,
+                         float* markers_rec, float* contact_lbl, float* markers_input, double* workspace, void* stream);
+
 /* ---------------------------------------------------------------- Chamfer (temp_prox/dist_chamfer.py) --- */
 /* xyz1 [B,n,3]; xyz2 [B,m,3] with xyz2_batch_stride floats between batches (0 = one shared scene).
  * dist = squared L2 to the nearest neighbour (first minimum wins), idx int32.  (dist_chamfer.py:10-28) */

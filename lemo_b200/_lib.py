@@ -118,6 +118,10 @@ SIGNATURES = {
     'lemo_adam_step': (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _P]),
     'lemo_fit_create': (C.c_int, [_P, _P, _P, _P, C.POINTER(LemoFitConfigC), C.c_int, C.POINTER(_P)]),
     'lemo_fit_destroy': (C.c_int, [_P]),
+    'lemo_repr_local_markers_4chan': (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    'lemo_reconstruct_global_body': (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    'lemo_infill_prepare_input': (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
+    'lemo_infill_finalize': (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     'lemo_fit_set_sequence': (C.c_int, [_P, _I, _P, _P, _P, _P]),
     'lemo_fit_set_sequences': (C.c_int, [_P, _P, _P, _P, _P]),
     'lemo_fit_run': (C.c_int, [_P, _I, _F, _F, _I, _P]),

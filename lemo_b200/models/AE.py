@@ -116,7 +116,7 @@ class AE(nn.Module):
         st = _lib.cur_stream(x.device)
         _lib.call('lemo_convnet_set_weights', net.handle, _lib.ptr(self.flat.detach().contiguous()), st)
         mask = torch.zeros(H, device=x.device)
-        rows = torch.as_tensor(np.asarray(row_ids), device=x.device).long()
+        rows = row_ids.to(x.device).long() if torch.is_tensor(row_ids) else torch.as_tensor(np.asarray(row_ids), device=x.device).long()
         mask[rows] = 1.0
         losses = torch.zeros(steps, device=x.device)
         for t in range(1, steps + 1):

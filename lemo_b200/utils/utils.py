@@ -1,5 +1,5 @@
-"""Drop-in for the hot-path functions of the reference's utils/utils.py (lines 50-169): 6D <-> axis-angle
-conversions and the params72 -> body mesh helpers."""
+"""Drop-in for the hot-path functions of the reference's utils/utils.py: 6D <-> axis-angle conversions and the
+params72 -> body mesh helpers (lines 50-169), the clip representation builder and its inverse (lines 180-265)."""
 import torch
 
 from .. import _lib
@@ -87,3 +87,30 @@ def gen_body_mesh_v1(body_params, smplx_model, vposer_model, return_joints=False
 def gen_body_joints_v1(body_params, smplx_model, vposer_model):
     """utils/utils.py:156-169."""
     return gen_body_mesh_v1(body_params, smplx_model, vposer_model, return_joints=True)
+
+
+def get_local_markers_4chan(cur_body, contact_lbls, device='cuda'):
+    """utils/utils.py:209-265 on the device: cur_body [T,1+67,3], contact_lbls [T,4] -> (cur_body [4,T-1,208], rot_0_pivot [1]).
+    Un-normalised, in the function's own [channel, frame, row] order (a permuted view of the [4,208,T-1] wire layout)."""
+    from ..infill import body_repr
+    rep, rot0 = body_repr(cur_body, contact_lbls, stats=None, device=device)
+    return rep.permute(0, 2, 1), rot0
+
+
+def reconstruct_global_body(body_joints_input, rot_0_pivot, device='cuda'):
+    """utils/utils.py:180-203 on the device: [T, 1+68+1, 3] (zero reference joint, local pelvis + markers, (vx, vy, r) trajectory)
+    -> [T, 68, 3] world positions (float32; the heading / translation recurrence runs in double like the reference)."""
+    import numpy as np
+    from .. import _lib as L
+    x = torch.as_tensor(np.asarray(body_joints_input) if not torch.is_tensor(body_joints_input) else body_joints_input)
+    x = x.to(device, torch.float32).contiguous()
+    T = x.shape[0]
+    assert tuple(x.shape) == (T, 70, 3), 'expected [T, 1+68+1, 3]'
+    rot0 = torch.as_tensor(np.asarray(rot_0_pivot, np.float64) if not torch.is_tensor(rot_0_pivot) else rot_0_pivot)
+    rot0 = rot0.to(x.device, torch.float64).reshape(1)
+    out = torch.empty(T, 68, 3, device=x.device)
+    ws = torch.empty(8 * T, dtype=torch.float64, device=x.device)
+    L.call('lemo_reconstruct_global_body', L.ptr(x), L.ptr(rot0), T, L.ptr(out), L.ptr(ws), L.cur_stream(x.device))
+    for t in (x, rot0, ws):
+        t.record_stream(torch.cuda.current_stream(x.device))
+    return out
