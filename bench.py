@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-perframe', action='store_true')
     ap.add_argument('--skip-prox', action='store_true')
+    ap.add_argument('--skip-infill', action='store_true')
     return ap.parse_args()
 
 
@@ -378,6 +379,38 @@ def main():
                             '(1121 x 100k, shared scene) + Enc smoothness, Adam; SMPL-X evaluated once', 'ms_per_iteration': pms,
                 'iterations_per_sec': 1e3 / pms, 'note': 'operators = lemo kernels; loss glue + optimizer still PyTorch (DESIGN.md section 7)'}
 
+    # ---------------- secondary: infill pre-stage of one clip: representation + mask/pad + 60 AE fine-tune steps + inference
+    #                  + global reconstruction, everything on the device; the CPU leg is the oracle's numpy float64 post-processing only
+    infill = None
+    if rank == 0 and not a.skip_infill:
+        from lemo_b200.infill import InfillStage, body_repr, load_infill_prior, load_infill_stats
+        from oracle.make_golden import synth_marker_clip
+        from oracle import ref_infill as ri
+        body68, con68 = synth_marker_clip(5, T=120)
+        st64 = load_infill_stats()
+        stage = InfillStage(load_infill_prior(), device=dev, stats=st64)
+        b_d, c_d = torch.from_numpy(body68).to(dev), torch.from_numpy(con68).to(dev)
+
+        def infill_clip():
+            clip, rot0 = body_repr(b_d, c_d, stats=st64, device=dev)
+            return stage.run(clip, rot0)
+        infill_clip()
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            out_inf = infill_clip()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        inf_ms = c0.elapsed_time(c1) / 3
+        t0 = time.perf_counter()
+        rep_np, rot0_np = ri.get_local_markers_4chan(body68, con68)
+        host_ms = (time.perf_counter() - t0) * 1e3
+        infill = {'workload': 'opt_amass_temp.py:141-325 for one 120-frame clip: get_local_markers_4chan + normalise, mask + reflect pad, 60 AE '
+                              'fine-tune steps (Adam lr 3e-6, 4.1 M weights), inference, labels, de-normalise, reconstruct_global_body',
+                  'ms_per_clip': inf_ms, 'clips_per_sec': 1e3 / inf_ms, 'finetune_steps': 60,
+                  'cpu_repr_only_ms': host_ms, 'note': 'AE weights = shipped runs/59547; synthetic marker clip'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -389,7 +422,7 @@ def main():
             'data': 'synthetic', 'config': workload_config(a, world), 'clocks': clocks,
             'e2e': {'value': e2e_rate, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(h_loss.numel() + h_par.numel()) * 4},
             'gpu_launches': int(launches), 'roofline': roof, 'roofline_lbs': roof_lbs,
-            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'], 'perframe': perframe, 'prox': prox,
+            'lbs_verts_per_sec': None if roof_lbs is None else roof_lbs['verts_per_sec'], 'perframe': perframe, 'prox': prox, 'infill': infill,
             'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}}
     print(json.dumps(line), flush=True)
     if world > 1:

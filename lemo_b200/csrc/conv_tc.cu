@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_pair(const __grid
                                                          const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                                                          const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
                                                          __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
-                                                         int Wp, int PS, int dbg) {
+                                                         int Wp, int PS, int dbg, int kmax) {
     constexpr int NCH = 256 / NEPI;                       // channels per epilogue thread: 32 (8 warps) or 16 (16 warps)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_pair(const __grid
                                 const uint64_t whi = desc_sw128(w0 + (kx * 2) * CT_W_TILE);
 #pragma unroll
                                 for (int k = 0; k < CT_C / 16; ++k) {
+                                    if (k >= kmax) continue;             // input channels >= 16 kmax are structurally zero (32-channel layers)
                                     const uint64_t o = (uint64_t)(k * 32 >> 4);
                                     if (dbg >= 8) {                       // timing experiments on the tensor pipe (tools/diag_conv_modes.py)
                                         constexpr uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
@@ -927,15 +928,16 @@ void enc_tc_free(ConvNet* n) {
 }
 
 static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
-                     const __nv_bfloat16* aux, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32, int N, int epi, cudaStream_t st) {
+                     const __nv_bfloat16* aux, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32, int N, int epi, cudaStream_t st, int kin = CT_C) {
     const PlaneGeom& g = t->g;
+    const int kmax = std::min(CT_C / 16, (kin + 15) / 16);     // real input channels of this layer, in MMA K steps
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
     if (g_conv_tc == 1 || g_conv_tc >= 7) {
         const int dbg = g_conv_tc >= 8 ? g_conv_tc - 8 : 0;      // 8 + bit mask: timing experiments (tools/diag_conv_modes.py), results invalid
         const int pg = std::min((ntiles + 1) / 2, t->sm_count);
-#define LEMO_PAIR(NE, E, F) k_conv_tc_pair<NE, E, F><<<pg, 64 + 32 * NE, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, dbg)
+#define LEMO_PAIR(NE, E, F) k_conv_tc_pair<NE, E, F><<<pg, 64 + 32 * NE, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, dbg, kmax)
         if (g_conv_tc != 7) { if (epi == 1) LEMO_PAIR(8, 1, false); else if (of32) LEMO_PAIR(8, 0, true); else LEMO_PAIR(8, 0, false); }
         else { if (epi == 1) LEMO_PAIR(16, 1, false); else if (of32) LEMO_PAIR(16, 0, true); else LEMO_PAIR(16, 0, false); }
 #undef LEMO_PAIR
@@ -959,7 +961,7 @@ int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
     const bool rr = g_conv_tc != 2;
     for (int l = 1; l < 10; ++l)
         LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[l] : t->m_a_hi[l], rr ? t->r_a_lo[l] : t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1],
-                           t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st));
+                           t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st, n->layers[l].Cin));
     n->launches += 10;
     return 0;
 }
@@ -979,7 +981,7 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
     const bool rr = g_conv_tc != 2;
     for (int l = 9; l >= 1; --l) {
         LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[cur] : t->m_g_hi[cur], rr ? t->r_g_lo[cur] : t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l],
-                           t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st));
+                           t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st, n->layers[l].Cout));
         cur ^= 1;
     }
     const ConvLayer& L0 = n->layers[0];
