@@ -261,35 +261,45 @@ def main():
         except Exception:
             pass
         net = fit._enc
-        tc = os.environ.get('LEMO_CONV', 'tc') != 'simt'
+        conv = os.environ.get('LEMO_CONV', 'wt')
+        tc = conv != 'simt'
         reps = 20
         st = _lib.cur_stream(dev)
-        _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, 0, 3, st)
-        torch.cuda.synchronize(dev)
+
+        def time_layer(backward):
+            _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, backward, 3, st)
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, backward, reps, st)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            return c0.elapsed_time(c1) / reps
+        k_ms, k_ms_bwd = time_layer(0), time_layer(1)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        _lib.call('lemo_convnet_profile_layer', net.handle, 5, S, 0, reps, st)
-        c1.record()
-        torch.cuda.synchronize(dev)
-        k_ms = c0.elapsed_time(c1) / reps
         W = T - 1 + 16
         flops = 2.0 * S * 64 * 64 * 9 * 245 * W                      # algorithmic flops of one 64->64 launch over S sequences
         ach = flops / (k_ms * 1e-3) / 1e12
         if tc:
             peak = float(peaks.get('bf16_tflops', 1590.0))
-            roof = {'kernel': 'k_conv_tc (Enc 64->64 conv3x3 + LeakyReLU on tcgen05, bf16x3 split, S=%d)' % S, 'bound': 'tensor',
+            pair = conv in ('pair', '1')
+            kname = 'k_conv_tc_pair' if pair else 'k_conv_tc_wt'
+            terms = 3 if pair else 4
+            roof = {'kernel': '%s (Enc 64->64 conv3x3 + LeakyReLU on tcgen05, bf16 (hi,lo) split, S=%d)' % (kname, S), 'bound': 'tensor',
                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    'traffic': traffic.get('k_conv_tc'), 'kernel_ms': k_ms,
+                    'traffic': traffic.get(kname), 'kernel_ms': k_ms, 'kernel_ms_input_gradient': k_ms_bwd,
                     'peak_source': ('measured' if 'bf16_tflops' in peaks else 'fallback') + ' bf16 dense burst (MEASURED_PEAKS.json)',
-                    'note': 'achieved counts ALGORITHMIC fp32 flops; the bf16x3 split issues 3 bf16 MMAs per product, so the tensor '
-                            'pipe executes 3x this figure; the kernel is L2->SMEM bound (9 shifted A tiles per output tile)'}
+                    'executed_tensor_tflops': terms * ach,
+                    'note': 'achieved counts ALGORITHMIC fp32 flops (2*S*64*64*9*245*%d per launch); fp32 parity needs the bf16 (hi,lo) split, so the '
+                            'tensor pipe executes %dx this figure (%s); DESIGN.md section 3' %
+                            (W, terms, 'stacked [W_hi;W_lo] x a_hi and x a_lo, weights resident in TMEM' if not pair else 'hi*hi + hi*lo + lo*hi')}
         else:
             sm_mhz = (clocks or {}).get('sm_max_mhz') or 1965.0
             peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12               # fp32 FMA roof at max SM clock
             roof = {'kernel': 'k_conv3x3<8> (Enc 64->64 conv3x3+LeakyReLU on CUDA cores, S=%d)' % S, 'bound': 'fp32', 'achieved': ach,
                     'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic.get('k_conv3x3'), 'kernel_ms': k_ms,
                     'peak_source': 'computed: 148 SMs x 128 FMA/clk x 2 x clocks.max.sm (MEASURED_PEAKS.json has no fp32 figure)'}
-        roof['share_of_step'] = 18 * k_ms / (ms_total / a.steps) if ms_total > 0 else None
+        roof['share_of_step'] = 9 * (k_ms + k_ms_bwd) / (ms_total / a.steps) if ms_total > 0 else None
 
         # ---------------- LBS verts/sec (BASELINE metric M2): full-mesh SMPL-X forward over a 120-frame batch, HBM roofline
         kw = {k: torch.zeros(T, n, device=dev) for k, n in (('transl', 3), ('global_orient', 3), ('body_pose', 63), ('left_hand_pose', 12),

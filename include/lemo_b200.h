@@ -141,7 +141,9 @@ int lemo_enc_backward_input(LemoConvNet* net, const float* dz, int32_t N, float*
 /* measurement hook: relaunch ONE conv layer of an Enc handle `reps` times on its resident activations
  * (forward: layer l of 0..9; backward: the input-gradient conv of layer l >= 1) so bench.py can time the
  * dominant kernel alone with CUDA events. */
-/* A/B switch for the Enc conv stack: 1 = tcgen05 bf16x3 kernels (default), 0 = fp32 CUDA-core kernels.  Debug/measurement only. */
+/* A/B switch for the Enc conv stack.  0 = fp32 CUDA-core kernels, 1 = tcgen05 pair kernel (3-term bf16 split), 8192 = tcgen05
+ * weights-in-TMEM kernel (4-term bf16 split), -1 = back to the default (environment LEMO_CONV=simt|pair|wt, else the built-in default).
+ * Other values select measured experiment variants (csrc/conv_tc.cu).  Debug/measurement only. */
 int lemo_debug_set_conv_tc(int32_t on);
 int lemo_enc_debug_backward(LemoConvNet* net, const float* dz, int32_t N, int32_t stop_layer, float* out, void* stream);
 int lemo_convnet_profile_layer(LemoConvNet* net, int32_t layer, int32_t N, int32_t backward, int32_t reps, void* stream);

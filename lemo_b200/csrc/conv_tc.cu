@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
 
@@ -625,6 +626,280 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) k_conv_tc_pair(const __grid
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ weights-in-TMEM variant
+// ncu on k_conv_tc_pair (profiles/r01_ncu_full_summary.md): tensor pipe 42 %, tensor-core shared-memory reads 49 %, L2 38 %, DRAM 17 % --
+// nothing saturated.  The kernel is pipeline-depth bound: 96 KB of streamed weight slots leave three 34 KB activation stages, i.e. ~1.2 us
+// of look-ahead against an L2 round trip + 82 KB of serialisation per step.  This variant removes the weights from shared memory
+// altogether by transposing the implicit GEMM:
+//     D^T[128 = {W_hi ; W_lo} x 64 oc, 96 px] += Wstack[128, 16 ic] . act^T[16 ic, 96 px]      (tcgen05.mma with A in TENSOR MEMORY)
+//   * the A operand is the stacked weight matrix [W_hi ; W_lo] of all 9 taps: 128 lanes x 288 columns of TMEM (2 bf16 per 32-bit
+//     column), written ONCE per CTA with tcgen05.st and resident for every tile of the persistent loop;
+//   * the B operand is the activation box (pixel rows of 64 channels = one 128 B swizzle row, exactly the NHWC tile the other variants
+//     use as A): N = 96 pixels per tile, the three kx taps are descriptor start addresses 0/128/256 B into one 104-row TMA box per ky;
+//   * each K step issues the SAME weight columns against act_hi and act_lo: rows [0,64) accumulate W_hi.(a_hi + a_lo), rows [64,128)
+//     W_lo.(a_hi + a_lo); the epilogue adds the two halves = the full (hi+lo) x (hi+lo) product (4 bf16 products, one more than the
+//     3-term split of the other variants, at the full M=128 rate and with no shared-memory operand traffic for the weights);
+//   * shared memory holds nothing but EIGHT 26 KB activation stages (almost three tiles of look-ahead); L2->SMEM traffic per output
+//     pixel drops from 1.36 KB (pair kernel) to 0.83 KB;
+//   * TMEM: accumulators at columns [0,96) and [128,224) (double buffered), weights at [224,512).
+// Epilogue (8 warps, NO shared memory, no CTA-level barrier).  The stacked rows are interleaved so that the two halves of one output
+// channel sit in the SAME warp: TMEM lane 32 q + l holds part (l >> 4) of channel 16 q + (l & 15).  A warp loads its 32 lanes x 48 pixel
+// columns, exchanges with lane ^ 16 (one SHFL per pixel pair: each lane keeps the pixels of its own parity and receives the other half
+// of them), applies bias + LeakyReLU or the LeakyReLU' mask, splits into bf16 (hi,lo) and stores 2-byte values: the 16 lanes of one
+// parity write 32 contiguous bytes (one full sector) of a pixel row per instruction.  Measured on B200 (tools/diag_conv_wt.py): the
+// first version of this kernel transposed through a 48 KB shared-memory buffer with two named barriers per tile; that epilogue alone
+// took 2.2 us per tile against 1.5 us of MMAs and did not overlap with them (66 us per layer, "MMA only" 61 us, "epilogue only" 42 us).
+constexpr int WT_N = 96;                                   // pixels per tile = MMA N
+constexpr int WT_BOX = 104;                                // TMA box rows: 96 + 2 halo rows, rounded up to the 8-row swizzle atom
+constexpr int WT_PLANE = WT_BOX * 128;                     // 13 KB
+constexpr int WT_STAGE = 2 * WT_PLANE;                     // hi + lo
+constexpr int WT_NST = 8;
+constexpr int WT_ACC1 = 128, WT_W0 = 224;                  // TMEM columns
+constexpr int WT_TL_MAX = 24;                              // timeline (debug) slots: tiles per CTA recorded
+constexpr size_t WT_SMEM = 1024 + WT_NST * WT_STAGE + 256 + WT_TL_MAX * 8 * 8;
+
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, with the shared-memory descriptor given as its LOW word only: the high word of every K-major SWIZZLE_128B descriptor of this file is the
+// constant 0x40004040 (SBO = 1024 B, version 1, layout 2), and (address >> 4) < 2^14 for any shared-memory address, so advancing a
+// descriptor is a 32-bit add on the low word -- one uniform-datapath instruction per MMA instead of a 64-bit mask/shift/add chain.
+__device__ __forceinline__ void mma_bf16_ts32(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 bd, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+          "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// wq: the layer's TMEM weight image (k_tc_prep_wt).
+// KMAX = real input channels / 16 (2 for the 32-channel layers: the other K steps are structurally zero and never issued).
+// NGRP epilogue groups of 8 warps: with 2, group g owns accumulator g and every other tile, so a group has TWO tile times for its tile.
+// var (timing experiments, tools/diag_conv_wt.py; results invalid): bit 1 = no epilogue stores, bit 2 = no MMAs, bit 3 = no TMA loads,
+// bit 4 = epilogue only hand-shakes (no TMEM load, no arithmetic), bit 5 = TMEM load but no arithmetic.
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// TL (timeline, debug builds of the kernel only): CTA 0 prints globaltimer stamps of its producer / MMA / epilogue warps (var bit 7).
+template <int EPI, bool F32OUT, int KMAX, int NGRP, bool TL = false>
+__global__ void __launch_bounds__(64 + 256 * NGRP, 1) k_conv_tc_wt(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                       const uint32_t* __restrict__ wq, const float* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ aux_hi, __nv_bfloat16* __restrict__ out_hi,
+                                                       __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, int N, int H, int W,
+                                                       int Wp, int PS, int var) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned long long tl0 = TL ? gtime_ns() : 0ull;
+    const bool tl = TL && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+    // timeline slots (shared memory, printed once at the end so the stamps do not perturb the run): per local tile
+    // [0] loads issued [1] accumulator free (MMA warp) [2] first stage ready [3] MMAs issued [4] accumulator complete (epilogue) [5] TMEM read [6] stored
+    unsigned long long* s_tl = (unsigned long long*)(smem_raw + WT_SMEM - WT_TL_MAX * 8 * 8);
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = smem;
+    uint64_t* bars = (uint64_t*)(smem + WT_NST * WT_STAGE);
+    // bars: [0..NST) stage full, [NST..2 NST) stage empty, then accumulator full [2], accumulator empty [2], weights of tap row ky in TMEM [3]
+    constexpr int B_EMPTY = WT_NST, B_AFULL = 2 * WT_NST, B_AEMPTY = 2 * WT_NST + 2, B_W = 2 * WT_NST + 4;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WT_NST + 7);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tps = (H * Wp + WT_N - 1) / WT_N;               // tiles per sample
+    const int ntiles = N * tps;
+    const int qend = (H + 1) * Wp;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < B_AEMPTY; ++i) mb_init(s_u32(&bars[i]), 1);
+        mb_init(s_u32(&bars[B_AEMPTY]), 8); mb_init(s_u32(&bars[B_AEMPTY + 1]), 8);
+        for (int i = 0; i < 3; ++i) mb_init(s_u32(&bars[B_W + i]), 12);       // 3 taps x 4 lane quarters
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const unsigned long long tl1 = TL ? gtime_ns() : 0ull;
+
+    if (warp >= 2) {
+        // stacked weights -> TMEM: lane 32 lq + l holds W_part[oc][tap][ic 0..63], part = l >> 4, oc = 16 lq + (l & 15), as 32 bf16 pairs per
+        // tap (K ascending along the columns, even K in the low half of a column).  The 2 NGRP warps of a lane quarter take the taps round
+        // robin and signal each tap row (ky) separately, so the first tile's ky = 0 MMAs start after one L2 round trip instead of after the
+        // whole 144 KB image (measured: 6.8 us of the 60 us kernel when the CTA waited for all of it), and the producer never waits.
+        // wq is the TMEM image prepared by k_tc_prep_wt: [tap][16-byte chunk i][TMEM lane r][4 words], so one warp-level load reads 512
+        // contiguous bytes (with the row-major tiles every lane read its own 128 B line: 32 tag look-ups per instruction, 4.7 us per CTA).
+        const int lq = warp & 3;
+        for (int tap = (warp - 2) >> 2; tap < 9; tap += 2 * NGRP) {
+            uint32_t wv[32];
+            const uint4* src = reinterpret_cast<const uint4*>(wq) + (size_t)tap * 8 * 128 + lq * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = __ldg(src + i * 128);
+                wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
+            }
+            tmem_st32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(WT_W0 + tap * 32), wv);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(s_u32(&bars[B_W + tap / 3]));
+        }
+    }
+    const unsigned long long tl2 = TL ? gtime_ns() : 0ull;
+
+    if (warp == 0) {
+        // ============================== TMA producer (converged warp, one elected lane issues) ==============================
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int n = tile / tps, q0 = Wp + (tile - n * tps) * WT_N;
+            for (int ky = 0; ky < 3; ++ky, ++it) {
+                const int s = it % WT_NST;
+                mb_wait(s_u32(&bars[B_EMPTY + s]), ((it / WT_NST) & 1) ^ 1);
+                const uint32_t full = s_u32(&bars[s]);
+                const int row = n * PS + q0 + (ky - 1) * Wp - 1;
+                const uint32_t dst = s_u32(s_a + s * WT_STAGE);
+                if (elect_one()) {
+                    if (var & 8) mb_arrive(full);
+                    else {
+                        mb_expect_tx(full, WT_STAGE);
+                        tma2d(dst, &map_hi, full, 0, row);
+                        tma2d(dst + WT_PLANE, &map_lo, full, 0, row);
+                    }
+                }
+                __syncwarp();
+            }
+            if (TL && tl && it / 3 - 1 < WT_TL_MAX) s_tl[(it / 3 - 1) * 8 + 0] = gtime_ns() - tl0;
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        // D = F32, A = B = BF16, both K-major, N = 96, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t wbase = tmem_base + (uint32_t)WT_W0;
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const uint32_t d = tmem_base + (uint32_t)(acc * WT_ACC1);
+            mb_wait(s_u32(&bars[B_AEMPTY + acc]), ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+            const unsigned long long tm0 = TL ? gtime_ns() : 0ull;
+            unsigned long long tm1 = 0ull;
+            for (int ky = 0; ky < 3; ++ky, ++it) {
+                const int s = it % WT_NST;
+                mb_wait(s_u32(&bars[s]), (it / WT_NST) & 1);
+                mb_wait(s_u32(&bars[B_W + ky]), 0);                             // weights of this tap row are in TMEM (only ever waits on the first tile)
+                if (TL && ky == 0) tm1 = gtime_ns();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // low descriptor word of the stage's hi plane (start address >> 4, LBO field = 1); every operand of the step is this + a constant
+                const uint32_t b0 = ((s_u32(s_a + s * WT_STAGE) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t wa = wbase + (uint32_t)(ky * 96);
+                if (elect_one()) {
+                    if (!(var & 4)) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) {                    // UMMA_K = 16 bf16 = 32 B in the swizzle atom = 8 TMEM columns of A
+                                // +1 pixel (kx) = +1 swizzle row = +128 B; +1 K step = +32 B; lo plane = +WT_PLANE
+                                const uint32_t bh = b0 + (uint32_t)((kx * 128 + k * 32) >> 4);
+                                const uint32_t bl = bh + (uint32_t)(WT_PLANE >> 4);
+                                const uint32_t a = wa + (uint32_t)(kx * 32 + k * 8);
+                                mma_bf16_ts32(d, a, bh, idesc, (kx | k) != 0 ? 1u : (ky != 0 ? 1u : 0u));
+                                mma_bf16_ts32(d, a, bl, idesc, 1u);
+                            }
+                        }
+                    }
+                    mma_commit(s_u32(&bars[B_EMPTY + s]));                     // stage reusable once these MMAs retire
+                    if (ky == 2) mma_commit(s_u32(&bars[B_AFULL + acc]));      // accumulator of this tile complete
+                }
+                __syncwarp();
+            }
+            if (TL && tl && lt < WT_TL_MAX) { s_tl[lt * 8 + 1] = tm0 - tl0; s_tl[lt * 8 + 2] = tm1 - tl0; s_tl[lt * 8 + 3] = gtime_ns() - tl0; }
+        }
+    } else {
+        // ============================== epilogue ==============================
+        const int lq = warp & 3, half = ((warp - 2) >> 2) & 1; // TMEM lane quarter; pixel half [48 half, 48 half + 48)
+        const int grp = (warp - 2) >> 3;                       // epilogue group: tiles lt = grp, grp + NGRP, ...
+        const int par = lane >> 4;                             // 0: this lane holds the W_hi rows and keeps the even pixels, 1: W_lo rows, odd pixels
+        const int oc = lq * 16 + (lane & 15);
+        const float breg = EPI == 0 ? __ldg(bias + oc) : 0.f;
+        for (uint32_t lt = grp; (long long)blockIdx.x + (long long)lt * gridDim.x < ntiles; lt += NGRP) {
+            const int tile = blockIdx.x + lt * gridDim.x;
+            const int acc = lt & 1;
+            const int n = tile / tps, q0 = Wp + (tile - n * tps) * WT_N;
+            const int qa = q0 + half * 48 + par;               // this lane's pixels: qa + 2 m, m = 0..23
+            const size_t obase = ((size_t)n * PS + qa) * CT_C + oc;
+            unsigned short ax[24];
+            if (EPI == 1) {                                    // forward activation bits: issued before the wait, consumed after it
+#pragma unroll
+                for (int m = 0; m < 24; ++m)
+                    ax[m] = qa + 2 * m < qend ? __ldg(reinterpret_cast<const unsigned short*>(aux_hi) + obase + (size_t)m * 2 * CT_C) : (unsigned short)0;
+            }
+            mb_wait(s_u32(&bars[B_AFULL + acc]), (lt >> 1) & 1);
+            const unsigned long long te0 = TL ? gtime_ns() : 0ull;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[48];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * WT_ACC1 + half * 48);
+            if (!(var & 16)) {
+                tmem_ld32(taddr, r);
+                tmem_ld16(taddr + 32, r + 32);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 48; ++j) r[j] = 0u;
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(s_u32(&bars[B_AEMPTY + acc]));            // this warp's share of the accumulator is free
+            const unsigned long long te1 = TL ? gtime_ns() : 0ull;
+            if (var & 48) continue;
+            int col = qa % Wp;
+#pragma unroll
+            for (int m = 0; m < 24; ++m) {
+                // keep the pixel of this lane's parity, hand the other one to lane ^ 16 (which holds the other half of the same channel)
+                const float own = __uint_as_float(par ? r[2 * m + 1] : r[2 * m]);
+                const float give = __uint_as_float(par ? r[2 * m] : r[2 * m + 1]);
+                float x = own + __shfl_xor_sync(0xFFFFFFFFu, give, 16);
+                const int q = qa + 2 * m;
+                const bool interior = col >= 1 && col <= W;
+                col += 2;
+                if (col >= Wp) col -= Wp;
+                if (EPI == 0) { x += breg; x = fmaxf(x, 0.2f * x); }
+                else x *= ((uint32_t)ax[m] - 1u < 0x7FFFu) ? 1.f : 0.2f;                  // forward activation positive and non-zero
+                x = interior ? x : 0.f;
+                if (q < qend && !(var & 2)) {
+                    const size_t o = obase + (size_t)m * 2 * CT_C;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+                    out_hi[o] = hi;
+                    out_lo[o] = __float2bfloat16_rn(x - __bfloat162float(hi));
+                    if (F32OUT) out_f32[o] = x;
+                }
+            }
+            if (TL && tl && (warp == 2 || warp == 10) && lt < WT_TL_MAX) {
+                s_tl[lt * 8 + 4] = te0 - tl0; s_tl[lt * 8 + 5] = te1 - tl0; s_tl[lt * 8 + 6] = gtime_ns() - tl0;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (TL && blockIdx.x == 0 && threadIdx.x == 0) {
+        printf("[tl] CTA 0 (ns since entry): TMEM alloc + barriers %llu | weights in TMEM %llu | kernel end %llu\n", tl1 - tl0, tl2 - tl0, gtime_ns() - tl0);
+        printf("[tl] tile: loads issued | accumulator free, first stage ready, MMAs issued | accumulator complete, TMEM read, stored\n");
+        const int nloc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        for (int i = 0; i < nloc && i < WT_TL_MAX; ++i)
+            printf("[tl] %2d: %6llu | %6llu %6llu %6llu | %6llu %6llu %6llu\n", i, s_tl[i * 8], s_tl[i * 8 + 1], s_tl[i * 8 + 2], s_tl[i * 8 + 3], s_tl[i * 8 + 4],
+                   s_tl[i * 8 + 5], s_tl[i * 8 + 6]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ SIMT helpers (first / last layer, loss)
 // layer 0 (1 -> 32 channels): x planar fp32 [N][1][PS] -> NHWC (hi,lo) rows, channels 32..63 stay zero.
 // One thread per pixel; weights in shared memory; the 32 outputs leave as 4 + 4 16-byte stores (64 B of hi, 64 B of lo per pixel).
@@ -641,7 +916,10 @@ __global__ void __launch_bounds__(128) k_tc_first(const float* __restrict__ x, c
     const bool interior = col >= 1 && col <= W;
     float xin[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) xin[k] = x[(size_t)n * PS + q + (k / 3 - 1) * Wp + (k % 3 - 1)];
+    for (int k = 0; k < 9; ++k) {            // the first / last border pixel of a plane has a neighbour outside it (its output is zeroed below)
+        const int qq = q + (k / 3 - 1) * Wp + (k % 3 - 1);
+        xin[k] = (qq >= 0 && qq < PS) ? x[(size_t)n * PS + qq] : 0.f;
+    }
     uint4* oh = reinterpret_cast<uint4*>(out_hi + ((size_t)n * PS + q) * CT_C);
     uint4* ol = reinterpret_cast<uint4*>(out_lo + ((size_t)n * PS + q) * CT_C);
 #pragma unroll
@@ -813,6 +1091,16 @@ __global__ void k_tc_prep_w(const float* __restrict__ w, const float* __restrict
     }
 }
 
+// TMEM image of a layer for k_conv_tc_wt: dst[tap][i 8][r 128][w 4] (uint32 = two consecutive-K bf16) = tile word (4 i + w) of row
+// (part, oc) of tap, where TMEM lane r = 32 q + l holds part = l >> 4 of channel oc = 16 q + (l & 15).
+__global__ void k_tc_prep_wt(const __nv_bfloat16* __restrict__ tiles /*[tap][{hi,lo}][64][64]*/, uint32_t* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 9 * 8 * 128 * 4) return;
+    const int w = idx & 3, r = (idx >> 2) & 127, i = (idx >> 9) & 7, tap = idx >> 12;
+    const int q = r >> 5, l = r & 31, part = l >> 4, oc = q * 16 + (l & 15);
+    dst[idx] = reinterpret_cast<const uint32_t*>(tiles)[((size_t)(tap * 2 + part) * 64 + oc) * 32 + i * 4 + w];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct EncTC {
     int maxN = 0;
@@ -821,9 +1109,11 @@ struct EncTC {
     float* zf = nullptr;                                // final activation, fp32 NHWC
     __nv_bfloat16 *g_hi[2] = {}, *g_lo[2] = {};
     __nv_bfloat16 *wf[10] = {}, *wb[10] = {};
+    uint32_t *wtf[10] = {}, *wtb[10] = {};              // TMEM images of wf / wb for the weights-in-TMEM kernel
     float* bias[10] = {};
     CUtensorMap m_a_hi[11], m_a_lo[11], m_g_hi[2], m_g_lo[2], m_wf[10], m_wb[10];
     CUtensorMap r_a_hi[11], r_a_lo[11], r_g_hi[2], r_g_lo[2];   // 136-row boxes for the row-reuse variant
+    CUtensorMap w_a_hi[11], w_a_lo[11], w_g_hi[2], w_g_lo[2];   // 104-row boxes for the weights-in-TMEM variant
     int sm_count = 148;
 };
 
@@ -854,25 +1144,33 @@ static int zalloc(T** p, size_t n) {
 }
 
 // 0 = CUDA-core fp32 path (conv.cu).  Tensor-core variants, in the order they were developed and measured on B200 (64->64 layer,
-// S=8, T=120; tools/diag_conv_modes.py): 2 = one TMA box per tap, resident weights (92.6 us); 3 = row reuse (76.7 us);
+// S=8, T=120; tools/diag_conv_modes.py, tools/diag_conv_wt.py): 2 = one TMA box per tap, resident weights (92.6 us); 3 = row reuse (76.7 us);
 // 4 = + streamed weights, 3 A stages (71.2 us); 5 = + stacked [W_hi;W_lo] N=128 MMA (68.9 us); 6 = + 8 epilogue warps (61.8 us);
-// 1 = DEFAULT = pair kernel: weight slot shared by two tiles, lean epilogue, converged MMA/TMA issue (57.7 us); 7 = same with 16 epilogue warps.
-// >= 8: timing experiments on the pair kernel (bit mask, see tools/diag_conv_modes.py) -- results are garbage by construction.
+// 1 (LEMO_CONV=pair) = pair kernel: weight slot shared by two tiles, lean epilogue, converged MMA/TMA issue (67.9 us forward / 64.7 us input
+// gradient in the final measurement series); 7 = same with 16 epilogue warps.
+// 8..8191: timing experiments on the pair kernel (bit mask, see tools/diag_conv_modes.py) -- results are garbage by construction.
+// 8192 (LEMO_CONV=wt) = DEFAULT = weights-in-TMEM kernel k_conv_tc_wt (57.6 us forward / 59.8 us input gradient); 8192 + bits = its
+// experiments (tools/diag_conv_wt.py).
+constexpr int CONV_TC_DEFAULT = 8192;
 static int g_conv_tc = -1;
 static void conv_tc_init() {
     if (g_conv_tc < 0) {
         const char* e = getenv("LEMO_CONV");
-        g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : 1;
+        g_conv_tc = (e && strcmp(e, "simt") == 0) ? 0 : (e && strcmp(e, "wt") == 0) ? 8192 : (e && strcmp(e, "pair") == 0) ? 1
+                    : (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : CONV_TC_DEFAULT;
     }
 }
 bool conv_tc_enabled() { conv_tc_init(); return g_conv_tc >= 1; }
-void conv_tc_set(int on) { g_conv_tc = on < 0 ? 0 : (on > 4095 ? 4095 : on); }
+void conv_tc_set(int on) { g_conv_tc = on < 0 ? -1 : (on > 16383 ? 16383 : on); }     // -1: re-read LEMO_CONV / default at the next use
+static inline int conv_tc_maps() { return g_conv_tc >= 8192 ? 2 : g_conv_tc == 2 ? 0 : 1; }   // which activation box: 128 / 136 / 104 rows
 
 int enc_tc_refresh_weights(ConvNet* n, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
     for (int l = 1; l < 10; ++l) {
         const ConvLayer& L = n->layers[l];
         k_tc_prep_w<<<cdiv(9 * 64 * 64, 256), 256, 0, st>>>(n->w_flat + L.w_off, n->w_flat + L.b_off, L.Cin, L.Cout, t->wf[l], t->wb[l], t->bias[l]);
+        k_tc_prep_wt<<<cdiv(9 * 8 * 128 * 4, 256), 256, 0, st>>>(t->wf[l], t->wtf[l]);
+        k_tc_prep_wt<<<cdiv(9 * 8 * 128 * 4, 256), 256, 0, st>>>(t->wb[l], t->wtb[l]);
     }
     LEMO_CUDA(cudaGetLastError());
     return 0;
@@ -887,6 +1185,7 @@ int enc_tc_create(ConvNet* n) {
         LEMO_TRY(zalloc(&t->a_hi[l], rows * 64)); LEMO_TRY(zalloc(&t->a_lo[l], rows * 64));
         LEMO_TRY(make_bf16_map(&t->m_a_hi[l], t->a_hi[l], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_a_lo[l], t->a_lo[l], rows, CT_M));
         LEMO_TRY(make_bf16_map(&t->r_a_hi[l], t->a_hi[l], rows, CT_M2)); LEMO_TRY(make_bf16_map(&t->r_a_lo[l], t->a_lo[l], rows, CT_M2));
+        LEMO_TRY(make_bf16_map(&t->w_a_hi[l], t->a_hi[l], rows, WT_BOX)); LEMO_TRY(make_bf16_map(&t->w_a_lo[l], t->a_lo[l], rows, WT_BOX));
     }
     LEMO_TRY(zalloc(&t->zf, rows * 64));
     if (n->with_backward)
@@ -894,9 +1193,11 @@ int enc_tc_create(ConvNet* n) {
             LEMO_TRY(zalloc(&t->g_hi[i], rows * 64)); LEMO_TRY(zalloc(&t->g_lo[i], rows * 64));
             LEMO_TRY(make_bf16_map(&t->m_g_hi[i], t->g_hi[i], rows, CT_M)); LEMO_TRY(make_bf16_map(&t->m_g_lo[i], t->g_lo[i], rows, CT_M));
             LEMO_TRY(make_bf16_map(&t->r_g_hi[i], t->g_hi[i], rows, CT_M2)); LEMO_TRY(make_bf16_map(&t->r_g_lo[i], t->g_lo[i], rows, CT_M2));
+            LEMO_TRY(make_bf16_map(&t->w_g_hi[i], t->g_hi[i], rows, WT_BOX)); LEMO_TRY(make_bf16_map(&t->w_g_lo[i], t->g_lo[i], rows, WT_BOX));
         }
     for (int l = 1; l < 10; ++l) {
         LEMO_TRY(zalloc(&t->wf[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->wb[l], (size_t)18 * 64 * 64)); LEMO_TRY(zalloc(&t->bias[l], 64));
+        LEMO_TRY(zalloc(&t->wtf[l], (size_t)9 * 8 * 128 * 4)); LEMO_TRY(zalloc(&t->wtb[l], (size_t)9 * 8 * 128 * 4));
         LEMO_TRY(make_bf16_map(&t->m_wf[l], t->wf[l], 18 * 64, CT_C)); LEMO_TRY(make_bf16_map(&t->m_wb[l], t->wb[l], 18 * 64, CT_C));
     }
     cudaDeviceProp prop;
@@ -914,6 +1215,12 @@ int enc_tc_create(ConvNet* n) {
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_pair<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
+#define LEMO_WT_ATTR(E, F, K) \
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_wt<E, F, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM)); \
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_wt<E, F, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM))
+    LEMO_CUDA(cudaFuncSetAttribute(k_conv_tc_wt<0, false, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
+    LEMO_WT_ATTR(0, false, 4); LEMO_WT_ATTR(0, true, 4); LEMO_WT_ATTR(1, false, 4); LEMO_WT_ATTR(0, false, 2); LEMO_WT_ATTR(1, false, 2);
+#undef LEMO_WT_ATTR
     return enc_tc_refresh_weights(n, 0);
 }
 void enc_tc_free(ConvNet* n) {
@@ -922,19 +1229,34 @@ void enc_tc_free(ConvNet* n) {
     for (int l = 0; l <= 10; ++l) { cudaFree(t->a_hi[l]); cudaFree(t->a_lo[l]); }
     cudaFree(t->zf);
     for (int i = 0; i < 2; ++i) { cudaFree(t->g_hi[i]); cudaFree(t->g_lo[i]); }
-    for (int l = 0; l < 10; ++l) { cudaFree(t->wf[l]); cudaFree(t->wb[l]); cudaFree(t->bias[l]); }
+    for (int l = 0; l < 10; ++l) { cudaFree(t->wf[l]); cudaFree(t->wb[l]); cudaFree(t->bias[l]); cudaFree(t->wtf[l]); cudaFree(t->wtb[l]); }
     delete t;
     n->tc = nullptr;
 }
 
-static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
+static int launch_tc(const EncTC* t, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mw, const uint32_t* wimg, const float* bias,
                      const __nv_bfloat16* aux, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32, int N, int epi, cudaStream_t st, int kin = CT_C) {
     const PlaneGeom& g = t->g;
     const int kmax = std::min(CT_C / 16, (kin + 15) / 16);     // real input channels of this layer, in MMA K steps
     const int ntiles = N * cdiv((long long)g.H * g.Wp, CT_M);
     const int grid = std::min(ntiles, t->sm_count);
     conv_tc_init();
-    if (g_conv_tc == 1 || g_conv_tc >= 7) {
+    if (g_conv_tc >= 8192) {
+        const int var = g_conv_tc - 8192;
+        const int wtiles = N * cdiv((long long)g.H * g.Wp, WT_N);
+        const int wg = std::min(wtiles, t->sm_count);
+        const uint32_t* wq = wimg;
+#define LEMO_WT(E, F, K) do { if (var & 64) k_conv_tc_wt<E, F, K, 1><<<wg, 320, WT_SMEM, st>>>(mh, ml, wq, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, var); \
+                              else k_conv_tc_wt<E, F, K, 2><<<wg, 576, WT_SMEM, st>>>(mh, ml, wq, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, var); } while (0)
+        // var bit 6: one epilogue group of 8 warps instead of two (A/B measurement); bit 7: timeline print of CTA 0 (64->64 forward layers only)
+        if ((var & 128) && kmax > 2 && epi == 0 && !of32)
+            k_conv_tc_wt<0, false, 4, 2, true><<<wg, 576, WT_SMEM, st>>>(mh, ml, wq, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, var & ~128);
+        else if (kmax <= 2) { if (epi == 1) LEMO_WT(1, false, 2); else LEMO_WT(0, false, 2); }      // 32-channel layers (never the fp32-output layer)
+        else if (epi == 1) LEMO_WT(1, false, 4);
+        else if (of32) LEMO_WT(0, true, 4);
+        else LEMO_WT(0, false, 4);
+#undef LEMO_WT
+    } else if (g_conv_tc == 1 || g_conv_tc >= 7) {
         const int dbg = g_conv_tc >= 8 ? g_conv_tc - 8 : 0;      // 8 + bit mask: timing experiments (tools/diag_conv_modes.py), results invalid
         const int pg = std::min((ntiles + 1) / 2, t->sm_count);
 #define LEMO_PAIR(NE, E, F) k_conv_tc_pair<NE, E, F><<<pg, 64 + 32 * NE, CW_SMEM, st>>>(mh, ml, mw, bias, aux, oh, ol, of32, N, g.H, g.W, g.Wp, g.PS, dbg, kmax)
@@ -958,10 +1280,11 @@ int enc_tc_forward(ConvNet* n, const float* x_planes, int N, cudaStream_t st) {
     k_tc_first<<<dim3(cdiv((long long)g.H * g.Wp, 128), N), 128, 0, st>>>(x_planes, n->w_flat + L0.w_off, n->w_flat + L0.b_off, t->a_hi[1], t->a_lo[1],
                                                                           g.H, g.W, g.Wp, g.PS);
     conv_tc_init();
-    const bool rr = g_conv_tc != 2;
+    const int mk = conv_tc_maps();
     for (int l = 1; l < 10; ++l)
-        LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[l] : t->m_a_hi[l], rr ? t->r_a_lo[l] : t->m_a_lo[l], t->m_wf[l], t->bias[l], nullptr, t->a_hi[l + 1],
-                           t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st, n->layers[l].Cin));
+        LEMO_TRY(launch_tc(t, mk == 2 ? t->w_a_hi[l] : mk ? t->r_a_hi[l] : t->m_a_hi[l], mk == 2 ? t->w_a_lo[l] : mk ? t->r_a_lo[l] : t->m_a_lo[l],
+                           t->m_wf[l], t->wtf[l], t->bias[l], nullptr, t->a_hi[l + 1], t->a_lo[l + 1], l == 9 ? t->zf : nullptr, N, 0, st,
+                           n->layers[l].Cin));
     n->launches += 10;
     return 0;
 }
@@ -978,10 +1301,10 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
     const PlaneGeom& g = t->g;
     int cur = 0;
     conv_tc_init();
-    const bool rr = g_conv_tc != 2;
+    const int mk = conv_tc_maps();
     for (int l = 9; l >= 1; --l) {
-        LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[cur] : t->m_g_hi[cur], rr ? t->r_g_lo[cur] : t->m_g_lo[cur], t->m_wb[l], nullptr, t->a_hi[l],
-                           t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st, n->layers[l].Cout));
+        LEMO_TRY(launch_tc(t, mk == 2 ? t->w_g_hi[cur] : mk ? t->r_g_hi[cur] : t->m_g_hi[cur], mk == 2 ? t->w_g_lo[cur] : mk ? t->r_g_lo[cur] : t->m_g_lo[cur],
+                           t->m_wb[l], t->wtb[l], nullptr, t->a_hi[l], t->g_hi[cur ^ 1], t->g_lo[cur ^ 1], nullptr, N, 1, st, n->layers[l].Cout));
         cur ^= 1;
     }
     const ConvLayer& L0 = n->layers[0];
@@ -997,10 +1320,16 @@ int enc_tc_backward(ConvNet* n, int N, float* dx_planes, cudaStream_t st) {
 int enc_tc_profile_layer(ConvNet* n, int layer, int N, int backward, int reps, cudaStream_t st) {
     EncTC* t = (EncTC*)n->tc;
     LEMO_CHECK(layer >= 1 && layer <= 9, "tensor-core layers are 1..9");
+    conv_tc_init();
     for (int r = 0; r < reps; ++r) {
-        const bool rr = g_conv_tc != 2;
-        if (!backward) LEMO_TRY(launch_tc(t, rr ? t->r_a_hi[layer] : t->m_a_hi[layer], rr ? t->r_a_lo[layer] : t->m_a_lo[layer], t->m_wf[layer], t->bias[layer], nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
-        else LEMO_TRY(launch_tc(t, rr ? t->r_g_hi[0] : t->m_g_hi[0], rr ? t->r_g_lo[0] : t->m_g_lo[0], t->m_wb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
+        const int mk = conv_tc_maps();
+        if (!backward)
+            LEMO_TRY(launch_tc(t, mk == 2 ? t->w_a_hi[layer] : mk ? t->r_a_hi[layer] : t->m_a_hi[layer],
+                               mk == 2 ? t->w_a_lo[layer] : mk ? t->r_a_lo[layer] : t->m_a_lo[layer], t->m_wf[layer], t->wtf[layer], t->bias[layer],
+                               nullptr, t->a_hi[layer + 1], t->a_lo[layer + 1], nullptr, N, 0, st));
+        else
+            LEMO_TRY(launch_tc(t, mk == 2 ? t->w_g_hi[0] : mk ? t->r_g_hi[0] : t->m_g_hi[0], mk == 2 ? t->w_g_lo[0] : mk ? t->r_g_lo[0] : t->m_g_lo[0],
+                               t->m_wb[layer], t->wtb[layer], nullptr, t->a_hi[layer], t->g_hi[1], t->g_lo[1], nullptr, N, 1, st));
     }
     return 0;
 }

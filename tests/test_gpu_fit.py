@@ -21,10 +21,13 @@ def _fitter(S, T, **kw):
     return TemporalFitter(smplx_module(), vposer_module(), S, T, enc=enc_module(), device=DEV, **kw)
 
 
-@pytest.mark.parametrize('graph,conv', [(False, 'tc'), (True, 'tc'), (True, 'simt')])
+_CONV_MODES = {'simt': 0, 'pair': 1, 'wt': 8192}    # fp32 CUDA cores | tcgen05 pair kernel | tcgen05 weights-in-TMEM kernel (default)
+
+
+@pytest.mark.parametrize('graph,conv', [(False, 'wt'), (True, 'wt'), (True, 'pair'), (True, 'simt')])
 def test_temporal_first_iteration_gradients(graph, conv):
     from lemo_b200 import _lib
-    _lib.call('lemo_debug_set_conv_tc', 1 if conv == 'tc' else 0)
+    _lib.call('lemo_debug_set_conv_tc', _CONV_MODES[conv])
     T, S = 119, 2
     c32, c64 = oracle_ctx(torch.float32), oracle_ctx(torch.float64)
     fit = _fitter(S, T, use_cuda_graph=graph)
@@ -50,7 +53,7 @@ def test_temporal_first_iteration_gradients(graph, conv):
             want = tr64[0][k]
             assert abs(float(losses[s, i]) - want) <= 2e-4 * abs(want) + 1e-9, (k, float(losses[s, i]), want)
         assert rel(p72[s], ref72) < 2e-5                    # parameters of the (first) forward incl. tgm axis-angle
-    _lib.call('lemo_debug_set_conv_tc', 1)
+    _lib.call('lemo_debug_set_conv_tc', -1)
 
 
 def test_temporal_loop_tracks_oracle():
