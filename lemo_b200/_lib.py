@@ -83,6 +83,7 @@ SIGNATURES = {
     'lemo_smplx_forward': (C.c_int, [_P, C.POINTER(LemoPoseC), _I, _P, _P, _P, _P]),
     'lemo_smplx_backward': (C.c_int, [_P, C.POINTER(LemoPoseC), _I, _P, _P, C.POINTER(LemoPoseGradC), _P]),
     'lemo_debug_set_blend_tc': (C.c_int, [_I]),
+    'lemo_debug_set_skin_tc': (C.c_int, [_I]),
     'lemo_gather_rows': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_scatter_rows_add': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_rot6d_to_rotmat': (C.c_int, [_P, _I, _P, _P]),

@@ -243,6 +243,12 @@ int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N,
 int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st) {
     return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, TcEpi{}, st, nullptr);
 }
+// same GEMM with a per-column bias: bias = v_template gives v_posed directly (the tcgen05 skinning kernel reads it as is)
+int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st) {
+    TcEpi ep;
+    ep.bias = bias;
+    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
+}
 int tc_map_a(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BM); }
 int tc_map_b(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BN); }
 

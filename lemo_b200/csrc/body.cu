@@ -55,6 +55,12 @@ bool blend_tc_enabled() {
     return g_blend_tc == 1;
 }
 void blend_tc_set(int on) { g_blend_tc = on ? 1 : 0; }
+static int g_skin_tc = -1;
+bool skin_tc_enabled() {
+    if (g_skin_tc < 0) { const char* e = getenv("LEMO_SKIN"); g_skin_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
+    return g_skin_tc == 1;
+}
+void skin_tc_set(int on) { g_skin_tc = on ? 1 : 0; }
 
 // K-major transposed copy of Wt + its TMA descriptor for the tensor-core blend GEMM
 static int model_setup_tc(Model* m) {
@@ -64,6 +70,14 @@ static int model_setup_tc(Model* m) {
     LEMO_CUDA(cudaDeviceSynchronize());
     LEMO_TRY(blend_tc_map_w(m->WtT, 3 * m->V, m->map_w));
     m->has_tc = true;
+    // tensor-core skinning operand (full meshes only: the loss-row sub-models are a single CTA wave on the CUDA-core kernel)
+    m->has_skin_tc = false;
+    if (m->V >= 2048) {
+        LEMO_TRY(dev_alloc(&m->W2, (size_t)skin_tc_vpad(m->V) * 128));
+        LEMO_TRY(skin_tc_prep_w(m->w_jm, m->V, m->W2, m->map_w2));
+        LEMO_CUDA(cudaDeviceSynchronize());
+        m->has_skin_tc = true;
+    }
     return 0;
 }
 
@@ -180,7 +194,7 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
 void model_free(Model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->WtT); cudaFree(m->w_jm);
+    cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->WtT); cudaFree(m->W2); cudaFree(m->w_jm);
     if (!m->is_sub) {
         cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth);
         cudaFree(m->hand_l); cudaFree(m->hand_r); cudaFree(m->pose_mean);
@@ -202,6 +216,11 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
     LEMO_TRY(blend_tc_map_x(c->X2, maxB, c->map_x));
     LEMO_TRY(dev_alloc(&c->G, B * NJ * 12));
     LEMO_TRY(dev_alloc(&c->A, B * NJ * 12));
+    if (m->has_skin_tc) {
+        LEMO_TRY(dev_alloc(&c->A2, B * 12 * 128));
+        LEMO_CUDA(cudaMemset(c->A2, 0, B * 12 * 128 * sizeof(float)));      // joints 55..63 of both halves stay zero
+        LEMO_TRY(skin_tc_map_a(c->A2, maxB, c->map_a2));
+    }
     LEMO_TRY(dev_alloc(&c->Jrest, B * NJ * 3));
     LEMO_TRY(dev_alloc(&c->Jposed, B * NJ * 3));
     LEMO_TRY(dev_alloc(&c->VP, B * 3 * V));
@@ -221,7 +240,7 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
 void bodyctx_free(BodyCtx* c) {
     if (!c) return;
     cudaSetDevice(c->m->device);
-    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->dA, c->dX, c->dR, c->dJp, c->dtr};
+    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->A2, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->dA, c->dX, c->dR, c->dJp, c->dtr};
     for (float* p : ptrs) cudaFree(p);
     delete c;
 }
@@ -336,7 +355,8 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
                                                   const float* __restrict__ J_dirs, const int* __restrict__ parents,
                                                   const int* __restrict__ depth, int max_depth,
                                                   float* __restrict__ X, float* __restrict__ X2, float* __restrict__ G,
-                                                  float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed) {
+                                                  float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed,
+                                                  float* __restrict__ A2) {
     __shared__ float sG[NJ][12];
     __shared__ float sJ[NJ][3];
     __shared__ float sbeta[NBETA];
@@ -403,6 +423,15 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
             ao[i * 4] = g[i * 4]; ao[i * 4 + 1] = g[i * 4 + 1]; ao[i * 4 + 2] = g[i * 4 + 2];
             ao[i * 4 + 3] = g[i * 4 + 3] - (g[i * 4] * sJ[j][0] + g[i * 4 + 1] * sJ[j][1] + g[i * 4 + 2] * sJ[j][2]);
             Jposed[((size_t)b * NJ + j) * 3 + i] = g[i * 4 + 3];
+        }
+        if (A2) {                 // transposed TF32 split for the tensor-core skinning GEMM: row (b, k), column j
+            for (int k = 0; k < 12; ++k) {
+                const float a = ao[k];
+                const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+                float* row = A2 + ((size_t)b * 12 + k) * 128;
+                row[j] = hi;
+                row[64 + j] = a - hi;
+            }
         }
     }
 }
@@ -691,7 +720,7 @@ int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st) {
     const Model* m = c->m;
     k_pose_to_rot<<<cdiv(B * NJ, 128), 128, 0, st>>>(make_posek(m, in), B, c->full_pose, c->R);
     k_chain_fwd<<<B, 64, 0, st>>>(c->R, in.betas, in.betas_stride, in.expression, m->J_template, m->J_dirs, m->parents, m->depth,
-                                   m->max_depth, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed);
+                                   m->max_depth, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->A2);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -701,6 +730,19 @@ int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, fl
     const Model* m = c->m;
     const int V = m->V;
     // VP[B,3V] = X[B,512] . Wt[512,3V]: tcgen05 TF32 GEMM (blend_tc.cu); LEMO_BLEND=simt selects the CUDA-core GEMM (debug A/B)
+    if (m->has_tc && blend_tc_enabled() && m->has_skin_tc && ps->A2 && skin_tc_enabled()) {
+        // both contractions on tcgen05: the blend epilogue adds v_template (VP = v_posed), the skinning GEMM applies T in its epilogue
+        LEMO_TRY(blend_tc_launch_bias(ps->map_x, m->map_w, c->VP, B, 3 * V, m->v_template, st));
+        LEMO_TRY(skin_tc_launch(m->map_w2, ps->map_a2, c->VP, in.transl, V, B, verts, st));
+        if (joints) {
+            LEMO_CHECK(!m->is_sub, "output joints need the full model");
+            const int nout = NJ + m->n_extra + m->n_lmk;
+            k_joints_fwd<<<cdiv(B * nout, 128), 128, 0, st>>>(ps->Jposed, in.transl, verts, m->extra_vids, m->n_extra, m->lmk_tri,
+                                                                m->lmk_bary, m->n_lmk, V, B, joints);
+        }
+        LEMO_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (m->has_tc && blend_tc_enabled()) {
         LEMO_TRY(blend_tc_launch(ps->map_x, m->map_w, c->VP, B, 3 * V, st));
     } else {

@@ -18,6 +18,9 @@ struct Model {
     float* WtT = nullptr;          // [3V, 512]  K-major copy for the tcgen05 blend GEMM (blend_tc.cu)
     alignas(64) unsigned char map_w[128];   // CUtensorMap over WtT
     bool has_tc = false;
+    float* W2 = nullptr;           // [Vpad,128] TF32-split skinning weights [hi | lo], vertex-major (skin_tc.cu); full models only
+    alignas(64) unsigned char map_w2[128];  // CUtensorMap over W2
+    bool has_skin_tc = false;
     float* w_jm = nullptr;         // [55, V]    skinning weights, joint-major (lbs_weights^T)
     float* J_template = nullptr;   // [55,3]     J_regressor . v_template
     float* J_dirs = nullptr;       // [55,3,20]  J_regressor . shapedirs
@@ -76,6 +79,8 @@ struct BodyCtx {
     alignas(64) unsigned char map_x[128];   // CUtensorMap over X2
     float* G = nullptr;          // [B,55,12]
     float* A = nullptr;          // [B,55,12]
+    float* A2 = nullptr;         // [B*12,128] TF32 split of A^T: row b*12+k = [hi(A[b,:,k]) (64) | lo (64)]  (B operand of skin_tc.cu)
+    alignas(64) unsigned char map_a2[128];  // CUtensorMap over A2
     float* Jrest = nullptr;      // [B,55,3]
     float* Jposed = nullptr;     // [B,55,3]  (without transl)
     float* VP = nullptr;         // [B,3V]    v_posed (saved for backward)
@@ -125,8 +130,16 @@ int blend_tc_map_x(const float* X2, int maxB, void* map_x);
 int blend_tc_map_w(const float* WtT, int N, void* map_w);
 int blend_tc_transpose(const float* Wt, float* WtT, int N);
 int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st);
+int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st);
 bool blend_tc_enabled();
 void blend_tc_set(int on);
+// tcgen05 skinning (skin_tc.cu)
+int skin_tc_vpad(int V);
+int skin_tc_prep_w(const float* w_jm, int V, float* W2, void* map_w2);
+int skin_tc_map_a(const float* A2, int maxB, void* map_a2);
+int skin_tc_launch(const void* map_w2, const void* map_a2, const float* VP, const float* transl, int V, int B, float* verts, cudaStream_t st);
+bool skin_tc_enabled();
+void skin_tc_set(int on);
 
 int gather_rows(const float* src, const int* idx_dev, int B, int V, int n, float* out, cudaStream_t st);
 int scatter_rows_add(const float* g_rows, const int* idx_dev, int B, int V, int n, float* g_dense, cudaStream_t st);

@@ -18,13 +18,17 @@ def _oracle(nv, pose, dtype, grad=False):
     return v, j, fp, t
 
 
-@pytest.fixture(params=['tc', 'simt'])
+@pytest.fixture(params=['tc', 'tc_blend_simt_skin', 'simt'])
 def blend_mode(request):
-    """Both blend-shape GEMM back ends: tcgen05 TF32 (default; Wt rounded once to TF32, X split hi/lo) and fp32 CUDA cores."""
+    """Back ends of the two LBS contractions: 'tc' = tcgen05 blend GEMM (TF32; Wt rounded once, X split hi/lo) + tcgen05 skinning
+    GEMM (TF32 3-term split, full meshes only) -- the default; 'tc_blend_simt_skin' = the CUDA-core skinning kernel after the
+    tensor-core blend; 'simt' = both on fp32 CUDA cores."""
     from lemo_b200 import _lib
-    _lib.call('lemo_debug_set_blend_tc', 1 if request.param == 'tc' else 0)
-    yield request.param
+    _lib.call('lemo_debug_set_blend_tc', 0 if request.param == 'simt' else 1)
+    _lib.call('lemo_debug_set_skin_tc', 1 if request.param == 'tc' else 0)
+    yield 'simt' if request.param == 'simt' else 'tc'
     _lib.call('lemo_debug_set_blend_tc', 1)
+    _lib.call('lemo_debug_set_skin_tc', 1)
 
 
 @pytest.mark.parametrize('nv,B', [(640, 5), (synth.V, 3), (synth.V, 119)])
@@ -44,6 +48,26 @@ def test_forward_matches_oracle(nv, B, blend_mode):
     else:
         # TF32 tensor-core blend: the only rounding is Wt -> TF32 (2^-12 relative, once, unbiased): measured 2.3e-5 of max|v|
         assert rel(out.vertices, v64) < 5e-5, rel(out.vertices, v64)
+
+
+@pytest.mark.parametrize('B', [1, 13, 300])
+def test_skin_tc_matches_cuda_core_skinning(B):
+    """tcgen05 skinning (3-term TF32 split, fp32-grade) against the CUDA-core kernel on the same v_posed: ragged frame chunks
+    (B not a multiple of 12), the ragged last vertex tile (10475 = 81 x 128 + 107) and CTAs that change weight tile mid-range."""
+    from lemo_b200 import _lib
+    pose = {k: torch.from_numpy(v).to(DEV) for k, v in rand_pose(B, 50 + B).items()}
+    mod = smplx_module(synth.V)
+    out = {}
+    try:
+        for on in (1, 0):
+            _lib.call('lemo_debug_set_skin_tc', on)
+            o = mod(return_verts=True, **pose)
+            out[on] = (o.vertices.clone(), o.joints.clone())
+    finally:
+        _lib.call('lemo_debug_set_skin_tc', 1)
+    assert torch.isfinite(out[1][0]).all()
+    assert rel(out[1][0], out[0][0]) < 2e-6, rel(out[1][0], out[0][0])
+    assert rel(out[1][1], out[0][1]) < 2e-6
 
 
 def test_golden_reference_lbs(golden):
