@@ -74,9 +74,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // i.e. the full 3-term split A_hi B_hi + A_lo B_hi + A_hi B_lo (fp32-grade; used where the result is not diluted by a larger term).
 __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                                        const __grid_constant__ CUtensorMap map_wlo, float* __restrict__ VP, int B, int N, int K,
-                                                       int lo_col, int three, TcEpi ep) {
+                                                       int lo_col, int three, int b_tiled, TcEpi ep) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
+    // SWIZZLE_128B tiles need 1024 B alignment.  Offsetting the __shared__ array (rather than rounding a uintptr_t) keeps the
+    // address space known to the compiler: the epilogue staging then compiles to LDS/STS instead of generic LD/ST.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int stage_bytes = three ? TC_STAGE_BYTES + TC_B_BYTES : TC_STAGE_BYTES;
     const int nstages = three ? 2 : TC_STAGES;                                         // 2 x 88 KB or 3 x 60 KB
     uint64_t* bars = (uint64_t*)(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
@@ -115,7 +117,9 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
                 if (three) tma_load_2d(a_dst + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, full, kb * TC_BK, n0);
                 tma_load_2d(a_dst, &map_x, full, kb * TC_BK, m0);                   // X_hi block
                 tma_load_2d(a_dst + TC_A_BYTES, &map_x, full, lo_col + kb * TC_BK, m0);  // X_lo block
-                tma_load_2d(a_dst + 2 * TC_A_BYTES, &map_w, full, kb * TC_BK, n0);
+                // b_tiled: B was re-laid out as [n tile][k block][224 rows][32 floats], one contiguous 28 KB box per (tile, k block)
+                if (b_tiled) tma_load_2d(a_dst + 2 * TC_A_BYTES, &map_w, full, 0, (blockIdx.x * nkb + kb) * TC_BN);
+                else tma_load_2d(a_dst + 2 * TC_A_BYTES, &map_w, full, kb * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -167,23 +171,46 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
             for (int j = 0; j < 32; ++j) s_out[row * TC_OUT_PITCH + c0 + j] = __uint_as_float(r[j]);
         }
         __syncwarp();
-        for (int rr = 0; rr < 32; ++rr) {                                           // this warp's 32 rows, lanes along columns
-            const int gr = m0 + lq * 32 + rr;
-            if (gr >= B) break;
-            const float* src = s_out + (lq * 32 + rr) * TC_OUT_PITCH;
-            const long long ldc = ep.ldc ? ep.ldc : N;
-            for (int c = lane; c < TC_BN; c += 32) {
-                const int gc = n0 + c;
-                if (gc >= N) continue;
-                float v = src[c];
-                if (ep.bias) v += ep.bias[gc];
-                if (ep.act == 1) v = v > 0.f ? v : 0.2f * v;
-                else if (ep.act == 2) v *= ep.mask_src[(size_t)gr * ldc + gc] > 0.f ? 1.f : 0.2f;
-                if (VP) VP[(size_t)gr * ldc + gc] = v;
-                if (ep.split_out) {               // (hi|lo) TF32 split of the result = A operand of the next GEMM
-                    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                    ep.split_out[(size_t)gr * ep.split_ld + gc] = hi;
-                    ep.split_out[(size_t)gr * ep.split_ld + ep.split_lo + gc] = v - hi;
+        const long long ldc = ep.ldc ? ep.ldc : N;
+        if (ep.act == 0 && !ep.split_out && VP) {
+            // plain / bias epilogue (the blend GEMM): bias hoisted into registers, 7 independent 128 B row stores per iteration
+            // (the generic loop below re-loaded the bias and serialised LDS -> LDG -> STG per element: 2/3 of the kernel's 48 us)
+            float bias_r[TC_BN / 32];
+#pragma unroll
+            for (int k = 0; k < TC_BN / 32; ++k) {
+                const int gc = n0 + lane + 32 * k;
+                bias_r[k] = (ep.bias && gc < N) ? __ldg(ep.bias + gc) : 0.f;
+            }
+            const int nrows = min(32, B - (m0 + lq * 32));
+#pragma unroll 4
+            for (int rr = 0; rr < nrows; ++rr) {
+                const float* src = s_out + (lq * 32 + rr) * TC_OUT_PITCH + lane;
+                float* dst = VP + (size_t)(m0 + lq * 32 + rr) * ldc + n0 + lane;
+                float v[TC_BN / 32];
+#pragma unroll
+                for (int k = 0; k < TC_BN / 32; ++k) v[k] = src[32 * k] + bias_r[k];
+#pragma unroll
+                for (int k = 0; k < TC_BN / 32; ++k)
+                    if (n0 + lane + 32 * k < N) dst[32 * k] = v[k];
+            }
+        } else {
+            for (int rr = 0; rr < 32; ++rr) {                                       // this warp's 32 rows, lanes along columns
+                const int gr = m0 + lq * 32 + rr;
+                if (gr >= B) break;
+                const float* src = s_out + (lq * 32 + rr) * TC_OUT_PITCH;
+                for (int c = lane; c < TC_BN; c += 32) {
+                    const int gc = n0 + c;
+                    if (gc >= N) continue;
+                    float v = src[c];
+                    if (ep.bias) v += ep.bias[gc];
+                    if (ep.act == 1) v = v > 0.f ? v : 0.2f * v;
+                    else if (ep.act == 2) v *= ep.mask_src[(size_t)gr * ldc + gc] > 0.f ? 1.f : 0.2f;
+                    if (VP) VP[(size_t)gr * ldc + gc] = v;
+                    if (ep.split_out) {               // (hi|lo) TF32 split of the result = A operand of the next GEMM
+                        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                        ep.split_out[(size_t)gr * ep.split_ld + gc] = hi;
+                        ep.split_out[(size_t)gr * ep.split_ld + ep.split_lo + gc] = v - hi;
+                    }
                 }
             }
         }
@@ -224,7 +251,12 @@ int make_kmajor_map(void* out_map /*CUtensorMap, 128 B*/, const float* base, lon
 }
 
 int blend_tc_map_x(const float* X2, int maxB, void* map_x) { return make_kmajor_map(map_x, X2, maxB, 2 * XK, TC_BM); }
-int blend_tc_map_w(const float* WtT, int N, void* map_w) { return make_kmajor_map(map_w, WtT, N, XK, TC_BN); }
+// WtT is stored box by box (k_transpose_wt): a [n_tiles * 16 * 224][32] tensor whose boxes are contiguous 28 KB runs of HBM.
+// (The plain [3V][512] layout made every box 224 separate 128 B pieces at a 2 KB stride: 47 us for the 64 MB read, 1.4 TB/s.)
+int blend_tc_wtt_floats(int N) { return cdiv(N, TC_BN) * TC_BN * XK; }
+int blend_tc_map_w(const float* WtT, int N, void* map_w) {
+    return make_kmajor_map(map_w, WtT, (long long)cdiv(N, TC_BN) * (XK / TC_BK) * TC_BN, TC_BK, TC_BN);
+}
 
 int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N, int K, int lo_col, const TcEpi& ep, cudaStream_t st,
                    const void* map_b_lo) {
@@ -236,17 +268,21 @@ int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N,
     LEMO_CHECK(K % TC_BK == 0 && K > 0, "tc_gemm: K must be a positive multiple of 32");
     dim3 grid(cdiv(N, TC_BN), cdiv(M, TC_BM));
     k_blend_tf32<<<grid, 192, TC_SMEM, st>>>(*(const CUtensorMap*)map_a, *(const CUtensorMap*)map_b,
-                                             *(const CUtensorMap*)(map_b_lo ? map_b_lo : map_b), C, M, N, K, lo_col, map_b_lo ? 1 : 0, ep);
+                                             *(const CUtensorMap*)(map_b_lo ? map_b_lo : map_b), C, M, N, K, lo_col, map_b_lo ? 1 : 0,
+                                             ep.b_tiled, ep);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
 int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st) {
-    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, TcEpi{}, st, nullptr);
+    TcEpi ep;
+    ep.b_tiled = 1;
+    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
 }
 // same GEMM with a per-column bias: bias = v_template gives v_posed directly (the tcgen05 skinning kernel reads it as is)
 int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st) {
     TcEpi ep;
     ep.bias = bias;
+    ep.b_tiled = 1;
     return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
 }
 int tc_map_a(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BM); }
@@ -289,7 +325,10 @@ __global__ void k_transpose_wt(const float* __restrict__ Wt, float* __restrict__
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i;
-        if (c < N) WtT[(size_t)c * XK + p0 + threadIdx.x] = rn_tf32(t[threadIdx.x][i]);
+        if (c < N) {              // box (n tile, k block) = 224 rows x 32 floats, contiguous; p0 is a multiple of 32 = one k block
+            const size_t box = (size_t)(c / TC_BN) * (XK / TC_BK) + p0 / TC_BK;
+            WtT[(box * TC_BN + c % TC_BN) * TC_BK + threadIdx.x] = rn_tf32(t[threadIdx.x][i]);
+        }
     }
 }
 int blend_tc_transpose(const float* Wt, float* WtT, int N) {

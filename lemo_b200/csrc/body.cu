@@ -65,7 +65,8 @@ void skin_tc_set(int on) { g_skin_tc = on ? 1 : 0; }
 // K-major transposed copy of Wt + its TMA descriptor for the tensor-core blend GEMM
 static int model_setup_tc(Model* m) {
     m->has_tc = false;
-    LEMO_TRY(dev_alloc(&m->WtT, (size_t)3 * m->V * XK));
+    LEMO_TRY(dev_alloc(&m->WtT, (size_t)blend_tc_wtt_floats(3 * m->V)));
+    LEMO_CUDA(cudaMemset(m->WtT, 0, (size_t)blend_tc_wtt_floats(3 * m->V) * sizeof(float)));     // rows past 3V of the last tile
     LEMO_TRY(blend_tc_transpose(m->Wt, m->WtT, 3 * m->V));
     LEMO_CUDA(cudaDeviceSynchronize());
     LEMO_TRY(blend_tc_map_w(m->WtT, 3 * m->V, m->map_w));

@@ -15,7 +15,7 @@ struct Model {
     bool is_sub = false;
     float* v_template = nullptr;   // [V,3]
     float* Wt = nullptr;           // [512, 3V]  rows 0..485 posedirs, 486..505 shapedirs^T, 506..511 zero
-    float* WtT = nullptr;          // [3V, 512]  K-major copy for the tcgen05 blend GEMM (blend_tc.cu)
+    float* WtT = nullptr;          // K-major copy of Wt for the tcgen05 blend GEMM, stored box by box: [3V/224][16][224][32] (blend_tc.cu)
     alignas(64) unsigned char map_w[128];   // CUtensorMap over WtT
     bool has_tc = false;
     float* W2 = nullptr;           // [Vpad,128] TF32-split skinning weights [hi | lo], vertex-major (skin_tc.cu); full models only
@@ -119,6 +119,7 @@ struct TcEpi {
     long long ldc = 0;                 // row pitch of C / mask_src (0 = N)
     float* split_out = nullptr;        // optional [M, split_ld]: hi at column n, lo at column split_lo + n
     long long split_ld = 0, split_lo = 0;
+    int b_tiled = 0;                   // B operand stored box by box (blend_tc_map_w) instead of plain [N][K]
 };
 int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N, int K, int lo_col, const TcEpi& ep, cudaStream_t st,
                    const void* map_b_lo = nullptr);   // map_b_lo: B - rn_tf32(B) => fp32-grade 3-term product
@@ -128,6 +129,7 @@ int tc_prep_b(const float* src, int rows_src, int cols_src, int transpose, int k
 // tcgen05 blend GEMM (blend_tc.cu)
 int blend_tc_map_x(const float* X2, int maxB, void* map_x);
 int blend_tc_map_w(const float* WtT, int N, void* map_w);
+int blend_tc_wtt_floats(int N);       // allocation size of the box-tiled WtT
 int blend_tc_transpose(const float* Wt, float* WtT, int N);
 int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st);
 int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st);

@@ -12,7 +12,7 @@
 //                W2 [Vpad][128] = [rn_tf32(W) (55 -> 64 cols) | W - hi]     made once at model create
 //                A2 [B*12][128] = [hi(A^T) (55 -> 64 cols)  | A^T - hi]      written by k_chain_fwd, row = b*12 + k
 //              TMA boxes of 32 floats (one 128 B swizzle row) x 128 / 144 rows; joints 56..63 are zero padding and never multiplied
-//   warps      0: TMA producer   1: TMEM alloc + MMA issuer   2..5: epilogue (lane = vertex), accumulators double-buffered in TMEM
+//   warps      0: TMA producer   1: TMEM alloc + MMA issuer   2..9: epilogue (lane = vertex), two groups of four, one per TMEM accumulator
 //   HBM        reads v_posed (4.B.3V) + W2 (5.4 MB, L2 resident), writes verts (4.B.3V)
 #include "body.cuh"
 #include <cuda.h>
@@ -30,7 +30,9 @@ constexpr int SK_W_BYTES = 4 * SK_W_SUB;  // hi atom0, hi atom1, lo atom0, lo at
 constexpr int SK_A_BYTES = 4 * SK_A_SUB;
 constexpr int SK_STAGES = 2;
 constexpr int SK_ACC_COLS = 256;          // column pitch between the two accumulators
-constexpr size_t SK_SMEM = 1024 + SK_W_BYTES + SK_STAGES * SK_A_BYTES + 256;
+constexpr int SK_EPI_WARPS = 8;
+constexpr int SK_STAGE_OUT = SK_EPI_WARPS * 4 * 96 * 4;   // per epilogue warp: 4 frames x 96 floats
+constexpr size_t SK_SMEM = 1024 + SK_W_BYTES + SK_STAGES * SK_A_BYTES + SK_STAGE_OUT + 256;
 
 __device__ __forceinline__ uint32_t sk_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sk_mb_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -71,14 +73,15 @@ __device__ __forceinline__ void sk_tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 // barriers: [0] W full, [1] W empty, [2..3] A full, [4..5] A empty, [6..7] accumulator full, [8..9] accumulator empty
-__global__ void __launch_bounds__(192, 1) k_skin_tc(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_a2,
+__global__ void __launch_bounds__(64 + 32 * SK_EPI_WARPS, 1) k_skin_tc(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_a2,
                                                     const float* __restrict__ VP, const float* __restrict__ transl, int V, int B,
                                                     int n_fc, int n_units, float* __restrict__ verts) {
     extern __shared__ uint8_t sk_smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)sk_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = sk_smem_raw + ((1024u - (sk_u32(sk_smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
     uint8_t* s_w = smem;
     uint8_t* s_a = smem + SK_W_BYTES;
-    uint64_t* bars = (uint64_t*)(smem + SK_W_BYTES + SK_STAGES * SK_A_BYTES);
+    uint8_t* s_stage = smem + SK_W_BYTES + SK_STAGES * SK_A_BYTES;
+    uint64_t* bars = (uint64_t*)(s_stage + SK_STAGE_OUT);
     uint32_t* tmem_slot = (uint32_t*)(bars + 12);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // contiguous, balanced range of units for this CTA; unit u = (vertex tile u / n_fc, frame chunk u % n_fc)
@@ -167,22 +170,25 @@ __global__ void __launch_bounds__(192, 1) k_skin_tc(const __grid_constant__ CUte
         }
     } else {
         // ===================== epilogue: lane = vertex, 12 columns per frame =====================
-        const int lq = warp & 3;
-        for (int u = u_begin, i = 0; u < u_end; ++u, ++i) {
+        // Two groups of four warps; group e owns accumulator e (units i with i & 1 == e), so two units' global loads, TMEM reads and
+        // stores are in flight per SM.  [B,V,3] rows are 12 B per vertex: a warp's 32 vertices of one frame are 96 contiguous floats,
+        // moved as three fully coalesced 128 B requests and transposed to/from the per-lane (x,y,z) through a small staging buffer
+        // (the direct 12 B-stride form issued 3 partial writes per sector and held this kernel at 20 us).
+        const int ew = warp - 2, grp = ew >> 2, lq = warp & 3;
+        float* stg = reinterpret_cast<float*>(s_stage) + ew * (4 * 96);
+        for (int u = u_begin + grp, i = grp; u < u_end; u += 2, i += 2) {
             const int vt = u / n_fc, fc = u - vt * n_fc;
-            const int v = vt * SK_M + lq * 32 + lane;
+            const int v0 = vt * SK_M + lq * 32;                                      // first vertex of this warp
             const int b0 = fc * SK_FR;
-            const bool vok = v < V;
-            const int s = i & 1;
-            // v_posed of this vertex for the unit's frames: issued before the accumulator wait so the loads overlap the MMAs
-            float p[SK_FR][3];
+            const int nval = min(96, 3 * (V - v0));                                  // valid floats of the warp's 96 (<= 0: none)
+            const int s = grp;
+            // v_posed of the warp's vertices for the unit's frames: issued before the accumulator wait so the loads overlap the MMAs
+            float q[SK_FR][3];
 #pragma unroll
             for (int f = 0; f < SK_FR; ++f) {
-                const bool ok = vok && (b0 + f) < B;
-                const float* src = VP + ((size_t)(b0 + f) * V + v) * 3;
-                p[f][0] = ok ? __ldg(src) : 0.f;
-                p[f][1] = ok ? __ldg(src + 1) : 0.f;
-                p[f][2] = ok ? __ldg(src + 2) : 0.f;
+                const float* src = VP + ((size_t)(b0 + f) * V + v0) * 3;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) q[f][k] = ((b0 + f) < B && 32 * k + lane < nval) ? __ldg(src + 32 * k + lane) : 0.f;
             }
             sk_mb_wait(sk_u32(&bars[6 + s]), (i >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -193,25 +199,46 @@ __global__ void __launch_bounds__(192, 1) k_skin_tc(const __grid_constant__ CUte
                 sk_tmem_ld16(taddr + g * 48, r);
                 sk_tmem_ld16(taddr + g * 48 + 16, r + 16);
                 sk_tmem_ld16(taddr + g * 48 + 32, r + 32);
+#pragma unroll
+                for (int ff = 0; ff < 4; ++ff)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) stg[ff * 96 + 32 * k + lane] = q[g * 4 + ff][k];
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (g == SK_FR / 4 - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) sk_mb_arrive(sk_u32(&bars[8 + s]));               // accumulator s may be overwritten
                 }
+                __syncwarp();
+                float o[4][3];
 #pragma unroll
                 for (int ff = 0; ff < 4; ++ff) {
-                    const int f = g * 4 + ff, b = b0 + f;
-                    if (vok && b < B) {
-                        const float* T = reinterpret_cast<const float*>(r) + ff * 12;
-                        const float t0 = transl ? __ldg(transl + b * 3) : 0.f, t1 = transl ? __ldg(transl + b * 3 + 1) : 0.f,
-                                    t2 = transl ? __ldg(transl + b * 3 + 2) : 0.f;
-                        float* o = verts + ((size_t)b * V + v) * 3;
-                        o[0] = T[0] * p[f][0] + T[1] * p[f][1] + T[2] * p[f][2] + T[3] + t0;
-                        o[1] = T[4] * p[f][0] + T[5] * p[f][1] + T[6] * p[f][2] + T[7] + t1;
-                        o[2] = T[8] * p[f][0] + T[9] * p[f][1] + T[10] * p[f][2] + T[11] + t2;
+                    const int b = b0 + g * 4 + ff;
+                    const float p0 = stg[ff * 96 + 3 * lane], p1 = stg[ff * 96 + 3 * lane + 1], p2 = stg[ff * 96 + 3 * lane + 2];
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                    if (transl && b < B) { t0 = __ldg(transl + b * 3); t1 = __ldg(transl + b * 3 + 1); t2 = __ldg(transl + b * 3 + 2); }
+                    const uint32_t* T = r + ff * 12;
+                    o[ff][0] = __uint_as_float(T[0]) * p0 + __uint_as_float(T[1]) * p1 + __uint_as_float(T[2]) * p2 + __uint_as_float(T[3]) + t0;
+                    o[ff][1] = __uint_as_float(T[4]) * p0 + __uint_as_float(T[5]) * p1 + __uint_as_float(T[6]) * p2 + __uint_as_float(T[7]) + t1;
+                    o[ff][2] = __uint_as_float(T[8]) * p0 + __uint_as_float(T[9]) * p1 + __uint_as_float(T[10]) * p2 + __uint_as_float(T[11]) + t2;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int ff = 0; ff < 4; ++ff) {
+                    stg[ff * 96 + 3 * lane] = o[ff][0]; stg[ff * 96 + 3 * lane + 1] = o[ff][1]; stg[ff * 96 + 3 * lane + 2] = o[ff][2];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int ff = 0; ff < 4; ++ff) {
+                    const int b = b0 + g * 4 + ff;
+                    if (b < B) {
+                        float* dst = verts + ((size_t)b * V + v0) * 3;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (32 * k + lane < nval) dst[32 * k + lane] = stg[ff * 96 + 32 * k + lane];
                     }
                 }
+                __syncwarp();
             }
         }
     }
@@ -277,7 +304,7 @@ int skin_tc_launch(const void* map_w2, const void* map_a2, const float* VP, cons
     }
     const int n_fc = cdiv(B, SK_FR), n_units = cdiv(V, SK_M) * n_fc;
     const int grid = n_units < n_sm ? n_units : n_sm;
-    k_skin_tc<<<grid, 192, SK_SMEM, st>>>(*(const CUtensorMap*)map_w2, *(const CUtensorMap*)map_a2, VP, transl, V, B, n_fc, n_units, verts);
+    k_skin_tc<<<grid, 64 + 32 * SK_EPI_WARPS, SK_SMEM, st>>>(*(const CUtensorMap*)map_w2, *(const CUtensorMap*)map_a2, VP, transl, V, B, n_fc, n_units, verts);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
