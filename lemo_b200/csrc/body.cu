@@ -218,8 +218,8 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
     LEMO_TRY(dev_alloc(&c->G, B * NJ * 12));
     LEMO_TRY(dev_alloc(&c->A, B * NJ * 12));
     if (m->has_skin_tc) {
-        LEMO_TRY(dev_alloc(&c->A2, B * 12 * 128));
-        LEMO_CUDA(cudaMemset(c->A2, 0, B * 12 * 128 * sizeof(float)));      // joints 55..63 of both halves stay zero
+        LEMO_TRY(dev_alloc(&c->A2, skin_tc_a2_floats(maxB)));
+        LEMO_CUDA(cudaMemset(c->A2, 0, skin_tc_a2_floats(maxB) * sizeof(float)));      // joints 55..63 and frames past B stay zero
         LEMO_TRY(skin_tc_map_a(c->A2, maxB, c->map_a2));
     }
     LEMO_TRY(dev_alloc(&c->Jrest, B * NJ * 3));
@@ -426,12 +426,13 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
             Jposed[((size_t)b * NJ + j) * 3 + i] = g[i * 4 + 3];
         }
         if (A2) {                 // transposed TF32 split for the tensor-core skinning GEMM: row (b, k), column j
+            float* chunk = A2 + (size_t)(b / SKIN_TC_FR) * (4 * SKIN_TC_FR * 12 * 32);      // four [96][32] sub-tiles per 8-frame chunk
+            const int r0 = (b % SKIN_TC_FR) * 12, sub = j >> 5, col = j & 31;
             for (int k = 0; k < 12; ++k) {
                 const float a = ao[k];
                 const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-                float* row = A2 + ((size_t)b * 12 + k) * 128;
-                row[j] = hi;
-                row[64 + j] = a - hi;
+                chunk[((size_t)sub * (SKIN_TC_FR * 12) + r0 + k) * 32 + col] = hi;
+                chunk[((size_t)(2 + sub) * (SKIN_TC_FR * 12) + r0 + k) * 32 + col] = a - hi;
             }
         }
     }

@@ -5,6 +5,8 @@
 
 namespace lemo {
 
+constexpr int SKIN_TC_FR = 8;      // frames per unit of the tensor-core skinning kernel (layout of BodyCtx::A2)
+
 // Immutable device-resident model (created once per gender per device).
 struct Model {
     int device = 0;
@@ -18,7 +20,7 @@ struct Model {
     float* WtT = nullptr;          // K-major copy of Wt for the tcgen05 blend GEMM, stored box by box: [3V/224][16][224][32] (blend_tc.cu)
     alignas(64) unsigned char map_w[128];   // CUtensorMap over WtT
     bool has_tc = false;
-    float* W2 = nullptr;           // [Vpad,128] TF32-split skinning weights [hi | lo], vertex-major (skin_tc.cu); full models only
+    float* W2 = nullptr;           // TF32-split skinning weights, box by box: [V/128][hi j0-31 | hi j32-63 | lo .. | lo ..][128][32]; full models only
     alignas(64) unsigned char map_w2[128];  // CUtensorMap over W2
     bool has_skin_tc = false;
     float* w_jm = nullptr;         // [55, V]    skinning weights, joint-major (lbs_weights^T)
@@ -79,7 +81,7 @@ struct BodyCtx {
     alignas(64) unsigned char map_x[128];   // CUtensorMap over X2
     float* G = nullptr;          // [B,55,12]
     float* A = nullptr;          // [B,55,12]
-    float* A2 = nullptr;         // [B*12,128] TF32 split of A^T: row b*12+k = [hi(A[b,:,k]) (64) | lo (64)]  (B operand of skin_tc.cu)
+    float* A2 = nullptr;         // TF32 split of A^T, box by box: [B/8][hi j0-31 | hi j32-63 | lo j0-31 | lo j32-63][(b%8)*12+k][32]  (skin_tc.cu)
     alignas(64) unsigned char map_a2[128];  // CUtensorMap over A2
     float* Jrest = nullptr;      // [B,55,3]
     float* Jposed = nullptr;     // [B,55,3]  (without transl)
@@ -139,6 +141,7 @@ void blend_tc_set(int on);
 int skin_tc_vpad(int V);
 int skin_tc_prep_w(const float* w_jm, int V, float* W2, void* map_w2);
 int skin_tc_map_a(const float* A2, int maxB, void* map_a2);
+size_t skin_tc_a2_floats(int maxB);
 int skin_tc_launch(const void* map_w2, const void* map_a2, const float* VP, const float* transl, int V, int B, float* verts, cudaStream_t st);
 bool skin_tc_enabled();
 void skin_tc_set(int on);
