@@ -187,6 +187,8 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
     LEMO_CUDA(cudaDeviceSynchronize());
     cudaFree(rows_dev);
     s->WtT = nullptr;
+    s->W2 = nullptr;          // the copy above must not alias the parent's tensor-core operands (model_free would free them twice)
+    s->has_skin_tc = false;
     LEMO_TRY(model_setup_tc(s));
     *out = s;      // shares J_template/J_dirs/parents/hand/pose_mean pointers with the parent model
     return 0;
