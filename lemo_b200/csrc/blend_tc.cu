@@ -8,11 +8,12 @@
 //   warps      0: TMA producer   1: TMEM alloc + MMA issuer (one elected lane)   2-5: epilogue (TMEM -> smem -> coalesced stores)
 //   operands   A = X2  [B,1024] K-major (hi | lo);  B = WtT [3V,512] K-major (transposed copy of Wt made at model-create time)
 //   HBM        reads WtT once (64.3 MB) + X (L2 resident), writes VP (4*B*3V bytes): HBM-bound, 78.7 MB at B=120
-// Precision: TF32 keeps 10 explicit mantissa bits.  X is split by k_chain_fwd into X2 = [Xhi | Xlo] (Xhi = X with the low 13
+// Precision: TF32 keeps 10 explicit mantissa bits.  X is split by k_pose_chain_fwd into X2 = [Xhi | Xlo] (Xhi = X with the low 13
 // bits cleared, Xlo = X - Xhi, both exactly representable products of the split), and every Wt block is multiplied by both
 // halves, so the only rounding left is the tensor core's conversion of the model constant Wt -- see DESIGN.md section 4.
 #include "body.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace lemo {
 
@@ -220,6 +221,127 @@ __global__ void __launch_bounds__(192, 1) k_blend_tf32(const __grid_constant__ C
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ blend GEMM, version 2
+// The blend-shape contraction proper (k_blend_tf32 above stays the generic TF32 GEMM).  Two changes, both aimed at bytes in flight,
+// since the kernel is HBM-bound on the 64 MB of WtT and the first version spent 32 of every 60 KB stage on the (L2-resident) X tile:
+//   * X_lo is multiplied only where it matters.  X_hi = rn_tf32(X) (k_pose_chain_fwd), and for the 486 pose-feature columns the
+//     residual X_lo . W is 2^-12 of blend offsets that are themselves ~1 % of the body size: 5.0e-6 vs 3.9e-6 of max|v| with / without
+//     it on the synthetic model (W's own TF32 rounding dominates either way).  Only k-blocks >= lo_from_kb (the block holding betas and
+//     expression, whose offsets are 10x larger) get the second pass, as extra pipeline steps that re-read their W box from L2.
+//   * stages shrink to 16 KB (X) + 28 KB (W) = 44 KB, so FIVE fit in shared memory: 140 KB of W in flight per SM instead of 84 KB, and
+//     the tensor pipe does 17 instead of 32 MMA groups per tile.
+constexpr int B2_STAGES = 5;
+constexpr int B2_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr size_t B2_SMEM = 1024 + (size_t)B2_STAGES * B2_STAGE_BYTES + 256;
+static_assert((size_t)TC_BM * TC_OUT_PITCH * 4 <= (size_t)B2_STAGES * B2_STAGE_BYTES, "epilogue staging reuses the pipeline buffers");
+
+__global__ void __launch_bounds__(192, 1) k_blend_v2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                                                     float* __restrict__ VP, int B, int N, int nkb, int lo_from_kb, int lo_col,
+                                                     const float* __restrict__ bias) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = (uint64_t*)(smem + (size_t)B2_STAGES * B2_STAGE_BYTES);        // [0,5) full, [5,10) empty, [10] accumulator complete
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+    const int nsteps = nkb + (nkb - lo_from_kb);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < B2_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[B2_STAGES + s]), 1); }
+        mbar_init(smem_u32(&bars[2 * B2_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int st = 0; st < nsteps; ++st) {
+                const bool lo = st >= nkb;
+                const int kb = lo ? lo_from_kb + (st - nkb) : st;
+                const int s = st % B2_STAGES;
+                mbar_wait(smem_u32(&bars[B2_STAGES + s]), ((st / B2_STAGES) & 1) ^ 1);
+                const uint32_t full = smem_u32(&bars[s]);
+                mbar_expect_tx(full, B2_STAGE_BYTES);
+                const uint32_t dst = smem_u32(smem + (size_t)s * B2_STAGE_BYTES);
+                tma_load_2d(dst + TC_A_BYTES, &map_w, full, 0, (blockIdx.x * nkb + kb) * TC_BN);      // contiguous 28 KB box of WtT
+                tma_load_2d(dst, &map_x, full, (lo ? lo_col : 0) + kb * TC_BK, m0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+            for (int st = 0; st < nsteps; ++st) {
+                const int s = st % B2_STAGES;
+                mbar_wait(smem_u32(&bars[s]), (st / B2_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * B2_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint64_t off = (uint64_t)(k * TC_UMMA_K * 4 >> 4);
+                    umma_tf32(tmem_base, adesc + off, bdesc + off, idesc, (st | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bars[B2_STAGES + s]));
+            }
+            umma_commit(smem_u32(&bars[2 * B2_STAGES]));
+        }
+    } else {
+        const int lq = warp & 3;
+        // bias (v_template) for this lane's 7 columns: fetched while the main loop runs
+        float bias_r[TC_BN / 32];
+#pragma unroll
+        for (int k = 0; k < TC_BN / 32; ++k) {
+            const int gc = n0 + lane + 32 * k;
+            bias_r[k] = (bias && gc < N) ? __ldg(bias + gc) : 0.f;
+        }
+        mbar_wait(smem_u32(&bars[2 * B2_STAGES]), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* s_out = reinterpret_cast<float*>(smem);
+        const int row = lq * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+                "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s_out[row * TC_OUT_PITCH + c0 + j] = __uint_as_float(r[j]);
+        }
+        __syncwarp();
+        const int nrows = min(32, B - (m0 + lq * 32));
+#pragma unroll 4
+        for (int rr = 0; rr < nrows; ++rr) {
+            const float* src = s_out + (lq * 32 + rr) * TC_OUT_PITCH + lane;
+            float* dst = VP + (size_t)(m0 + lq * 32 + rr) * N + n0 + lane;
+            float v[TC_BN / 32];
+#pragma unroll
+            for (int k = 0; k < TC_BN / 32; ++k) v[k] = src[32 * k] + bias_r[k];
+#pragma unroll
+            for (int k = 0; k < TC_BN / 32; ++k)
+                if (n0 + lane + 32 * k < N) dst[32 * k] = v[k];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -273,17 +395,32 @@ int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N,
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
+// LEMO_BLEND_V=1 selects the first kernel (X_lo on every k-block, 3 stages) for A/B measurements
+static int blend_v2_launch(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st) {
+    static int ver = -1;
+    if (ver < 0) {
+        const char* e = getenv("LEMO_BLEND_V");
+        ver = (e && e[0] == '1') ? 1 : 2;
+        LEMO_CUDA(cudaFuncSetAttribute(k_blend_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
+    }
+    if (ver == 1) {
+        TcEpi ep;
+        ep.bias = bias;
+        ep.b_tiled = 1;
+        return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
+    }
+    // the last k-block (columns 480..511) holds the 6 last pose features, betas, expression and the zero padding
+    k_blend_v2<<<dim3(cdiv(N, TC_BN), cdiv(B, TC_BM)), 192, B2_SMEM, st>>>(*(const CUtensorMap*)map_x, *(const CUtensorMap*)map_w, VP, B, N,
+                                                                           XK / TC_BK, XK / TC_BK - 1, XK, bias);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
 int blend_tc_launch(const void* map_x, const void* map_w, float* VP, int B, int N, cudaStream_t st) {
-    TcEpi ep;
-    ep.b_tiled = 1;
-    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
+    return blend_v2_launch(map_x, map_w, VP, B, N, nullptr, st);
 }
 // same GEMM with a per-column bias: bias = v_template gives v_posed directly (the tcgen05 skinning kernel reads it as is)
 int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B, int N, const float* bias, cudaStream_t st) {
-    TcEpi ep;
-    ep.bias = bias;
-    ep.b_tiled = 1;
-    return tc_gemm_launch(map_x, map_w, VP, B, N, XK, XK, ep, st, nullptr);
+    return blend_v2_launch(map_x, map_w, VP, B, N, bias, st);
 }
 int tc_map_a(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BM); }
 int tc_map_b(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BN); }

@@ -283,25 +283,6 @@ __device__ __forceinline__ void joint_aa(const PoseK& p, int b, int j, float* aa
     for (int k = 0; k < 3; ++k) aa[k] += p.pose_mean[j * 3 + k];
 }
 
-__global__ void k_pose_to_rot(PoseK p, int B, float* __restrict__ full_pose, float* __restrict__ R) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * NJ) return;
-    const int b = i / NJ, j = i - b * NJ;
-    float aa[3], r[9];
-    const float* Rov = nullptr;
-    if (j == 0 && p.in.R_global) Rov = p.in.R_global + b * 9;
-    if (j >= 1 && j <= NBODY && p.in.R_body) Rov = p.in.R_body + (b * NBODY + (j - 1)) * 9;
-    if (Rov) {
-        for (int k = 0; k < 9; ++k) r[k] = Rov[k];
-        rotmat_to_aa_tgm(r, aa);                 // what the reference scripts store in the [T,72] result
-    } else {
-        joint_aa(p, b, j, aa);
-        rodrigues_fwd(aa, r);
-    }
-    for (int k = 0; k < 3; ++k) full_pose[b * 165 + j * 3 + k] = aa[k];
-    for (int k = 0; k < 9; ++k) R[(b * NJ + j) * 9 + k] = r[k];
-}
-
 // adjoint: dR -> parameter gradients.  One block (64 threads) per frame.
 __global__ void __launch_bounds__(64) k_pose_to_rot_bwd(PoseK p, PoseGrad g, int B, const float* __restrict__ full_pose,
                                                         const float* __restrict__ dR) {
@@ -351,42 +332,71 @@ __global__ void __launch_bounds__(64) k_pose_to_rot_bwd(PoseK p, PoseGrad g, int
 }
 
 // =============================================================================================
-// kinematic chain (lbs.py:196-263): one block (64 threads) per frame, level-synchronous over the tree
+// pose -> rotations -> kinematic chain, one kernel: one block (64 threads) per frame, thread j = joint j.
+//   * axis-angle -> R by Rodrigues (lbs.py:166-193), or rotation-matrix overrides (global 6D rotation / VPoser output) whose
+//     axis-angle is produced with the torchgeometry algorithm for the [T,72] result
+//   * blend-shape operand X = [R(1..54) - I | betas | expression | 0] and its TF32 split X2 = [Xhi | Xlo] (Xhi = X rounded to
+//     TF32's 10 explicit mantissa bits, Xlo = X - Xhi), staged in shared memory and written as coalesced rows
+//   * rest joints from the folded regressor, then the chain (lbs.py:196-263) level-synchronously over the tree (<= 10 levels)
+// (Two kernels -- one thread per (frame, joint), then this block shape -- cost 5.5 + 8 us per forward at B=120; forking the chain
+// onto a side stream beside the blend GEMM was measured too: the fork/join edges cost what the overlap saves.)
 // =============================================================================================
-__global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, const float* __restrict__ betas, int betas_stride,
-                                                  const float* __restrict__ expr, const float* __restrict__ J_template,
-                                                  const float* __restrict__ J_dirs, const int* __restrict__ parents,
-                                                  const int* __restrict__ depth, int max_depth,
-                                                  float* __restrict__ X, float* __restrict__ X2, float* __restrict__ G,
-                                                  float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed,
-                                                  float* __restrict__ A2) {
+__global__ void __launch_bounds__(64) k_pose_chain_fwd(PoseK p, const float* __restrict__ J_template,
+                                                       const float* __restrict__ J_dirs, const int* __restrict__ parents,
+                                                       const int* __restrict__ depth, int max_depth, float* __restrict__ full_pose,
+                                                       float* __restrict__ R, float* __restrict__ X, float* __restrict__ X2,
+                                                       float* __restrict__ G,
+                                                       float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed,
+                                                       float* __restrict__ A2) {
     __shared__ float sG[NJ][12];
     __shared__ float sJ[NJ][3];
     __shared__ float sbeta[NBETA];
+    __shared__ float sX[XK];
     const int b = blockIdx.x, j = threadIdx.x;
     if (j < NBETA) {
         float v = 0.f;
-        if (j < 10) v = betas ? betas[(size_t)b * betas_stride + j] : 0.f;
-        else v = expr ? expr[b * 10 + (j - 10)] : 0.f;
+        if (j < 10) v = p.in.betas ? p.in.betas[(size_t)b * p.in.betas_stride + j] : 0.f;
+        else v = p.in.expression ? p.in.expression[b * 10 + (j - 10)] : 0.f;
         sbeta[j] = v;
-        X[(size_t)b * XK + NPF + j] = v;
+        sX[NPF + j] = v;
     }
-    if (j >= NBETA && j < NBETA + (XK - NPF - NBETA)) X[(size_t)b * XK + NPF + j] = 0.f;
-    __syncthreads();
+    if (j >= NBETA && j < XK - NPF) sX[NPF + j] = 0.f;
     float r[9];
     int par = -1, dep = 0;
     if (j < NJ) {
-        for (int k = 0; k < 9; ++k) r[k] = R[((size_t)b * NJ + j) * 9 + k];
+        float aa[3];
+        const float* Rov = nullptr;
+        if (j == 0 && p.in.R_global) Rov = p.in.R_global + b * 9;
+        if (j >= 1 && j <= NBODY && p.in.R_body) Rov = p.in.R_body + (b * NBODY + (j - 1)) * 9;
+        if (Rov) {
+            for (int k = 0; k < 9; ++k) r[k] = Rov[k];
+            rotmat_to_aa_tgm(r, aa);                 // what the reference scripts store in the [T,72] result
+        } else {
+            joint_aa(p, b, j, aa);
+            rodrigues_fwd(aa, r);
+        }
+        for (int k = 0; k < 3; ++k) full_pose[b * 165 + j * 3 + k] = aa[k];
+        for (int k = 0; k < 9; ++k) R[((size_t)b * NJ + j) * 9 + k] = r[k];
+        if (j >= 1)
+            for (int k = 0; k < 9; ++k) sX[(j - 1) * 9 + k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < XK; k += blockDim.x) {
+        const float x = sX[k];
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));       // round to nearest: k_blend_v2 multiplies most columns by Xhi alone
+        const float hi = __uint_as_float(t);
+        X[(size_t)b * XK + k] = x;
+        X2[(size_t)b * 2 * XK + k] = hi;
+        X2[(size_t)b * 2 * XK + XK + k] = x - hi;
+    }
+    if (j < NJ) {
         for (int k = 0; k < 3; ++k) {
             float acc = J_template[j * 3 + k];
             const float* jd = J_dirs + (j * 3 + k) * NBETA;
             for (int l = 0; l < NBETA; ++l) acc = fmaf(jd[l], sbeta[l], acc);
             sJ[j][k] = acc;
             Jrest[((size_t)b * NJ + j) * 3 + k] = acc;
-        }
-        if (j >= 1) {
-            float* x = X + (size_t)b * XK + (j - 1) * 9;
-            for (int k = 0; k < 9; ++k) x[k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
         }
         par = parents[j]; dep = depth[j];
     }
@@ -408,14 +418,6 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
             for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
         }
         __syncthreads();
-    }
-    // TF32 split of the row of X for the tensor-core blend GEMM: Xhi keeps the 10 explicit mantissa bits TF32 has, Xlo the rest
-    __syncthreads();
-    for (int k = threadIdx.x; k < XK; k += blockDim.x) {
-        const float x = X[(size_t)b * XK + k];
-        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        X2[(size_t)b * 2 * XK + k] = hi;
-        X2[(size_t)b * 2 * XK + XK + k] = x - hi;
     }
     if (j < NJ) {
         const float* g = sG[j];
@@ -722,38 +724,34 @@ static PoseK make_posek(const Model* m, const PoseIn& in) {
 int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st) {
     LEMO_CHECK(c && B > 0 && B <= c->maxB, "batch exceeds the size this body handle was created for");
     const Model* m = c->m;
-    k_pose_to_rot<<<cdiv(B * NJ, 128), 128, 0, st>>>(make_posek(m, in), B, c->full_pose, c->R);
-    k_chain_fwd<<<B, 64, 0, st>>>(c->R, in.betas, in.betas_stride, in.expression, m->J_template, m->J_dirs, m->parents, m->depth,
-                                   m->max_depth, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->A2);
+    k_pose_chain_fwd<<<B, 64, 0, st>>>(make_posek(m, in), m->J_template, m->J_dirs, m->parents, m->depth, m->max_depth, c->full_pose,
+                                        c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->A2);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
 
-int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st) {
-    LEMO_CHECK(c && ps && verts && B > 0 && B <= c->maxB, "bad arguments");
+static bool both_tc(const Model* m, const BodyCtx* ps) {
+    return m->has_tc && blend_tc_enabled() && m->has_skin_tc && ps->A2 && skin_tc_enabled();
+}
+
+// VP[B,3V] = X[B,512] . Wt[512,3V]: tcgen05 TF32 GEMM (blend_tc.cu); LEMO_BLEND=simt selects the CUDA-core GEMM (debug A/B).
+// When skinning runs on the tensor cores too, the epilogue adds v_template so that VP = v_posed (skin_tc.cu reads it as is).
+int body_blend_forward(BodyCtx* c, const BodyCtx* ps, int B, cudaStream_t st) {
+    LEMO_CHECK(c && ps && B > 0 && B <= c->maxB, "bad arguments");
     const Model* m = c->m;
     const int V = m->V;
-    // VP[B,3V] = X[B,512] . Wt[512,3V]: tcgen05 TF32 GEMM (blend_tc.cu); LEMO_BLEND=simt selects the CUDA-core GEMM (debug A/B)
-    if (m->has_tc && blend_tc_enabled() && m->has_skin_tc && ps->A2 && skin_tc_enabled()) {
-        // both contractions on tcgen05: the blend epilogue adds v_template (VP = v_posed), the skinning GEMM applies T in its epilogue
-        LEMO_TRY(blend_tc_launch_bias(ps->map_x, m->map_w, c->VP, B, 3 * V, m->v_template, st));
-        LEMO_TRY(skin_tc_launch(m->map_w2, ps->map_a2, c->VP, in.transl, V, B, verts, st));
-        if (joints) {
-            LEMO_CHECK(!m->is_sub, "output joints need the full model");
-            const int nout = NJ + m->n_extra + m->n_lmk;
-            k_joints_fwd<<<cdiv(B * nout, 128), 128, 0, st>>>(ps->Jposed, in.transl, verts, m->extra_vids, m->n_extra, m->lmk_tri,
-                                                                m->lmk_bary, m->n_lmk, V, B, joints);
-        }
-        LEMO_CUDA(cudaGetLastError());
-        return 0;
-    }
-    if (m->has_tc && blend_tc_enabled()) {
-        LEMO_TRY(blend_tc_launch(ps->map_x, m->map_w, c->VP, B, 3 * V, st));
-    } else {
-        GemmP g = gemm_rowmajor(ps->X, m->Wt, c->VP, B, 3 * V, XK, false);
-        LEMO_TRY(gemm_launch(g, st));
-    }
-    k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
+    if (both_tc(m, ps)) return blend_tc_launch_bias(ps->map_x, m->map_w, c->VP, B, 3 * V, m->v_template, st);
+    if (m->has_tc && blend_tc_enabled()) return blend_tc_launch(ps->map_x, m->map_w, c->VP, B, 3 * V, st);
+    GemmP g = gemm_rowmajor(ps->X, m->Wt, c->VP, B, 3 * V, XK, false);
+    return gemm_launch(g, st);
+}
+
+// skinning (+ output joints): needs VP from body_blend_forward and A / Jposed from body_chain_forward
+static int body_apply_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st) {
+    const Model* m = c->m;
+    const int V = m->V;
+    if (both_tc(m, ps)) LEMO_TRY(skin_tc_launch(m->map_w2, ps->map_a2, c->VP, in.transl, V, B, verts, st));
+    else k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
     if (joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");
         const int nout = NJ + m->n_extra + m->n_lmk;
@@ -762,6 +760,12 @@ int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, fl
     }
     LEMO_CUDA(cudaGetLastError());
     return 0;
+}
+
+int body_skin_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st) {
+    LEMO_CHECK(c && ps && verts && B > 0 && B <= c->maxB, "bad arguments");
+    LEMO_TRY(body_blend_forward(c, ps, B, st));
+    return body_apply_forward(c, ps, in, B, verts, joints, st);
 }
 
 int body_grad_begin(BodyCtx* ps, int B, cudaStream_t st) {

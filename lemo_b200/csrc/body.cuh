@@ -105,6 +105,8 @@ void bodyctx_free(BodyCtx* c);
 
 // pose -> R, chain -> X, A (shared by a full model and its sub-models: pass the same ctx pose buffers)
 int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st);
+// blend GEMM only / everything after it: body_skin_forward = body_blend_forward + body_apply_forward
+int body_blend_forward(BodyCtx* c, const BodyCtx* pose_src, int B, cudaStream_t st);
 // X, A -> verts [B,V,3] (+transl) ; joints_out [B,127,3] nullable (full model only)
 int body_skin_forward(BodyCtx* c, const BodyCtx* pose_src, const PoseIn& in, int B, float* verts, float* joints, cudaStream_t st);
 // d_verts [B,V,3] nullable, d_joints [B,127,3] nullable -> accumulates into pose_src->dA / dX / dtr / dJp

@@ -352,7 +352,7 @@ static int fit_iteration(Fit* f, cudaStream_t st) {
     PoseIn in;
     in.transl = f->tr(); in.R_global = f->Rg; in.R_body = f->Rb; in.lhand = f->lh(); in.rhand = f->rh();
     in.betas = f->betas; in.betas_stride = 10; in.hand_is_pca = 1;
-    LEMO_TRY(body_pose_forward(f->ctx, in, B, st)); nl += 2;
+    LEMO_TRY(body_pose_forward(f->ctx, in, B, st)); nl += 1;
     LEMO_TRY(body_skin_forward(f->ctx, f->ctx, in, B, f->Vr, nullptr, st)); nl += 2;
     // snapshot of the parameters this forward used (what the scripts save after the loop)
     const float* contact = f->contact;

@@ -11,7 +11,7 @@
 //   operands   both pre-split for a 3-term TF32 product (hi.hi + lo.hi + hi.lo, fp32-grade: residual 2^-21) and stored box by box,
 //              so every TMA box (32 floats = one 128 B swizzle row, x 128 / 96 rows) is one contiguous run of memory:
 //                W2 [vertex tile][hi k0-31 | hi k32-63 | lo k0-31 | lo k32-63][128][32]   rn_tf32(W) and W - hi, made once at model create
-//                A2 [frame chunk][same four sub-tiles][96 = 8 frames x 12][32]             hi(A^T) and A^T - hi, written by k_chain_fwd
+//                A2 [frame chunk][same four sub-tiles][96 = 8 frames x 12][32]             hi(A^T) and A^T - hi, written by k_pose_chain_fwd
 //              joints 55..63 are zero padding; k-step 7 (joints 56..63) is never multiplied
 //   warps      0: TMA producer   1: TMEM alloc + MMA issuer   2..9: epilogue (lane = vertex), two groups of four; a group copies its
 //              accumulator to registers and releases it at once, so the MMAs of unit i+2 overlap the 3x4 apply of unit i
