@@ -578,11 +578,15 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
                                                   const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B, int tiles,
                                                   float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr) {
     __shared__ float sA[NJ * 12];
-    __shared__ float s_dt[SKB_TV * 12];
+    __shared__ __align__(16) float s_dt[SKB_TV * 12];
+    __shared__ float s_w[NJ][33];
     __shared__ float sred[32];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < NJ * 12; i += blockDim.x) sA[i] = A[(size_t)b * NJ * 12 + i];
-    float o[3] = {0.f, 0.f, 0.f};
+    const int jB = threadIdx.x % NJ, sB = threadIdx.x / NJ;       // phase-B role (threads < 220)
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
     float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f;
     const int t0 = blockIdx.x * tiles;
     for (int tl = 0; tl < tiles; ++tl) {
@@ -623,24 +627,42 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
         for (int k4 = 0; k4 < 3; ++k4)
             *reinterpret_cast<float4*>(&s_dt[threadIdx.x * 12 + k4 * 4]) = make_float4(dt[k4 * 4], dt[k4 * 4 + 1], dt[k4 * 4 + 2], dt[k4 * 4 + 3]);
         __syncthreads();
+        // phase B, register tiled: thread (joint jB, vertex residue sB) keeps the 12 entries of dA[jB] for vertices u = sB mod 4.
+        // The weight chunk [55 joints][32 vertices] is staged through shared memory (coalesced global read, conflict-free pitch 33),
+        // dT[u] is three broadcast 128-bit reads: 4 shared-memory wavefronts per 12 FMAs.  (One thread per (joint, entry) with a
+        // global weight load and a shared dT load per FMA was load-issue bound: 65 us per fitting step at B = 960.)
         const int nv = min(SKB_TV, V - v0);
+        for (int c0 = 0; c0 < nv; c0 += 32) {
+            for (int idx = threadIdx.x; idx < NJ * 32; idx += 256) {
+                const int j = idx >> 5, u = idx & 31;
+                s_w[j][u] = (c0 + u < nv) ? __ldg(w_jm + (size_t)j * V + v0 + c0 + u) : 0.f;
+            }
+            __syncthreads();
+            if (threadIdx.x < NJ * 4) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int t = threadIdx.x + r * 256;
-            if (t >= NJ * 12) break;
-            const int j = t / 12, k = t - j * 12;
-            const float* wj = w_jm + (size_t)j * V + v0;
-            float acc = o[r];
-            for (int u = 0; u < nv; ++u) acc = fmaf(__ldg(wj + u), s_dt[u * 12 + k], acc);
-            o[r] = acc;
+                for (int uu = sB; uu < 32; uu += 4) {
+                    const float w = s_w[jB][uu];
+                    const float4* d = reinterpret_cast<const float4*>(&s_dt[(c0 + uu) * 12]);
+                    const float4 d0 = d[0], d1 = d[1], d2 = d[2];
+                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]); acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]); acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                    acc[8] = fmaf(w, d2.x, acc[8]); acc[9] = fmaf(w, d2.y, acc[9]); acc[10] = fmaf(w, d2.z, acc[10]); acc[11] = fmaf(w, d2.w, acc[11]);
+                }
+            }
+            __syncthreads();
         }
     }
+    // combine the four vertex residues in a fixed order (s_dt is free now) and add into dA
+    __syncthreads();
+    if (threadIdx.x < NJ * 4) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int t = threadIdx.x + r * 256;
-        if (t >= NJ * 12) break;
+        for (int k = 0; k < 12; ++k) s_dt[sB * (NJ * 12) + jB * 12 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NJ * 12; t += 256) {
+        const float v = (s_dt[t] + s_dt[NJ * 12 + t]) + (s_dt[2 * NJ * 12 + t] + s_dt[3 * NJ * 12 + t]);
         const int j = t / 12, k = t - j * 12;
-        atomicAdd(&dA[(size_t)j * B * 12 + (size_t)b * 12 + k], o[r]);
+        atomicAdd(&dA[(size_t)j * B * 12 + (size_t)b * 12 + k], v);
     }
     float s;
     s = block_sum(gs0, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3], s);
