@@ -316,7 +316,7 @@ def main():
             c1.record()
             torch.cuda.synchronize(dev)
             lbs_eager_ms = c0.elapsed_time(c1) / 20           # through the Python module: includes ctypes + allocator + launch overhead
-            # device time of the same call: captured once into a CUDA graph (the chain / blend-GEMM fork becomes two branches), replayed
+            # device time of the same call: captured once into a CUDA graph and replayed
             gs = torch.cuda.Stream(device=dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(gs):
@@ -337,8 +337,8 @@ def main():
         Vn = 10475
         alg_bytes = 4.0 * (512 * 3 * Vn + Vn * 55 + 3 * Vn + T * (3 * 55 + 3)) + 4.0 * T * 3 * Vn     # SURVEY 8d bytes_fwd(B)
         hbm = float(peaks.get('hbm_gbs', 6650.0))
-        roof_lbs = {'kernel': 'lemo_smplx_forward (k_pose_to_rot, k_chain_fwd beside k_blend_tf32 [tcgen05 TF32 GEMM], k_skin_tc [tcgen05 TF32 '
-                              'GEMM + 3x4 apply], k_joints_fwd), B=%d, V=%d' % (T, Vn), 'bound': 'hbm',
+        roof_lbs = {'kernel': 'lemo_smplx_forward (k_pose_chain_fwd, k_blend_v2 [tcgen05 TF32 GEMM], k_skin_tc [tcgen05 TF32 GEMM + 3x4 apply], '
+                              'k_joints_fwd), B=%d, V=%d' % (T, Vn), 'bound': 'hbm',
                     'achieved': alg_bytes / (lbs_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s', 'frac': alg_bytes / (lbs_ms * 1e-3) / 1e9 / hbm,
                     'traffic': traffic.get('lbs_forward'), 'ms': lbs_ms, 'ms_eager_python_api': lbs_eager_ms,
                     'timing': 'CUDA-graph replay of one lemo_smplx_forward call (device time); ms_eager_python_api = the same call issued '

@@ -17,6 +17,9 @@ constexpr int GBN = 64, GBK = 16;
 // memory in slice order (deterministic), applies the full epilogue (bias / LeakyReLU / mask / accumulate) and stores.  The fit's GEMMs
 // have M = S*T <= 960 rows: 240 CTAs x 4 warps left 1.7 warps per scheduler and the FMA pipe 29 % busy (ncu: short-scoreboard stalls on
 // the shared-memory operands); slicing K four ways gives every scheduler ~7 warps without a second pass or atomics.
+// Measured: the narrow GEMMs (N = 126 / 32) halve (28 -> 11-15 us), the 512 x 512 ones stay at 36-51 us, i.e. those are bound by
+// per-SM throughput, not latency.  A 64 x 64 tile with 8 x 8 outputs per thread (251 registers, 8 warps per SM) was tried for them and
+// is slower end to end (1.505 vs 1.479 ms per fitting step); the tensor-core route is closed by accuracy (vposer.cu).
 template <int GBM, bool CLUSTER = false>
 __global__ void __launch_bounds__(GBM * 4) k_gemm(GemmP p) {
     constexpr int NT = GBM * 4, NB = GBN * GBK / NT;

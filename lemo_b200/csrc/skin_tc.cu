@@ -16,6 +16,11 @@
 //   warps      0: TMA producer   1: TMEM alloc + MMA issuer   2..9: epilogue (lane = vertex), two groups of four; a group copies its
 //              accumulator to registers and releases it at once, so the MMAs of unit i+2 overlap the 3x4 apply of unit i
 //   HBM        reads v_posed (4.B.3V) + W2 (5.4 MB, L2 resident), writes verts (4.B.3V)
+// Measured on B200 (tools/diag_skin_tl.py, CTA-0 timeline): 14 us warm at B=120; a unit costs ~1.2 us of which 0.85 us is the 21 MMAs
+// (78 cycles each: M=128 x N=96 x K=8 TF32 with both operands read from shared memory), the rest the hand-over to the next unit.
+// Tried and dropped: A2 streamed as plain fp32 with A_lo = A - trunc(A) written next to each landed tile by two converter warps
+// (the tensor core truncates an fp32 operand to TF32 itself; results identical, 9.5e-7 vs the CUDA-core kernel) -- it halves the
+// re-streamed operand but the kernel is not L2-bandwidth bound, 20.0 vs 19.5 us under ncu.
 #include "body.cuh"
 #include <cuda.h>
 #include <cstdio>

@@ -12,6 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
     python bench.py $FAST > gpurun_out/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_conv_tc" -s 40 -c 2 -o gpurun_out/prof_conv_tc -f \
     python bench.py $FAST > gpurun_out/bench_under_ncu2.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_blend_tf32|k_skin_fwd|k_chain_fwd|k_pose_to_rot" -s 16 -c 4 -o gpurun_out/prof_lbs -f \
-    python tools/diag_blend.py > gpurun_out/diag_under_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_blend_v2|k_skin_tc|k_pose_chain_fwd|k_joints_fwd" -s 4 -c 4 -o gpurun_out/prof_lbs -f \
+    python tools/diag_lbs.py 120 > gpurun_out/diag_under_ncu.log 2>&1
+timeout 120 python tools/diag_lbs.py 120 300 > gpurun_out/diag_lbs.log 2>&1
 ls -la gpurun_out | tail -12

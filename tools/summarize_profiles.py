@@ -87,6 +87,10 @@ def full(tag):
                 traffic[short] = rd + wr
             except Exception:
                 pass
+    # one lemo_smplx_forward = pose/chain + blend GEMM + skinning GEMM + output joints (bench.py: roofline_lbs.traffic)
+    parts = ['k_pose_chain_fwd', 'k_blend_v2', 'k_skin_tc', 'k_joints_fwd']
+    if all(p in traffic for p in parts):
+        traffic['lbs_forward'] = sum(traffic[p] for p in parts)
     traffic['_source'] = 'profiles/%s_ncu_full_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)' % tag
     open(os.path.join(PROF, tag + '_ncu_full_summary.md'), 'w').write('\n'.join(out) + '\n')
     json.dump(traffic, open(path, 'w'), indent=1)
