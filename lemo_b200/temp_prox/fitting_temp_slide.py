@@ -83,6 +83,13 @@ class SMPLifyLoss(torch.nn.Module):
         return total, T
 
 
+def create_loss(loss_type='smplify', **kwargs):
+    """fitting_temp_slide.py:316-322: 'smplify' -> SMPLifyLoss (the 'camera_init' loss belongs to PROX stage 1 and is not on this path)."""
+    if loss_type == 'smplify':
+        return SMPLifyLoss(**kwargs)
+    raise ValueError('Unknown loss type: {}'.format(loss_type))
+
+
 class FittingMonitor:
     """run_fitting (:169-313) for the Adam branch: `maxiters` closure steps, NaN/Inf stop, first-15 % gradient erase."""
 

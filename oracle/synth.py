@@ -109,7 +109,10 @@ def make_prox_problem(B, D=32, m_scene=3000, seed=0):
              left_hand_pose=clean[:, 48:60], right_hand_pose=clean[:, 60:72], jaw_pose=(0.05 * g.standard_normal((B, 3))).astype(f32),
              leye_pose=np.zeros((B, 3), f32), reye_pose=np.zeros((B, 3), f32), expression=(0.3 * g.standard_normal((B, 10))).astype(f32),
              betas=np.repeat(clean[:1, 6:16], B, 0))
-    jm = g.permutation(127)[:118].astype(np.int64)
+    # the reference's own tables (exported data, tools/export_assets.py prox): OpenPose coco25 map with hands + face (118 joints,
+    # temp_prox/main_slide.py:160-179), friction (307) and contact (1121) vertex ids (fit_temp_loadprox_slide.py:349-362)
+    pt = np.load(os.path.join(_HERE, '..', 'lemo_b200', 'assets', 'prox_tables.npz'))
+    jm = pt['smplx_coco25_h1_f1_c0'].astype(np.int64)
     Rc = rb.rodrigues(torch.tensor([[0.02, -0.01, 0.03]]))[0]
     tc = torch.tensor([0.01, 0.02, 0.0])
     Rw = rb.rodrigues(torch.tensor([[1.4, 0.1, -0.1]]))[0]
@@ -120,7 +123,7 @@ def make_prox_problem(B, D=32, m_scene=3000, seed=0):
     cfg = dict(gt_joints=torch.from_numpy((900 * g.random((B, 118, 2)) + 50).astype(f32)), joints_conf=torch.from_numpy((0.3 + 0.7 * g.random((B, 118))).astype(f32)),
                joint_weights=torch.ones(B, 118), joint_map=torch.from_numpy(jm), camera=(Rc, tc, 1060.53, 1060.38, torch.tensor([951.30, 536.77])),
                cam2world=(Rw, tw), sdf=torch.from_numpy(sdf), grid_min=torch.tensor([-3., -3., -3.]), grid_max=torch.tensor([3., 3., 3.]),
-               fric_ids=torch.from_numpy(g.choice(V, 307, replace=False)), contact_ids=torch.from_numpy(g.choice(V, 1121, replace=False)),
+               fric_ids=torch.from_numpy(pt['friction_ids'].astype(np.int64)), contact_ids=torch.from_numpy(pt['contact_ids'].astype(np.int64)),
                scene_v=torch.from_numpy((g.random((m_scene, 3)) * np.array([6, 6, 0.1]) - np.array([3, 3, -0.25])).astype(f32)),
                w=dict(data=1.0, body_pose=4.78e-5 * 1e3, hand_prior=4.78e-5 * 1e3, expr=0.03, jaw=0.03, sdf=0.003, fric_t=20.0, fric_n=10.0,
                       contact=1.0, smooth=1e8))

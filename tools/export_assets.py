@@ -58,5 +58,41 @@ def main():
     np.savez_compressed(os.path.join(OUT_G, 'seed_clips.npz'), **clips)
 
 
+def export_prox_tables():
+    """lemo_b200/assets/prox_tables.npz: OpenPose joint maps of the reference's own smpl_to_openpose (temp_prox/misc_utils.py:87-197) for
+    model_type='smplx', every (use_hands, use_face, use_face_contour) combination and both OpenPose formats; the friction (307) and contact
+    (1121) vertex-id lists built with the reference's expressions (fit_temp_loadprox_slide.py:349-362, `list(set(...))` in THIS
+    interpreter); and small known-answer vectors of the reference's prior / robustifier modules (prior.py:53-98, misc_utils.py:61-85)."""
+    sys.path.insert(0, os.path.join(REF, 'temp_prox'))
+    import misc_utils as mu
+    import prior as pr
+    j = lambda p: json.load(open(os.path.join(REF, p)))
+    tabs = {}
+    for fmt in ('coco25', 'coco19'):
+        for h in (0, 1):
+            for f in (0, 1):
+                for c in (0, 1):
+                    m = mu.smpl_to_openpose('smplx', use_hands=bool(h), use_face=bool(f), use_face_contour=bool(c), openpose_format=fmt)
+                    tabs['smplx_%s_h%d_f%d_c%d' % (fmt, h, f, c)] = np.asarray(m, np.int64)
+    seg = lambda part: list(set(j('body_segments/%s.json' % part)['verts_ind']))
+    tabs['friction_ids'] = np.concatenate([seg(p) for p in ('L_Leg', 'R_Leg', 'gluteus')]).astype(np.int64)
+    tabs['contact_ids'] = np.concatenate([seg(p) for p in ('L_Leg', 'R_Leg', 'L_Hand', 'R_Hand', 'gluteus', 'back', 'thighs')]).astype(np.int64)
+    np.savez(os.path.join(OUT_A, 'prox_tables.npz'), **tabs)
+    print({k: v.shape for k, v in tabs.items()})
+    # known-answer vectors of the reference modules themselves
+    g = torch.Generator().manual_seed(7)
+    pose = 0.5 * torch.randn(5, 63, generator=g)
+    pose_g = 0.5 * torch.randn(5, 66, generator=g)
+    res = 3.0 * torch.randn(4, 118, 2, generator=g)
+    gold = dict(pose=pose.numpy(), pose_g=pose_g.numpy(), res=res.numpy(),
+                angle=pr.SMPLifyAnglePrior()(pose).numpy(), angle_g=pr.SMPLifyAnglePrior()(pose_g, with_global_pose=True).numpy(),
+                l2=pr.L2Prior()(pose).numpy(), gmof100=mu.GMoF(rho=100)(res).numpy(), gmof_unscaled=mu.GMoF_unscaled(rho=0.5)(res).numpy(),
+                mapped=mu.JointMapper(tabs['smplx_coco25_h1_f1_c0'])(torch.arange(127.).view(1, 127, 1).expand(2, 127, 3)).numpy())
+    np.savez_compressed(os.path.join(OUT_G, 'reference_golden_prox.npz'), **gold)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'prox':
+        export_prox_tables()
+    else:
+        main()
