@@ -102,3 +102,25 @@ def test_infill_mask_rows_and_padding():
     assert p.shape == (4, 210, 46)
     assert np.all(p[0, masked + 1, :] == 0.0) and np.all(p[0, 205:209, :] == 0.0)
     assert np.array_equal(p[1, 1:-1, 8:-8], x[1]) and np.array_equal(p[1, 0, 8:-8], x[1, 1]) and np.array_equal(p[2, 5, 0:8], x[2, 4, 8:0:-1])
+
+
+def test_tgm_restatement_against_scipy():
+    """torchgeometry 0.1.2 is absent from the reference tree and this image (parity unpinned); its restated
+    conversions are at least checked here against an INDEPENDENT implementation (scipy.spatial.transform.Rotation) on the inputs the
+    fitting path produces: all four branches of rotation_matrix_to_quaternion (large rotations about each axis), small angles, and
+    the canonical-sign convention of quaternion_to_angle_axis (angle in [0, pi] after the aa -> R -> aa round trip)."""
+    from scipy.spatial.transform import Rotation
+    g = np.random.default_rng(5)
+    aa = np.concatenate([g.standard_normal((200, 3)) * 0.8,                         # generic
+                         g.standard_normal((50, 3)) * 1e-3,                         # near identity
+                         np.eye(3)[g.integers(0, 3, 60)] * 3.0 + 0.05 * g.standard_normal((60, 3)),    # ~172 deg about x / y / z
+                         -np.eye(3)[g.integers(0, 3, 60)] * 2.5 + 0.05 * g.standard_normal((60, 3))]).astype(np.float64)
+    R_sp = Rotation.from_rotvec(aa).as_matrix()
+    R_tgm = rb.tgm_aa_to_rotmat(torch.from_numpy(aa)).numpy()                       # angle_axis_to_rotation_matrix (utils/utils.py:89)
+    assert np.abs(R_tgm - R_sp).max() < 3e-6          # tgm normalises the axis with (theta + 1e-6): an O(1e-6 / theta) deviation by design
+    assert np.abs(rb.rodrigues(torch.from_numpy(aa)).numpy() - R_sp).max() < 1e-6   # lbs.py batch_rodrigues adds 1e-8 to the vector
+    aa_back = rb.rotmat_to_aa(torch.from_numpy(R_sp)).numpy()                       # rotation_matrix_to_angle_axis (utils/utils.py:80)
+    ref = Rotation.from_matrix(R_sp).as_rotvec()                                    # scipy: angle in [0, pi]
+    assert np.abs(aa_back - ref).max() < 1e-7, np.abs(aa_back - ref).max()
+    # and as rotations (insensitive to any sign convention)
+    assert np.abs(Rotation.from_rotvec(aa_back).as_matrix() - R_sp).max() < 1e-9
