@@ -75,3 +75,30 @@ def test_create_loss_dispatch():
     with pytest.raises(ValueError):
         fs.create_loss('camera_init')
     assert fs.create_loss.__doc__
+
+
+def test_fitting_monitor_adam_loop_semantics(capsys):
+    """FittingMonitor.run_fitting (fitting_temp_slide.py:169-313, Adam branch) on a toy problem: `maxiters` steps, the first 15 % of
+    the batch keeps its values when erase_first is set (:281-288), and a non-finite loss stops the run with the reference's message (:197-203)."""
+    from lemo_b200.temp_prox.fitting_temp_slide import FittingMonitor
+    target = torch.arange(20.).view(20, 1).expand(20, 3).clone()
+    p = torch.zeros(20, 3, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=0.1)
+    calls = []
+
+    def closure():
+        calls.append(1)
+        return ((p - target) ** 2).sum()
+    loss = FittingMonitor(maxiters=25, erase_first=True).run_fitting(opt, closure, [p])
+    assert len(calls) == 25 and torch.isfinite(loss)
+    assert float(p[:3].detach().abs().sum()) == 0.0 and float(p[3:].detach().abs().sum()) > 0.0       # int(20 * 0.15) = 3 frames frozen
+    q = torch.zeros(4, requires_grad=True)
+    n_calls = []
+    FittingMonitor(maxiters=40, check_every=10).run_fitting(torch.optim.Adam([q], lr=0.1),
+                                                            lambda: (n_calls.append(1), (q * float('nan')).sum())[1], [q])
+    assert 'NaN loss value, stopping!' in capsys.readouterr().out and len(n_calls) == 10
+    q = torch.zeros(4, requires_grad=True)                 # (the NaN run above poisoned the old one, as it does in the reference)
+    FittingMonitor(maxiters=3).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: (q * 0).sum() + float('inf'), [q])
+    assert 'Infinite loss value, stopping!' in capsys.readouterr().out
+    with pytest.raises(RuntimeError, match='capturable'):
+        FittingMonitor(maxiters=10, use_cuda_graph=True).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: q.sum(), [q])
