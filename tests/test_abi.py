@@ -70,3 +70,20 @@ def test_no_cpu_fallback_in_product():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), os.path.join(dp, f)
+
+
+def test_bad_arguments_return_status_and_message(built_lib):
+    """Error contract of the boundary: a non-zero int status plus a thread-local message via lemo_last_error(),
+    never an exception or a crash across the ABI -- checked on entry points of every subsystem with null / empty arguments (the
+    argument checks run before any CUDA call, so this needs no GPU)."""
+    L = built_lib
+    for name in ('lemo_smplx_forward', 'lemo_smplx_backward', 'lemo_gather_rows', 'lemo_scatter_rows_add', 'lemo_vposer_decode',
+                 'lemo_vposer_decode_backward', 'lemo_enc_forward', 'lemo_enc_backward_input', 'lemo_ae_forward', 'lemo_chamfer_forward',
+                 'lemo_chamfer_backward', 'lemo_camera_project', 'lemo_sdf_sample', 'lemo_adam_step', 'lemo_fit_run', 'lemo_fit_run_perframe',
+                 'lemo_fit_set_sequence', 'lemo_fit_get'):
+        f = getattr(L, name)
+        args = [None if t in (C.c_void_p,) or 'LP_' in t.__name__ or t.__name__.endswith('_p') else 0 for t in f.argtypes]
+        status = f(*args)                                  # empty problem (B = n = 0) on null buffers
+        assert status != 0, name
+        msg = L.lemo_last_error().decode()
+        assert msg and '@' in msg, (name, msg)             # "<what> (<failed condition>) @file:line"
