@@ -3,7 +3,7 @@
 //     verts[b,v]  = T[v,b,:3,:3] . v_posed[b,v] + T[v,b,:3,3] + transl[b]
 // The reference materialises W.repeat(B) (274 MB at B=119) and T [B,V,4,4] (80 MB); the CUDA-core kernel k_skin_fwd spends 660 FMAs
 // per (frame, vertex) and is FMA-bound (23 us floor for the dense synthetic weights, 43 us measured at B=120).  Here the per-vertex
-// weighted-transform reduction is one GEMM  M = vertices (128 per tile), N = frames x 12 (144 = 12 frames per unit), K = 55 -> 56 joints,
+// weighted-transform reduction is one GEMM  M = vertices (128 per tile), N = frames x 12 (96 = 8 frames per unit), K = 55 -> 56 joints,
 // on tcgen05.mma kind::tf32 with the accumulator in TMEM, and the 3x4 apply is the epilogue: T never leaves the SM.
 //
 //   unit       (vertex tile of 128, chunk of 8 frames); persistent CTAs walk a contiguous range of units (vertex tile major), so the
