@@ -32,7 +32,7 @@ UNIT = 'sequence-iterations/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--seqs-per-gpu', type=int, default=8)
@@ -60,6 +60,35 @@ class ClockSampler:
         self.index, self.rows, self.stop_flag, self.th = index, [], False, None
 
     def _run(self):
+        # NVML first (a poll costs tens of microseconds, so a 50 ms timed region still gets ~10 samples); nvidia-smi as the fallback
+        # (one process spawn per poll: 5-10 samples per second)
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))        # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            r = int(get_reasons(h))
+            row = [str(sm), str(mx), '%.1f' % pw, 'Not Active', 'Not Active', 'Not Active', 'Not Active']
+            for mask, col in bits:
+                if r & mask:
+                    row[col] = 'Active'
+            self.rows.append(row)
+            time.sleep(0.005)
+
+    def _run_smi(self):
         q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         while not self.stop_flag:
