@@ -111,6 +111,9 @@ int lemo_scatter_rows_add(const float* g_rows, const int32_t* idx, int32_t B, in
 int lemo_rot6d_to_rotmat(const float* x6, int32_t n, float* R, void* stream);                /* utils.py:64-70  */
 int lemo_rot6d_to_rotmat_backward(const float* x6, const float* dR, int32_t n, float* dx6, void* stream);
 int lemo_rotmat_to_aa(const float* R, int32_t n, float* aa, void* stream);                   /* utils.py:74-81 (tgm) */
+/* adjoint of lemo_rotmat_to_aa through the selected quaternion branch (what autograd does through tgm): daa [n,3] -> dR [n,9];
+ * makes vposer.decode(Z,'aa') / convert_to_3D_rot differentiable like the reference's graph (utils.py:148, opt_amass_temp.py:356). */
+int lemo_rotmat_to_aa_backward(const float* R, const float* daa, int32_t n, float* dR, void* stream);
 int lemo_aa_to_rot6d(const float* aa, int32_t n, float* x6, void* stream);                   /* utils.py:127-130 (tgm) */
 int lemo_rodrigues(const float* aa, int32_t n, float* R, void* stream);                      /* lbs.py:166-193  */
 int lemo_rodrigues_backward(const float* aa, const float* dR, int32_t n, float* daa, void* stream);
@@ -186,12 +189,15 @@ int lemo_infill_finalize(const float* rec_pad, const float* clip, const double* 
 
 /* ---------------------------------------------------------------- Chamfer (temp_prox/dist_chamfer.py) --- */
 /* xyz1 [B,n,3]; xyz2 [B,m,3] with xyz2_batch_stride floats between batches (0 = one shared scene).
- * dist = squared L2 to the nearest neighbour (first minimum wins), idx int32.  (dist_chamfer.py:10-28) */
+ * dist = squared L2 to the nearest neighbour (first minimum wins), idx int32.  (dist_chamfer.py:10-28)
+ * Arithmetic is pinned: d = fma(dz,dz, fma(dy,dy, dx*dx)) with dx = x1 - x2, so indices are bit-exact against
+ * oracle/csrc/chamfer_ref.c, ties included.  dist2 and idx2 may both be NULL: the xyz2 -> xyz1 direction is then skipped
+ * (the PROX contact term consumes dist1 only, fitting_temp_slide.py:749-753). */
 int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m,
                          int64_t xyz2_batch_stride, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
                          void* stream);
 /* grad 2*g*(x1-x2) scattered to both clouds (dist_chamfer.py:30-45).  d_xyz2 has the same batch stride
- * as xyz2 (a shared scene accumulates over the batch).  Outputs are overwritten. */
+ * as xyz2 (a shared scene accumulates over the batch).  Outputs are overwritten.  g_dist2 / idx2 may both be NULL. */
 int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m,
                           int64_t xyz2_batch_stride, const float* g_dist1, const float* g_dist2,
                           const int32_t* idx1, const int32_t* idx2, float* d_xyz1, float* d_xyz2, void* stream);
@@ -264,6 +270,7 @@ void lemo_host_rodrigues_bwd(const float* aa, const float* dR, float* daa);
 void lemo_host_gs6d(const float* x6, float* R);
 void lemo_host_gs6d_bwd(const float* x6, const float* dR, float* dx6);
 void lemo_host_rotmat_to_aa(const float* R, float* aa);
+void lemo_host_rotmat_to_aa_bwd(const float* R, const float* daa, float* dR);
 void lemo_host_aa_to_rotmat_tgm(const float* aa, float* R);
 
 #ifdef __cplusplus

@@ -89,6 +89,7 @@ SIGNATURES = {
     'lemo_rot6d_to_rotmat': (C.c_int, [_P, _I, _P, _P]),
     'lemo_rot6d_to_rotmat_backward': (C.c_int, [_P, _P, _I, _P, _P]),
     'lemo_rotmat_to_aa': (C.c_int, [_P, _I, _P, _P]),
+    'lemo_rotmat_to_aa_backward': (C.c_int, [_P, _P, _I, _P, _P]),
     'lemo_aa_to_rot6d': (C.c_int, [_P, _I, _P, _P]),
     'lemo_rodrigues': (C.c_int, [_P, _I, _P, _P]),
     'lemo_rodrigues_backward': (C.c_int, [_P, _P, _I, _P, _P]),
@@ -135,6 +136,7 @@ SIGNATURES = {
     'lemo_host_gs6d': (None, [_P, _P]),
     'lemo_host_gs6d_bwd': (None, [_P, _P, _P]),
     'lemo_host_rotmat_to_aa': (None, [_P, _P]),
+    'lemo_host_rotmat_to_aa_bwd': (None, [_P, _P, _P]),
     'lemo_host_aa_to_rotmat_tgm': (None, [_P, _P]),
 }
 STATUS_FUNCS = {k for k, (r, _) in SIGNATURES.items() if r is C.c_int and k not in ('lemo_version', 'lemo_model_num_verts')}

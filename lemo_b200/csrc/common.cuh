@@ -181,6 +181,62 @@ HD void rotmat_to_aa_tgm(const float* R, float* aa) {
     aa[0] = x * k; aa[1] = y * k; aa[2] = z * k;
 }
 
+// adjoint of rotmat_to_aa_tgm: dR[9] from daa[3], differentiating the SELECTED quaternion branch exactly as autograd does through
+// torchgeometry's mask-multiplied branches (the masks carry no gradient).  This is what lets vposer.decode(Z,'aa') and
+// convert_to_3D_rot carry gradient like the reference's own graph (utils/utils.py:148, opt_amass_temp.py:356-357,
+// fitting_temp_slide.py:243).  At exactly zero rotation (s2 == 0) torch's where() backward yields NaN; here k = 2 is a constant.
+HD void rotmat_to_aa_tgm_bwd(const float* R, const float* daa, float* dR) {
+    const float t00 = R[0], t01 = R[3], t02 = R[6], t10 = R[1], t11 = R[4], t12 = R[7], t20 = R[2], t21 = R[5], t22 = R[8];
+    float q[4], tt;
+    int br;
+    if (t22 < 1e-6f) {
+        if (t00 > t11) { br = 0; tt = 1.f + t00 - t11 - t22; q[0] = t12 - t21; q[1] = tt; q[2] = t01 + t10; q[3] = t20 + t02; }
+        else           { br = 1; tt = 1.f - t00 + t11 - t22; q[0] = t20 - t02; q[1] = t01 + t10; q[2] = tt; q[3] = t12 + t21; }
+    } else {
+        if (t00 < -t11) { br = 2; tt = 1.f - t00 - t11 + t22; q[0] = t01 - t10; q[1] = t20 + t02; q[2] = t12 + t21; q[3] = tt; }
+        else            { br = 3; tt = 1.f + t00 + t11 + t22; q[0] = tt; q[1] = t12 - t21; q[2] = t20 - t02; q[3] = t01 - t10; }
+    }
+    const float sc = 0.5f / sqrtf(tt);
+    const float w = q[0] * sc, x = q[1] * sc, y = q[2] * sc, z = q[3] * sc;
+    const float s2 = x * x + y * y + z * z, s = sqrtf(s2);
+    const float two_theta = 2.f * (w < 0.f ? atan2f(-s, -w) : atan2f(s, w));
+    const float k = s2 > 0.f ? two_theta / s : 2.f;
+    float dv[4] = {0.f, daa[0] * k, daa[1] * k, daa[2] * k};          // d(w,x,y,z)
+    if (s2 > 0.f) {
+        const float dk = daa[0] * x + daa[1] * y + daa[2] * z;
+        const float dtwo = dk / s;
+        const float den = s2 + w * w;
+        const float ds = -dk * two_theta / s2 + dtwo * 2.f * w / den;
+        dv[0] = dtwo * 2.f * (-s) / den;
+        const float ds2 = ds / (2.f * s);
+        dv[1] += 2.f * x * ds2; dv[2] += 2.f * y * ds2; dv[3] += 2.f * z * ds2;
+    }
+    float dq[4];
+    float dsc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dq[i] = dv[i] * sc; dsc += dv[i] * q[i]; }
+    const float dtt = -dsc * sc / (2.f * tt);
+    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // gradient on t[i][j], row-major
+    if (br == 0) {
+        const float a = dtt + dq[1];
+        g[0] += a; g[4] -= a; g[8] -= a; g[5] += dq[0]; g[7] -= dq[0]; g[1] += dq[2]; g[3] += dq[2]; g[6] += dq[3]; g[2] += dq[3];
+    } else if (br == 1) {
+        const float a = dtt + dq[2];
+        g[0] -= a; g[4] += a; g[8] -= a; g[6] += dq[0]; g[2] -= dq[0]; g[1] += dq[1]; g[3] += dq[1]; g[5] += dq[3]; g[7] += dq[3];
+    } else if (br == 2) {
+        const float a = dtt + dq[3];
+        g[0] -= a; g[4] -= a; g[8] += a; g[1] += dq[0]; g[3] -= dq[0]; g[6] += dq[1]; g[2] += dq[1]; g[5] += dq[2]; g[7] += dq[2];
+    } else {
+        const float a = dtt + dq[0];
+        g[0] += a; g[4] += a; g[8] += a; g[5] += dq[1]; g[7] -= dq[1]; g[6] += dq[2]; g[2] -= dq[2]; g[1] += dq[3]; g[3] -= dq[3];
+    }
+    // t = R^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dR[j * 3 + i] = g[i * 3 + j];
+}
+
 // aa -> R, torchgeometry 0.1.2 angle_axis_to_rotation_matrix (init conversion, utils/utils.py:84-90)
 HD void aa_to_rotmat_tgm(const float* aa, float* R) {
     const float th2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];

@@ -251,13 +251,13 @@ __global__ void k_smooth_bwd_a(const float* __restrict__ gx, int T, int H, int W
     int dds[2] = {d + 1, -1};
     if (d == 1) dds[1] = 0;
     if (d == H - 4) dds[1] = H - 1;             // reflect(H-2) = 2(H-3)-(H-2) = H-4   (H-2 = 243 rows before padding)
-    int tts[2] = {t + 8, -1};
+    int tts[3] = {t + 8, -1, -1};               // own slot, left reflection, right reflection (they overlap when T-1 < 18)
     if (t >= 1 && t <= 8) tts[1] = 8 - t;
-    if (t >= n - 9 && t <= n - 2) tts[1] = 8 + 2 * (n - 1) - t;
+    if (t >= n - 9 && t <= n - 2) tts[2] = 8 + 2 * (n - 1) - t;
     float a = 0.f;
     for (int i = 0; i < 2; ++i) {
         if (dds[i] < 0) continue;
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 3; ++j) {
             if (tts[j] < 0) continue;
             a += gx[(size_t)s * PS + (dds[i] + 1) * Wp + tts[j] + 1];
         }
@@ -474,6 +474,8 @@ int lemo_fit_create(const LemoModel* model, LemoVPoser* vposer, const float* unu
         LEMO_CUDA(cudaMemcpy(f->stats + 243, cfg->h_smooth_std, 243 * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (cfg->mode == 0 && f->enc) {
+        // F.pad(..., (8,8,1,1), 'reflect') needs more than 8 velocity frames (torch raises otherwise, opt_amass_temp.py:385-387)
+        LEMO_CHECK(f->T - 1 > 8, "the smoothness prior reflect-pads 8 frames: need n_frames >= 10");
         f->geom = f->enc->geom[0];
         LEMO_CHECK(f->geom.H == 245 && f->geom.W == f->T - 1 + 16, "Enc handle must be created for H=245, W=T-1+16");
         LEMO_CHECK(f->enc->maxN >= f->S && f->enc->with_backward, "Enc handle too small / without backward");

@@ -31,6 +31,15 @@ __global__ void k_rotmat_to_aa(const float* __restrict__ R, int n, float* __rest
     rotmat_to_aa_tgm(r, a);
     for (int k = 0; k < 3; ++k) aa[i * 3 + k] = a[k];
 }
+__global__ void k_rotmat_to_aa_bwd(const float* __restrict__ R, const float* __restrict__ daa, int n, float* __restrict__ dR) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r[9], a[3], g[9];
+    for (int k = 0; k < 9; ++k) r[k] = R[i * 9 + k];
+    for (int k = 0; k < 3; ++k) a[k] = daa[i * 3 + k];
+    rotmat_to_aa_tgm_bwd(r, a, g);
+    for (int k = 0; k < 9; ++k) dR[i * 9 + k] = g[k];
+}
 __global__ void k_aa_to_rot6d(const float* __restrict__ aa, int n, float* __restrict__ x6) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -86,6 +95,7 @@ int lemo_version(void) { return 100; }
 int lemo_rot6d_to_rotmat(const float* x6, int32_t n, float* R, void* stream) { EW(k_gs6d, n, x6, n, R); }
 int lemo_rot6d_to_rotmat_backward(const float* x6, const float* dR, int32_t n, float* dx6, void* stream) { EW(k_gs6d_bwd, n, x6, dR, n, dx6); }
 int lemo_rotmat_to_aa(const float* R, int32_t n, float* aa, void* stream) { EW(k_rotmat_to_aa, n, R, n, aa); }
+int lemo_rotmat_to_aa_backward(const float* R, const float* daa, int32_t n, float* dR, void* stream) { EW(k_rotmat_to_aa_bwd, n, R, daa, n, dR); }
 int lemo_aa_to_rot6d(const float* aa, int32_t n, float* x6, void* stream) { EW(k_aa_to_rot6d, n, aa, n, x6); }
 int lemo_rodrigues(const float* aa, int32_t n, float* R, void* stream) { EW(k_rodrigues, n, aa, n, R); }
 int lemo_rodrigues_backward(const float* aa, const float* dR, int32_t n, float* daa, void* stream) { EW(k_rodrigues_bwd, n, aa, dR, n, daa); }
@@ -107,5 +117,6 @@ void lemo_host_rodrigues_bwd(const float* aa, const float* dR, float* daa) { rod
 void lemo_host_gs6d(const float* x6, float* R) { gs6d_fwd(x6, R); }
 void lemo_host_gs6d_bwd(const float* x6, const float* dR, float* dx6) { gs6d_bwd(x6, dR, dx6); }
 void lemo_host_rotmat_to_aa(const float* R, float* aa) { rotmat_to_aa_tgm(R, aa); }
+void lemo_host_rotmat_to_aa_bwd(const float* R, const float* daa, float* dR) { rotmat_to_aa_tgm_bwd(R, daa, dR); }
 void lemo_host_aa_to_rotmat_tgm(const float* aa, float* R) { aa_to_rotmat_tgm(aa, R); }
 }

@@ -74,10 +74,10 @@ class _Fitter:
         cfg.use_cuda_graph = 1 if use_cuda_graph else 0
         with torch.cuda.device(idx):
             self._dmodel = smplx_model.device_model(self.device)
-            self._vp = vposer.handle(self.device, self.B)
+            self._vp = vposer.handle(self.device, self.B, private=True)      # private scratch: baked into this fitter's graph
             self._enc = None
             if self.MODE == 0 and enc is not None and w['w_smooth'] > 0:
-                self._enc = enc.net(self.device, n_seq, 245, n_frames - 1 + 16)
+                self._enc = enc.net(self.device, n_seq, 245, n_frames - 1 + 16, private=True)
             h = C.c_void_p()
             _lib.call('lemo_fit_create', self._dmodel.handle, self._vp.handle, None,
                       self._enc.handle if self._enc else None, C.byref(cfg), idx, C.byref(h))

@@ -90,8 +90,12 @@ class Enc(nn.Module):
     def _flat(self):
         return np.concatenate([self._params[k.replace('.', '/')].detach().cpu().numpy().ravel() for k in self._keys]).astype(np.float32)
 
-    def net(self, device, N, H, W):
+    def net(self, device, N, H, W, private=False):
+        """private=True: a fresh, un-cached handle (own activation planes) for a fused fitter that bakes them into its CUDA graph."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
+        if private:
+            with torch.cuda.device(idx):
+                return _Net(0, 1, self._flat(), N, H, W, idx)
         key = (idx, N, H, W)
         if key not in self._nets:
             with torch.cuda.device(idx):

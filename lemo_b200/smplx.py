@@ -45,7 +45,10 @@ def _normalise(d, num_pca_comps, flat_hand_mean):
     i32 = lambda a: np.ascontiguousarray(np.asarray(a), np.int32)
     V = np.asarray(d['v_template']).shape[0]
     out = {'v_template': f32(d['v_template'])}
-    out['shapedirs'] = f32(np.asarray(d['shapedirs'])[:, :, :20])
+    sd = np.asarray(d['shapedirs'])
+    if sd.shape[-1] >= 310:     # SMPL-X v1.1 files: 300 shape + 100 expression components; expression dirs start at 300 (smplx body_models)
+        sd = np.concatenate([sd[:, :, :10], sd[:, :, 300:310]], axis=-1)
+    out['shapedirs'] = f32(sd[:, :, :20])
     pd = np.asarray(d['posedirs'])
     if pd.ndim == 3:                                   # [V,3,486] -> [486, 3V]  (body_model.py:126-128)
         pd = pd.reshape(-1, pd.shape[-1]).T

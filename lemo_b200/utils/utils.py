@@ -25,6 +25,34 @@ class _Rot6dToMat(torch.autograd.Function):
         return dx
 
 
+class _MatToAA(torch.autograd.Function):
+    """tgm.rotation_matrix_to_angle_axis on [n,9] (utils/utils.py:74-81) with its adjoint through the selected quaternion branch."""
+
+    @staticmethod
+    def forward(ctx, R):
+        R = R.contiguous().float()
+        n = R.numel() // 9
+        aa = torch.empty(n, 3, device=R.device)
+        _lib.call('lemo_rotmat_to_aa', _lib.ptr(R), n, _lib.ptr(aa), _lib.cur_stream(R.device))
+        ctx.save_for_backward(R)
+        return aa
+
+    @staticmethod
+    def backward(ctx, gaa):
+        (R,) = ctx.saved_tensors
+        n = R.numel() // 9
+        dR = torch.empty_like(R)
+        _lib.call('lemo_rotmat_to_aa_backward', _lib.ptr(R), _lib.ptr(gaa.contiguous().float()), n, _lib.ptr(dR), _lib.cur_stream(R.device))
+        return dR
+
+
+def _no_grad_input(x, what):
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise RuntimeError('%s: this conversion is forward-only here (the reference uses it at initialisation, without gradient); '
+                           'differentiable paths: ContinousRotReprDecoder.decode / matrot2aa, convert_to_3D_rot, vposer.decode' % what)
+    return x.detach()
+
+
 def _ew(name, x, in_w, out_w):
     x = x.contiguous().float()
     n = x.numel() // in_w
@@ -42,17 +70,17 @@ class ContinousRotReprDecoder:
 
     @staticmethod
     def matrot2aa(pose_matrot):
-        return _ew('lemo_rotmat_to_aa', pose_matrot.detach().reshape(-1, 9), 9, 3)
+        return _MatToAA.apply(pose_matrot.reshape(-1, 9))
 
     @staticmethod
     def aa2matrot(pose):
-        x6 = _ew('lemo_aa_to_rot6d', pose.detach().reshape(-1, 3), 3, 6)
+        x6 = _ew('lemo_aa_to_rot6d', _no_grad_input(pose, 'aa2matrot').reshape(-1, 3), 3, 6)
         return _Rot6dToMat.apply(x6)      # exact for a rotation's own first two columns
 
 
 def convert_to_6D_all(x_batch):
     """utils/utils.py:127-130 (init only, no gradient in the reference's use)."""
-    return _ew('lemo_aa_to_rot6d', x_batch.detach().reshape(-1, 3), 3, 6)
+    return _ew('lemo_aa_to_rot6d', _no_grad_input(x_batch, 'convert_to_6D_all').reshape(-1, 3), 3, 6)
 
 
 def convert_to_3D_all(x_batch):
@@ -60,8 +88,9 @@ def convert_to_3D_all(x_batch):
 
 
 def convert_to_3D_rot(x_batch):
-    """utils/utils.py:111-123, forward values ([bs,75] -> [bs,72]).  The aa slot is produced for the result vector;
-    use gen_body_mesh_v1(params75) to differentiate through the body model (it consumes the 6D part directly)."""
+    """utils/utils.py:111-123 ([bs,75] -> [bs,72]), differentiable like the reference (6D Gram-Schmidt adjoint + tgm R->aa adjoint),
+    so `gen_body_mesh_v1(convert_to_3D_rot(x75), ...)` carries the data-term gradient to the 6D rotation (opt_amass_temp.py:356-357).
+    gen_body_mesh_v1(params75) is the shorter equivalent path (no R -> aa -> Rodrigues round trip)."""
     xr_aa = convert_to_3D_all(x_batch[:, 3:9])
     return torch.cat([x_batch[:, :3], xr_aa, x_batch[:, 9:]], dim=-1)
 

@@ -35,18 +35,29 @@ class _Decode(torch.autograd.Function):
         aa = torch.empty(B, 63, device=z.device) if want_aa else None
         _lib.call('lemo_vposer_decode', hnd.handle, _lib.ptr(z), B, _lib.ptr(R), _lib.ptr(aa), _lib.cur_stream(z.device))
         hnd.stamp += 1
-        ctx.hnd, ctx.stamp = hnd, hnd.stamp
-        ctx.save_for_backward(z)
-        if aa is None:
+        ctx.hnd, ctx.stamp, ctx.want_aa = hnd, hnd.stamp, want_aa
+        if want_aa:
+            ctx.save_for_backward(z, R)
+        else:
+            ctx.save_for_backward(z)
             aa = torch.empty(0, device=z.device)
-        ctx.mark_non_differentiable(aa)
+            ctx.mark_non_differentiable(aa)
         return R, aa
 
     @staticmethod
-    def backward(ctx, gR, _gaa):
-        (z,) = ctx.saved_tensors
+    def backward(ctx, gR, gaa):
+        z = ctx.saved_tensors[0]
         hnd, B = ctx.hnd, z.shape[0]
         st = _lib.cur_stream(z.device)
+        if ctx.want_aa and gaa is not None:
+            # aa = tgm.rotation_matrix_to_angle_axis(R): adjoint through the selected quaternion branch, as autograd does in the
+            # reference (vposer_smpl.py:152-161); the gradient reaches z exactly as in `vposer.decode(z,'aa') -> body_model(body_pose=)`
+            R = ctx.saved_tensors[1]
+            dR = torch.empty_like(R)
+            _lib.call('lemo_rotmat_to_aa_backward', _lib.ptr(R), _lib.ptr(gaa.contiguous().float()), B * 21, _lib.ptr(dR), st)
+            gR = dR if gR is None else gR + dR
+        if gR is None:
+            return None, torch.zeros_like(z), None
         if hnd.stamp != ctx.stamp:      # activations were overwritten by a later decode: recompute ours
             R = torch.empty(B, 21, 9, device=z.device)
             _lib.call('lemo_vposer_decode', hnd.handle, _lib.ptr(z), B, _lib.ptr(R), None, st)
@@ -71,8 +82,14 @@ class VPoserDecoder(nn.Module):
         self._handles = {}
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets .to(device) / device queries work
 
-    def handle(self, device, B):
+    def handle(self, device, B, private=False):
+        """Scratch handle for batch B on `device`.  private=True returns a fresh handle that is NOT cached: a fused fitter bakes the
+        handle's activation buffers into its CUDA graph and replays it on its own stream, so it must not share them with other
+        fitters or with plain decode() calls of the same batch size."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
+        if private:
+            with torch.cuda.device(idx):
+                return _Handle(self._w, B, idx)
         key = (idx, B)
         if key not in self._handles:
             with torch.cuda.device(idx):
@@ -85,7 +102,7 @@ class VPoserDecoder(nn.Module):
             raise RuntimeError('lemo_b200 runs on CUDA devices only (no CPU fallback)')
         R, aa = _Decode.apply(self.handle(Zin.device, Zin.shape[0]), Zin, output_type == 'aa')
         if output_type == 'aa':
-            # forward value of the reference's decode(Z,'aa'); gradients flow through decode_matrot (see utils.gen_body_mesh_v1)
+            # differentiable like the reference's decode(Z,'aa') (adjoint of the tgm conversion: lemo_rotmat_to_aa_backward)
             return aa.view(Zin.shape[0], 1, 21, 3)
         return R.view(Zin.shape[0], 1, 21, 9)
 

@@ -141,20 +141,7 @@ def main():
           '%.1f KB' % (os.path.getsize(os.path.join(OUT, 'reference_golden.npz')) / 1024))
 
 
-def synth_marker_clip(seed, T=120):
-    """A moving, turning 68-point body (pelvis + 67 markers, z up) with float32 coordinates and 0/1 contact labels."""
-    g = np.random.default_rng(seed)
-    base = g.standard_normal((68, 3)) * np.array([0.25, 0.12, 0.45]) + np.array([0.0, 0.0, 0.9])
-    base[[27, 57], 0] += np.array([-0.2, 0.2])          # shoulders / hips apart along x so that `across` is well defined
-    base[[28, 58], 0] += np.array([-0.15, 0.15])
-    t = np.arange(T) / 30.0
-    yaw = 0.6 * np.sin(0.7 * t) + 0.3 * t
-    c, s_ = np.cos(yaw), np.sin(yaw)
-    R = np.stack([np.stack([c, -s_, 0 * c], -1), np.stack([s_, c, 0 * c], -1), np.stack([0 * c, 0 * c, 1 + 0 * c], -1)], -2)
-    pos = np.stack([0.8 * t + 0.1 * np.sin(2 * t), 0.3 * np.sin(0.9 * t), 0.02 * np.sin(5 * t)], -1)
-    body = np.einsum('tij,kj->tki', R, base) + pos[:, None] + 0.01 * g.standard_normal((T, 68, 3))
-    contact = (g.random((T, 4)) > 0.5).astype(np.float32)
-    return body.astype(np.float32), contact
+from lemo_b200.synth import synth_marker_clip      # noqa: E402  (data generator, shared with bench.py)
 
 
 def make_infill_golden():

@@ -61,6 +61,54 @@ def test_host_tgm_conversions(built_lib):
         assert np.abs(_host('lemo_host_rotmat_to_aa', Rr, out_shape=3) - want).max() < 5e-6 * max(1.0, np.abs(want).max())
 
 
+def test_host_rotmat_to_aa_adjoint_all_branches(built_lib):
+    """lemo_host_rotmat_to_aa_bwd (the same HD code as the lemo_rotmat_to_aa_backward kernel) vs autograd through the oracle's restated
+    torchgeometry conversion, on rotations that hit all four quaternion branches (angles up to pi)."""
+    g = np.random.default_rng(3)
+    seen = set()
+    for i in range(400):
+        aa = ((1.0, 3.0, 0.01, 3.1)[i % 4] * g.standard_normal(3)).astype(np.float32)
+        if i % 4 == 3:
+            aa = (aa / np.linalg.norm(aa) * 3.14).astype(np.float32)
+        R = rb.rodrigues(torch.from_numpy(aa)[None])[0].numpy().astype(np.float32).reshape(9)
+        t = R.reshape(3, 3).T
+        seen.add((0 if t[0, 0] > t[1, 1] else 1) if t[2, 2] < 1e-6 else (2 if t[0, 0] < -t[1, 1] else 3))
+        Rt = torch.from_numpy(R).double().requires_grad_(True)
+        d = g.standard_normal(3).astype(np.float32)
+        (rb.rotmat_to_aa(Rt.view(1, 3, 3))[0] * torch.from_numpy(d).double()).sum().backward()
+        want = Rt.grad.numpy()
+        got = _host('lemo_host_rotmat_to_aa_bwd', np.ascontiguousarray(R), d, out_shape=9)
+        assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+    assert seen == {0, 1, 2, 3}
+
+
+def test_tgm_known_answers_from_shipped_results(built_lib):
+    """Known-answer test for the sign / branch convention of the restated torchgeometry conversions.  The reference ships ten result
+    clips (res_opt_amass_{perframe,temp}/TotalCapture/body_params_opt_clip_*.npy, fixtures in tests/golden/seed_clips.npz) whose
+    global-orient axis-angles were produced by the REAL torchgeometry 0.1.2 `rotation_matrix_to_angle_axis` (utils/utils.py:80) with
+    angles up to pi, i.e. on the hard quaternion branches.  They must be fixed points of rotmat_to_aa(rodrigues(aa)) for the oracle's
+    restatement and for the library's HD code."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'seed_clips.npz'))
+    n, hard = 0, 0
+    for k in z.files:
+        if '_params_' not in k:
+            continue
+        aa = z[k][:, 3:6].astype(np.float32)
+        ang = np.linalg.norm(aa, axis=1)
+        hard += int((ang > 3.0).sum())
+        R = rb.rodrigues(torch.from_numpy(aa).double())
+        back = rb.rotmat_to_aa(R).numpy()
+        assert np.abs(back - aa).max() < 5e-6, (k, np.abs(back - aa).max())
+        R32 = R.float().numpy().reshape(-1, 9)
+        for i in range(0, aa.shape[0], 7):
+            got = _host('lemo_host_rotmat_to_aa', np.ascontiguousarray(R32[i]), out_shape=3)
+            # fp32 R -> aa loses ~1e-7/sin(theta/2) near pi: 2e-4 absolute covers the angle-3.1416 frames, branch/sign errors are O(1)
+            assert np.abs(got - aa[i]).max() < 2e-4, (k, i, got, aa[i])
+        n += aa.shape[0]
+    assert n == 10 * 119 and hard > 0
+
+
 def test_no_cpu_fallback_in_product():
     """The product package must never import the oracle (parity claims depend on it)."""
     import os, re
