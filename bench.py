@@ -123,7 +123,8 @@ class ClockSampler:
 def cpu_reference_rate(n_iters, warm=2):
     """Reference op sequence on the host cores: 1 sequence x 120 frames, `n_iters` timed Adam iterations."""
     import torch
-    from oracle import synth, ref_body as rb, ref_loops as rl
+    from lemo_b200 import synth
+    from oracle import ref_body as rb, ref_loops as rl
     ncpu = os.cpu_count() or 1
     ctx = rl.FitContext(synth.make_smplx_model(0), synth.make_vposer_weights(1), synth.load_enc_weights(), synth.load_tables())
     clean, init, contact = synth.make_sequence(0, T=T_FRAMES)
@@ -193,7 +194,7 @@ def main():
     import lemo_b200.smplx as smplx
     from lemo_b200.vposer import VPoserDecoder
     from lemo_b200.fit import TemporalFitter, load_smooth_prior
-    from oracle import synth            # synthetic inputs only (data generation, not compute)
+    from lemo_b200 import synth         # synthetic inputs (data generation only; the product arm never imports oracle/)
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -395,59 +396,34 @@ def main():
                     'frame_iterations_per_sec': S * Tp * it_pf / (pf_ms * 1e-3), 'us_per_iteration': 1e3 * pf_ms / (Tp * it_pf),
                     'clips_per_sec': S / (pf_ms * 1e-3)}
 
-    # ---------------- secondary: PROX stage-2 iteration (BASELINE configs[3] + contact on): B=100 window, full mesh, 256^3 SDF, 100k scene points
+    # ---------------- secondary: PROX stage-2 window (BASELINE configs[3] + contact on): B=100, full mesh, 256^3 SDF, 100k scene points,
+    #                  the fused device driver (lemo_fit_prox_run) that FittingMonitor.run_fitting dispatches to
     prox = None
     if rank == 0 and not a.skip_prox:
-        from lemo_b200.temp_prox.camera import PerspectiveCamera
-        from lemo_b200.temp_prox.fitting_temp_slide import SMPLifyLoss
-        Bp = 100
-        Pp, cfgp = synth.make_prox_problem(Bp, D=256, m_scene=100000, seed=3)
-        body.joint_mapper = None
-        Rc, tc_, fx, fy, cc = cfgp['camera']
-        cam = PerspectiveCamera(rotation=Rc[None].repeat(Bp, 1, 1), translation=tc_[None].repeat(Bp, 1), focal_length_x=fx, focal_length_y=fy,
-                                batch_size=Bp, center=cc[None].repeat(Bp, 1)).to(dev)
-        lossf = SMPLifyLoss(cfgp['w'], cam, cfgp['cam2world'], cfgp['sdf'].to(dev), cfgp['grid_min'], cfgp['grid_max'], cfgp['fric_ids'].to(dev),
-                            cfgp['contact_ids'].to(dev), cfgp['scene_v'].to(dev), torch.from_numpy(tables['markers81']).long().to(dev), enc,
-                            torch.from_numpy(tables['smooth_Xmean']).view(1, 1, 243).to(dev), torch.from_numpy(tables['smooth_Xstd']).to(dev),
-                            cfgp['joint_weights'].to(dev))
-        keys = ['transl', 'global_orient', 'pose_embedding', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression']
-        Pg = {k: torch.from_numpy(v).to(dev).requires_grad_(k in keys) for k, v in Pp.items()}
-        opt = torch.optim.Adam([Pg[k] for k in keys], lr=0.005)
-        jmap = cfgp['joint_map'].to(dev)
-        gtj, gtc = cfgp['gt_joints'].to(dev), cfgp['joints_conf'].to(dev)
-
-        def prox_iter():
-            opt.zero_grad()
-            Rb = vp.decode(Pg['pose_embedding'], 'matrot').reshape(Bp, 21, 9)
-            kw = {k: Pg[k] for k in ('transl', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression', 'betas')}
-            out = body(return_verts=True, return_full_pose=True, R_body=Rb, **kw)
-            raw = out.joints
-            out = out._replace(joints=raw[:, jmap])
-            tot, _ = lossf(out, raw, gtj, gtc, Pg['pose_embedding'])
-            tot.backward()
-            opt.step()
-        for _ in range(3):
-            prox_iter()
+        from lemo_b200.temp_prox.synthetic import make_window
+        pfit, _, _ = make_window(body, vp, enc, B=100, D=256, m_scene=100000, seed=3, device=dev, use_cuda_graph=not a.no_graph)
+        pfit.run(5)
         torch.cuda.synchronize(dev)
+        n_p = 100
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0p = pfit.kernel_launches()
         c0.record()
-        for _ in range(10):
-            prox_iter()
+        pfit.run(n_p)
         c1.record()
         torch.cuda.synchronize(dev)
-        pms = c0.elapsed_time(c1) / 10
-        prox = {'workload': 'PROXD_temp_S2-shaped window: B=100, full mesh, keypoints + priors + SDF 256^3 penetration + friction + Chamfer contact '
-                            '(1121 x 100k, shared scene) + Enc smoothness, Adam; SMPL-X evaluated once', 'ms_per_iteration': pms,
-                'iterations_per_sec': 1e3 / pms, 'note': 'operators = lemo kernels; loss glue + optimizer still PyTorch (DESIGN.md section 7)'}
+        pms = c0.elapsed_time(c1) / n_p
+        prox = {'workload': 'PROXD_temp_S2-shaped window: B=100, full mesh, keypoints + priors + SDF 256^3 penetration + friction + contact '
+                            '(1121 x 100k, shared static scene) + Enc smoothness + 15 % freeze + Adam, one CUDA graph per closure step; '
+                            'SMPL-X evaluated once', 'ms_per_iteration': pms, 'iterations_per_sec': 1e3 / pms,
+                'gpu_launches_per_iteration': (pfit.kernel_launches() - l0p) / n_p,
+                'window_900_iterations_s': 0.9 * pms, 'final_loss': float(pfit.losses()['total_loss'])}
 
     # ---------------- secondary: infill pre-stage of one clip: representation + mask/pad + 60 AE fine-tune steps + inference
     #                  + global reconstruction, everything on the device; the CPU leg is the oracle's numpy float64 post-processing only
     infill = None
     if rank == 0 and not a.skip_infill:
         from lemo_b200.infill import InfillStage, body_repr, load_infill_prior, load_infill_stats
-        from oracle.make_golden import synth_marker_clip
-        from oracle import ref_infill as ri
-        body68, con68 = synth_marker_clip(5, T=120)
+        body68, con68 = synth.synth_marker_clip(5, T=120)
         st64 = load_infill_stats()
         stage = InfillStage(load_infill_prior(), device=dev, stats=st64)
         b_d, c_d = torch.from_numpy(body68).to(dev), torch.from_numpy(con68).to(dev)
@@ -464,9 +440,12 @@ def main():
         c1.record()
         torch.cuda.synchronize(dev)
         inf_ms = c0.elapsed_time(c1) / 3
-        t0 = time.perf_counter()
-        rep_np, rot0_np = ri.get_local_markers_4chan(body68, con68)
-        host_ms = (time.perf_counter() - t0) * 1e3
+        host_ms = None
+        if not a.skip_cpu_baseline:                  # cpu_baseline leg: the oracle's numpy float64 representation builder, timed beside it
+            from oracle import ref_infill as ri
+            t0 = time.perf_counter()
+            ri.get_local_markers_4chan(body68, con68)
+            host_ms = (time.perf_counter() - t0) * 1e3
         infill = {'workload': 'opt_amass_temp.py:141-325 for one 120-frame clip: get_local_markers_4chan + normalise, mask + reflect pad, 60 AE '
                               'fine-tune steps (Adam lr 3e-6, 4.1 M weights), inference, labels, de-normalise, reconstruct_global_body',
                   'ms_per_clip': inf_ms, 'clips_per_sec': 1e3 / inf_ms, 'finetune_steps': 60,

@@ -202,6 +202,15 @@ int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* 
                           int64_t xyz2_batch_stride, const float* g_dist1, const float* g_dist2,
                           const int32_t* idx1, const int32_t* idx2, float* d_xyz1, float* d_xyz2, void* stream);
 
+/* Static scene accelerator for the PROX contact term (fitting_temp_slide.py:743-753): the scene mesh of a recording is fixed
+ * (fit_temp_loadprox_slide.py:366-372), so its points are Morton-sorted once into boxed tiles and a query scans only the tiles that
+ * can still hold a closer point.  dist1 / idx1 are IDENTICAL to lemo_chamfer_forward's against the same scene (same pinned
+ * arithmetic, same first-minimum rule; idx1 = index into the ORIGINAL scene array).  lemo_scene_create synchronises (create time). */
+typedef struct LemoScene LemoScene;
+int lemo_scene_create(const float* scene_points /* device [m,3] */, int32_t m, LemoScene** out);
+int lemo_scene_destroy(LemoScene* scene);
+int lemo_scene_query(const LemoScene* scene, const float* xyz1 /* [B,n,3] */, int32_t B, int32_t n, float* dist1, int32_t* idx1, void* stream);
+
 /* ---------------------------------------------------------------- PROX scene terms (temp_prox/fitting_temp_slide.py) --- */
 /* PerspectiveCamera.forward (temp_prox/camera.py:93-116): img = f * (R p + t).xy / (R p + t).z + c.  points [n,3] -> out [n,2].
  * h_R [9] / h_t [3] are HOST arrays (the camera is fixed in the shipped configs, S2.yaml camera_mode 'fixed'); NULL = identity / zero. */
@@ -263,6 +272,62 @@ int lemo_fit_get(LemoFit* fit, float* params72, float* losses, void* stream);
 int lemo_fit_get_state(LemoFit* fit, float* transl, float* rot6d, float* other, float* g_transl, float* g_rot6d,
                        float* g_other, void* stream);
 int64_t lemo_fit_kernel_launches(const LemoFit* fit);   /* kernels enqueued by this handle so far */
+
+/* ---------------------------------------------------------------- fused PROX stage-2 driver ------------ */
+/* One B-frame sliding window of temp_prox: FittingMonitor.run_fitting + create_fitting_closure.fitting_func
+ * (fitting_temp_slide.py:169-313) over SMPLifyLoss.forward (:564-1062) with the terms PROXD_temp_S2.yaml selects + `contact`.
+ * Loss weights carry the reference's attribute names (SMPLifyLoss.__init__ :339-387, reset_loss_weights :548-562). */
+typedef struct LemoProxFit LemoProxFit;
+typedef struct LemoProxWeightsC {
+    float data_weight, body_pose_weight, shape_weight, bending_prior_weight, hand_prior_weight, expr_prior_weight, jaw_prior_weight;
+    float sdf_penetration_weight, contact_loss_weight, motion_prior_smooth_weight, friction_normal_weight, friction_tangent_weight;
+    int32_t use_joints_conf;          /* weights = joint_weights * joints_conf (:577-579) */
+} LemoProxWeightsC;
+typedef struct LemoProxConfigC {
+    int32_t n_frames;                 /* B: frames of the window (100 in the shipped configs)                          */
+    int32_t n_joints_mapped;          /* Jm: keypoints after the OpenPose JointMapper (118)                            */
+    const int32_t* h_joint_map;       /* [Jm] indices into the 127 model joints (misc_utils.smpl_to_openpose); NULL = identity */
+    float cam_R[9], cam_t[3], fx, fy, cx, cy;     /* fixed PerspectiveCamera (camera.py:93-116)                        */
+    float R[9], t[3];                 /* cam2world (fit_temp_loadprox_slide.py:307-310)                                 */
+    const float* sdf;                 /* DEVICE [dim,dim,dim] signed distances, indexed [x][y][z], caller-owned; NULL = no scene SDF */
+    int32_t sdf_dim;
+    float grid_min[3], grid_max[3];
+    int32_t sdf_penetration, use_friction, contact, use_motion_smooth_prior;      /* term switches (S2.yaml)            */
+    const int32_t* h_fric_ids; int32_t n_fric;            /* contact_fric_verts_ids (fit_temp_loadprox_slide.py:349-354) */
+    const int32_t* h_contact_ids; int32_t n_contact;      /* contact_verts_ids (:356-362)                                */
+    const int32_t* h_markers81;       /* smooth_marker_ids (loader/SSM2_withhand.json)                                  */
+    const float* scene_v; int32_t n_scene;                /* DEVICE [m,3] scene vertices, caller-owned                   */
+    const float* h_smooth_mean; const float* h_smooth_std;    /* [243] preprocess_stats_smooth_withHand_global_markers   */
+    LemoProxWeightsC weights;
+    int32_t use_cuda_graph;
+} LemoProxConfigC;
+typedef struct LemoProxWindowC {      /* device pointers, [B, .]; NULL = zeros (joints_conf NULL = ones) */
+    const float* transl; const float* global_orient; const float* pose_embedding; const float* left_hand_pose; const float* right_hand_pose;
+    const float* jaw_pose; const float* leye_pose; const float* reye_pose; const float* expression; const float* betas;
+    const float* gt_joints;           /* [B,Jm,2] */
+    const float* joints_conf;         /* [B,Jm]   */
+    const float* joint_weights;       /* [B,Jm]   */
+} LemoProxWindowC;
+typedef struct LemoProxParamsOutC {   /* device pointers, any may be NULL */
+    float* transl; float* global_orient; float* pose_embedding; float* left_hand_pose; float* right_hand_pose;
+    float* jaw_pose; float* leye_pose; float* reye_pose; float* expression;
+} LemoProxParamsOutC;
+int lemo_fit_prox_create(const LemoModel* model, LemoVPoser* vposer, LemoConvNet* enc_or_null, const LemoProxConfigC* cfg, int device,
+                         LemoProxFit** out);
+int lemo_fit_prox_destroy(LemoProxFit* fit);
+/* loss.reset_loss_weights(curr_weights) per optimisation stage + the closure's gradient erase: frames [0, erase_n) are frozen
+ * (erase_n = int(bs*0.15) when first_batch_flag is False, else 0; fitting_temp_slide.py:281-288). */
+int lemo_fit_prox_set_weights(LemoProxFit* fit, const LemoProxWeightsC* w, int32_t erase_n, void* stream);
+int lemo_fit_prox_set_window(LemoProxFit* fit, const LemoProxWindowC* window, void* stream);
+/* n_iters closure steps with a fresh Adam(lr, betas .9/.999, eps 1e-8) (optim_factory.py:77-80), no host synchronisation.
+ * resume = 1 continues the previous call's moments / step count / lr (a run split into chunks to read the loss in between). */
+int lemo_fit_prox_run(LemoProxFit* fit, int32_t n_iters, float lr, int32_t resume, void* stream);
+/* one closure evaluation (loss terms + gradients after the erase) without an optimiser step: the closure-level parity hook */
+int lemo_fit_prox_eval(LemoProxFit* fit, void* stream);
+/* current parameters / gradients of the last closure / losses16 = {joint, pprior, shape, angle, hand(l+r), expr, jaw, sdf_penetration,
+ * fric_tangent, fric_normal, contact, motion_prior_smooth, 0, 0, 0, total} of the last closure */
+int lemo_fit_prox_get(LemoProxFit* fit, const LemoProxParamsOutC* params, const LemoProxParamsOutC* grads, float* losses16, void* stream);
+int64_t lemo_fit_prox_kernel_launches(const LemoProxFit* fit);
 
 /* ---------------------------------------------------------------- test hooks (host math, no GPU) -------- */
 void lemo_host_rodrigues(const float* aa, float* R);

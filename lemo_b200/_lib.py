@@ -68,6 +68,36 @@ class LemoFitConfigC(C.Structure):
                 ('use_cuda_graph', C.c_int32)]
 
 
+class LemoProxWeightsC(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ('data_weight', 'body_pose_weight', 'shape_weight', 'bending_prior_weight', 'hand_prior_weight',
+                                         'expr_prior_weight', 'jaw_prior_weight', 'sdf_penetration_weight', 'contact_loss_weight',
+                                         'motion_prior_smooth_weight', 'friction_normal_weight', 'friction_tangent_weight')] + \
+               [('use_joints_conf', C.c_int32)]
+
+
+class LemoProxConfigC(C.Structure):
+    _fields_ = [('n_frames', C.c_int32), ('n_joints_mapped', C.c_int32), ('h_joint_map', C.c_void_p),
+                ('cam_R', C.c_float * 9), ('cam_t', C.c_float * 3), ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
+                ('R', C.c_float * 9), ('t', C.c_float * 3),
+                ('sdf', C.c_void_p), ('sdf_dim', C.c_int32), ('grid_min', C.c_float * 3), ('grid_max', C.c_float * 3),
+                ('sdf_penetration', C.c_int32), ('use_friction', C.c_int32), ('contact', C.c_int32), ('use_motion_smooth_prior', C.c_int32),
+                ('h_fric_ids', C.c_void_p), ('n_fric', C.c_int32), ('h_contact_ids', C.c_void_p), ('n_contact', C.c_int32),
+                ('h_markers81', C.c_void_p), ('scene_v', C.c_void_p), ('n_scene', C.c_int32),
+                ('h_smooth_mean', C.c_void_p), ('h_smooth_std', C.c_void_p), ('weights', LemoProxWeightsC), ('use_cuda_graph', C.c_int32)]
+
+
+PROX_PARAMS = ['transl', 'global_orient', 'pose_embedding', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose',
+               'expression']
+
+
+class LemoProxWindowC(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in PROX_PARAMS + ['betas', 'gt_joints', 'joints_conf', 'joint_weights']]
+
+
+class LemoProxParamsOutC(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in PROX_PARAMS]
+
+
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); restype int means "status code"
@@ -112,6 +142,9 @@ SIGNATURES = {
     'lemo_ae_finetune_step': (C.c_int, [_P, _P, _P, _I, _I, _D, _I, _P, _P]),
     'lemo_chamfer_forward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P]),
     'lemo_chamfer_backward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    'lemo_scene_create': (C.c_int, [_P, _I, C.POINTER(_P)]),
+    'lemo_scene_destroy': (C.c_int, [_P]),
+    'lemo_scene_query': (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     'lemo_camera_project': (C.c_int, [_P, _L, _P, _P, _F, _F, _F, _F, _P, _P]),
     'lemo_camera_project_backward': (C.c_int, [_P, _L, _P, _P, _F, _F, _F, _F, _P, _P, _P]),
     'lemo_rigid_transform': (C.c_int, [_P, _L, _P, _P, _I, _P, _P]),
@@ -131,6 +164,14 @@ SIGNATURES = {
     'lemo_fit_get': (C.c_int, [_P, _P, _P, _P]),
     'lemo_fit_get_state': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'lemo_fit_kernel_launches': (_L, [_P]),
+    'lemo_fit_prox_create': (C.c_int, [_P, _P, _P, C.POINTER(LemoProxConfigC), C.c_int, C.POINTER(_P)]),
+    'lemo_fit_prox_destroy': (C.c_int, [_P]),
+    'lemo_fit_prox_set_weights': (C.c_int, [_P, C.POINTER(LemoProxWeightsC), _I, _P]),
+    'lemo_fit_prox_set_window': (C.c_int, [_P, C.POINTER(LemoProxWindowC), _P]),
+    'lemo_fit_prox_run': (C.c_int, [_P, _I, _F, _I, _P]),
+    'lemo_fit_prox_eval': (C.c_int, [_P, _P]),
+    'lemo_fit_prox_get': (C.c_int, [_P, C.POINTER(LemoProxParamsOutC), C.POINTER(LemoProxParamsOutC), _P, _P]),
+    'lemo_fit_prox_kernel_launches': (_L, [_P]),
     'lemo_host_rodrigues': (None, [_P, _P]),
     'lemo_host_rodrigues_bwd': (None, [_P, _P, _P]),
     'lemo_host_gs6d': (None, [_P, _P]),

@@ -803,7 +803,8 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
     LEMO_CHECK(c && ps && c->Gv && ps->dA, "body handle was created without backward buffers");
     const Model* m = c->m;
     const int V = m->V;
-    if (d_verts) LEMO_CUDA(cudaMemcpyAsync(c->Gv, d_verts, (size_t)B * V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (d_verts == c->Gv) {}      // the caller assembled the vertex gradient in place (fit_prox.cu): no 12 MB copy
+    else if (d_verts) LEMO_CUDA(cudaMemcpyAsync(c->Gv, d_verts, (size_t)B * V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     else LEMO_CUDA(cudaMemsetAsync(c->Gv, 0, (size_t)B * V * 3 * sizeof(float), st));
     if (d_joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");

@@ -7,7 +7,10 @@
 // staged as float4 through 16 KB of shared memory, and each thread keeps 4 queries in registers so one
 // broadcast LDS.128 feeds 4 distance evaluations.
 #include "common.cuh"
+#include "chamfer.cuh"
 #include "../../include/lemo_b200.h"
+#include <vector>
+#include <algorithm>
 
 namespace lemo {
 
@@ -77,10 +80,189 @@ __global__ void k_chamfer_bwd(const float* __restrict__ a, long long a_bs, int n
     }
 }
 
+int chamfer_nn_launch(const float* q, long long q_bs, int nq, const float* t, long long t_bs, int nt, int B, float* dist, int* idx,
+                      cudaStream_t st) {
+    k_chamfer_nn<<<dim3(cdiv(nq, 256 * CH_QT), B), 256, 0, st>>>(q, q_bs, nq, t, t_bs, nt, dist, idx);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- static scene, tiled + pruned
+// One warp per query.  Pass 1: every lane computes the squared distance from the query to the boxes of its tiles (lower bound of
+// every point inside); the tile with the smallest bound is scanned first, which gives a near-optimal `best`.  Pass 2: every tile
+// whose bound (shrunk by 0.1 % so that fp32 rounding can never hide an equal-distance point) does not exceed `best` is scanned, 4
+// points per lane; (distance, original index) pairs are compared lexicographically, so the result is the brute-force scan's
+// first minimum.
+__device__ __forceinline__ void sg_scan_tile(const float4* __restrict__ tp, float qx, float qy, float qz, float& best, int& bi) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < SG_TILE / 32; ++k) {
+        const float4 p = tp[k * 32 + lane];
+        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));       // pinned order, see k_chamfer_nn
+        const int id = __float_as_int(p.w);
+        if (d < best || (d == best && id < bi)) { best = d; bi = id; }
+    }
+}
+__device__ __forceinline__ void sg_warp_min(float& best, int& bi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    }
+}
+__global__ void __launch_bounds__(256) k_scene_query(const float4* __restrict__ pts, const float* __restrict__ box, int ntile,
+                                                     const float* __restrict__ q, long long q_bs, int nq, int B, float* __restrict__ dist,
+                                                     int* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const long long wq = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wq >= (long long)B * nq) return;
+    const int b = (int)(wq / nq), i = (int)(wq - (long long)b * nq);
+    const float* qp = q + (size_t)b * q_bs + (size_t)i * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    // pass 1: nearest box
+    float lmin = 3.4e38f;
+    int tmin = 0;
+    for (int t = lane; t < ntile; t += 32) {
+        const float* bx = box + (size_t)t * 6;
+        const float ex = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.f), ey = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.f),
+                    ez = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.f);
+        const float lb = ex * ex + ey * ey + ez * ez;
+        if (lb < lmin) { lmin = lb; tmin = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ol = __shfl_xor_sync(0xffffffffu, lmin, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, tmin, o);
+        if (ol < lmin || (ol == lmin && ot < tmin)) { lmin = ol; tmin = ot; }
+    }
+    float best = 3.4e38f;
+    int bi = 0x7fffffff;
+    sg_scan_tile(pts + (size_t)tmin * SG_TILE, qx, qy, qz, best, bi);
+    sg_warp_min(best, bi);
+    // pass 2: every tile that can still hold a point at distance <= best
+    for (int t0 = 0; t0 < ntile; t0 += 32) {
+        const int t = t0 + lane;
+        bool need = false;
+        if (t < ntile && t != tmin) {
+            const float* bx = box + (size_t)t * 6;
+            const float ex = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.f), ey = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.f),
+                        ez = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.f);
+            need = (ex * ex + ey * ey + ez * ez) * 0.999f <= best;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, need);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            float tb = best;
+            int ti = bi;
+            sg_scan_tile(pts + (size_t)(t0 + l) * SG_TILE, qx, qy, qz, tb, ti);
+            sg_warp_min(tb, ti);
+            best = tb; bi = ti;
+            // boxes already flagged stay flagged (a smaller `best` only makes the remaining scans redundant, never wrong)
+        }
+    }
+    if (lane == 0) { dist[wq] = best; idx[wq] = bi; }
+}
+
+static inline unsigned morton_spread(unsigned v) {      // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x30000ffu;
+    v = (v | (v << 8)) & 0x300f00fu;
+    v = (v | (v << 4)) & 0x30c30c3u;
+    v = (v | (v << 2)) & 0x9249249u;
+    return v;
+}
+
+int scene_grid_create(const float* scene_dev, int n, SceneGrid** out) {
+    LEMO_CHECK(scene_dev && n > 0 && out, "bad arguments");
+    std::vector<float> h((size_t)n * 3);
+    LEMO_CUDA(cudaMemcpy(h.data(), scene_dev, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], h[(size_t)i * 3 + a]); hi[a] = std::max(hi[a], h[(size_t)i * 3 + a]); }
+    std::vector<std::pair<unsigned, int>> key(n);
+    for (int i = 0; i < n; ++i) {
+        unsigned c[3];
+        for (int a = 0; a < 3; ++a) {
+            const float ext = hi[a] - lo[a];
+            const float u = ext > 0.f ? (h[(size_t)i * 3 + a] - lo[a]) / ext : 0.f;
+            c[a] = (unsigned)std::min(1023.f, std::max(0.f, u * 1023.f));
+        }
+        key[i] = {morton_spread(c[0]) | (morton_spread(c[1]) << 1) | (morton_spread(c[2]) << 2), i};
+    }
+    std::sort(key.begin(), key.end());
+    const int ntile = (n + SG_TILE - 1) / SG_TILE;
+    std::vector<float4> pts((size_t)ntile * SG_TILE);
+    std::vector<float> box((size_t)ntile * 6);
+    for (int t = 0; t < ntile; ++t) {
+        float bl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, bh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (int k = 0; k < SG_TILE; ++k) {
+            const int s = t * SG_TILE + k;
+            float4 p;
+            if (s < n) {
+                const int id = key[s].second;
+                p.x = h[(size_t)id * 3]; p.y = h[(size_t)id * 3 + 1]; p.z = h[(size_t)id * 3 + 2];
+                int ii = id;
+                memcpy(&p.w, &ii, 4);
+                const float v[3] = {p.x, p.y, p.z};
+                for (int a = 0; a < 3; ++a) { bl[a] = std::min(bl[a], v[a]); bh[a] = std::max(bh[a], v[a]); }
+            } else {
+                p.x = p.y = p.z = 1e18f;               // padding: (1e18)^2 is finite and never the minimum
+                int ii = 0x7fffffff;
+                memcpy(&p.w, &ii, 4);
+            }
+            pts[s] = p;
+        }
+        for (int a = 0; a < 3; ++a) { box[(size_t)t * 6 + a] = bl[a]; box[(size_t)t * 6 + 3 + a] = bh[a]; }
+    }
+    SceneGrid* g = new SceneGrid();
+    g->n = n; g->ntile = ntile;
+    cudaGetDevice(&g->device);
+    LEMO_CUDA(cudaMalloc((void**)&g->pts, pts.size() * sizeof(float4)));
+    LEMO_CUDA(cudaMalloc((void**)&g->box, box.size() * sizeof(float)));
+    LEMO_CUDA(cudaMemcpy(g->pts, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    LEMO_CUDA(cudaMemcpy(g->box, box.data(), box.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = g;
+    return 0;
+}
+
+void scene_grid_free(SceneGrid* g) {
+    if (!g) return;
+    cudaFree(g->pts); cudaFree(g->box);
+    delete g;
+}
+
+int scene_grid_query(const SceneGrid* g, const float* q, long long q_bs, int nq, int B, float* dist, int* idx, cudaStream_t st) {
+    LEMO_CHECK(g && q && dist && idx && nq > 0 && B > 0, "bad arguments");
+    const long long threads = (long long)B * nq * 32;
+    k_scene_query<<<cdiv(threads, 256), 256, 0, st>>>(g->pts, g->box, g->ntile, q, q_bs, nq, B, dist, idx);
+    LEMO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace lemo
 
 using namespace lemo;
+struct LemoScene { lemo::SceneGrid* g; };
 extern "C" {
+
+int lemo_scene_create(const float* scene_points, int32_t n, LemoScene** out) {
+    LEMO_CHECK(out, "null argument");
+    SceneGrid* g = nullptr;
+    LEMO_TRY(scene_grid_create(scene_points, n, &g));
+    *out = new LemoScene{g};
+    return 0;
+}
+int lemo_scene_destroy(LemoScene* s) {
+    if (s) { scene_grid_free(s->g); delete s; }
+    return 0;
+}
+int lemo_scene_query(const LemoScene* s, const float* xyz1, int32_t B, int32_t n, float* dist1, int32_t* idx1, void* stream) {
+    LEMO_CHECK(s && s->g, "null scene");
+    return scene_grid_query(s->g, xyz1, (long long)n * 3, n, B, dist1, idx1, (cudaStream_t)stream);
+}
 
 int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m, int64_t xyz2_batch_stride, float* dist1,
                          float* dist2, int32_t* idx1, int32_t* idx2, void* stream) {
@@ -88,7 +270,7 @@ int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* x
     LEMO_CHECK((dist2 == nullptr) == (idx2 == nullptr), "dist2 and idx2 must both be given or both be NULL");
     LEMO_CHECK(xyz2_batch_stride == 0 || xyz2_batch_stride >= (int64_t)m * 3, "xyz2_batch_stride must be 0 (shared) or >= 3*m");
     cudaStream_t st = (cudaStream_t)stream;
-    k_chamfer_nn<<<dim3(cdiv(n, 256 * CH_QT), B), 256, 0, st>>>(xyz1, (long long)n * 3, n, xyz2, xyz2_batch_stride, m, dist1, idx1);
+    LEMO_TRY(chamfer_nn_launch(xyz1, (long long)n * 3, n, xyz2, xyz2_batch_stride, m, B, dist1, idx1, st));
     // the scene -> body direction is skipped when the caller does not consume it (the PROX contact term reads dist1 only,
     // fitting_temp_slide.py:749-753: 100 000 x 1121 x B pair evaluations saved)
     if (dist2) k_chamfer_nn<<<dim3(cdiv(m, 256 * CH_QT), B), 256, 0, st>>>(xyz2, xyz2_batch_stride, m, xyz1, (long long)n * 3, n, dist2, idx2);

@@ -5,11 +5,10 @@
 //     align_corners=False (the torch>=1.3 default the reference ran with), and its adjoint w.r.t. the query points.
 // The SDF volume is SHARED by the batch (the reference replicates it B times: 6.4 GB at B=100, fit_temp_loadprox_slide.py:299).
 #include "common.cuh"
+#include "prox_common.cuh"
 #include "../../include/lemo_b200.h"
 
 namespace lemo {
-
-struct Cam { float R[9]; float t[3]; float fx, fy, cx, cy; };
 
 __global__ void k_cam_project(const float* __restrict__ p, Cam c, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,55 +49,19 @@ __global__ void k_rigid(const float* __restrict__ p, Cam c, int n, int transpose
     }
 }
 
-struct Grid { float gmin[3], gmax[3]; int dim; };
-
-// grid_sample semantics for one axis: normalise to [-1,1], un-normalise with align_corners=False, clamp to [0, dim-1] (padding 'border')
-__device__ __forceinline__ void axis_coord(float p, float gmin, float gmax, int dim, float& ic, float& scale) {
-    const float nrm = (p - gmin) / (gmax - gmin) * 2.f - 1.f;
-    float i = ((nrm + 1.f) * (float)dim - 1.f) * 0.5f;
-    scale = (float)dim / (gmax - gmin);                      // d i / d p
-    if (i < 0.f) { i = 0.f; scale = 0.f; }                   // clip_coordinates_set_grad: zero gradient where clipped
-    else if (i > (float)(dim - 1)) { i = (float)(dim - 1); scale = 0.f; }
-    ic = i;
-}
-
-// sdf array is [dim][dim][dim] indexed [x][y][z] (the reference feeds (z,y,x) as grid_sample's (W,H,D) coordinates)
 template <bool BWD>
 __global__ void k_sdf_sample(const float* __restrict__ pts, const float* __restrict__ sdf, Grid g, long long n, float* __restrict__ val,
                              const float* __restrict__ gval, float* __restrict__ dpts) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float ic[3], sc[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) axis_coord(pts[i * 3 + a], g.gmin[a], g.gmax[a], g.dim, ic[a], sc[a]);
-    int i0[3];
-    float f[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { i0[a] = (int)floorf(ic[a]); f[a] = ic[a] - (float)i0[a]; }
-    const int D = g.dim;
-    float acc = 0.f, d[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int cx = 0; cx < 2; ++cx)
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-            for (int cz = 0; cz < 2; ++cz) {
-                const int x = i0[0] + cx, y = i0[1] + cy, z = i0[2] + cz;
-                if (x >= D || y >= D || z >= D) continue;                 // zero-weight corner past the border
-                const float v = __ldg(sdf + ((size_t)x * D + y) * D + z);
-                const float wx = cx ? f[0] : 1.f - f[0], wy = cy ? f[1] : 1.f - f[1], wz = cz ? f[2] : 1.f - f[2];
-                acc = fmaf(v, wx * wy * wz, acc);
-                if (BWD) {
-                    d[0] += v * (cx ? 1.f : -1.f) * wy * wz;
-                    d[1] += v * wx * (cy ? 1.f : -1.f) * wz;
-                    d[2] += v * wx * wy * (cz ? 1.f : -1.f);
-                }
-            }
-    if (!BWD) val[i] = acc;
+    const float p[3] = {pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
+    float d[3];
+    const float v = sdf_eval<BWD>(sdf, g, p, d);
+    if (!BWD) val[i] = v;
     else {
         const float gv = gval[i];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) dpts[i * 3 + a] = gv * d[a] * sc[a];
+        for (int a = 0; a < 3; ++a) dpts[i * 3 + a] = gv * d[a];
     }
 }
 

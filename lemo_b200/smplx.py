@@ -201,7 +201,7 @@ class SMPLX(nn.Module):
     NUM_JOINTS = 55
 
     def __init__(self, arrays, batch_size=1, num_pca_comps=12, use_pca=True, joint_mapper=None, dtype=torch.float32,
-                 gender='neutral'):
+                 gender='neutral', create_body_pose=True):
         super().__init__()
         self._arrays = arrays
         self.batch_size = batch_size
@@ -214,7 +214,10 @@ class SMPLX(nn.Module):
         z = lambda n: nn.Parameter(torch.zeros(batch_size, n, dtype=dtype), requires_grad=True)
         self.betas = z(10)
         self.global_orient = z(3)
-        self.body_pose = z(63)
+        if create_body_pose:
+            self.body_pose = z(63)
+        else:       # smplx create_body_pose=False (temp_prox/main_slide.py: `create_body_pose=not use_vposer`): not a parameter
+            self.register_buffer('body_pose', torch.zeros(batch_size, 63, dtype=dtype))
         self.left_hand_pose = z(hand_dim)
         self.right_hand_pose = z(hand_dim)
         self.jaw_pose = z(3)
@@ -290,9 +293,10 @@ class SMPLX(nn.Module):
 def create(model_path, model_type='smplx', gender='neutral', ext='npz', num_pca_comps=12, use_pca=True,
            flat_hand_mean=False, batch_size=1, joint_mapper=None, dtype=torch.float32, **kwargs):
     """smplx.create(...) for model_type='smplx'.  `model_path` may also be a dict of model arrays (synthetic models).
-    create_* flags are accepted and ignored: every parameter exists, as in the reference's calls."""
+    create_body_pose=False keeps body_pose out of .parameters() (the PROX script passes `create_body_pose=not use_vposer`); the other
+    create_* flags are accepted and ignored: those parameters always exist, as in the reference's calls."""
     if model_type != 'smplx':
         raise ValueError('only model_type="smplx" is on the LEMO fitting path')
     arrays = _normalise(_load_model_dict(model_path, model_type, gender, ext), num_pca_comps if use_pca else 45, flat_hand_mean)
     return SMPLX(arrays, batch_size=batch_size, num_pca_comps=num_pca_comps, use_pca=use_pca, joint_mapper=joint_mapper,
-                 dtype=dtype, gender=gender)
+                 dtype=dtype, gender=gender, create_body_pose=bool(kwargs.get('create_body_pose', True)))

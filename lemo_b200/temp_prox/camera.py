@@ -102,8 +102,16 @@ class _SdfSample(torch.autograd.Function):
         return dp, None, None, None
 
 
+def one_volume(sdf):
+    """[D,D,D] view of an SDF given as [D,D,D], [bs,D,D,D] or [bs,1,D,D,D] (the reference's caller repeats ONE scene volume bs times,
+    fit_temp_loadprox_slide.py:297-299: the first replica is the scene)."""
+    while sdf.dim() > 3:
+        sdf = sdf[0]
+    return sdf
+
+
 def sdf_sample(sdf, vertices_world, grid_min, grid_max):
     """body_sdf of fitting_temp_slide.py:682-687 as [B, V]: trilinear, border padding, align_corners=False.  `sdf` is ONE
     [dim,dim,dim] volume on the device (the reference repeats it B times), indexed [x][y][z]."""
-    sdf = sdf.reshape(sdf.shape[-3:]).contiguous().float()
+    sdf = one_volume(sdf).contiguous().float()
     return _SdfSample.apply(vertices_world, sdf, _host(grid_min, 3), _host(grid_max, 3))

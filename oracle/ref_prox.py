@@ -31,6 +31,7 @@ def s2_loss(P, ctx, cfg):
     T = {}
     T['joint'] = torch.mean(wts ** 2 * torch.abs(cfg['gt_joints'] - proj)) * w['data']                   # :577-581
     T['pprior'] = P['pose_embedding'].pow(2).sum() * w['body_pose'] ** 2                                  # :587
+    T['shape'] = P['betas'].pow(2).sum() * w.get('shape', 0.0) ** 2                                       # :592 (L2Prior on betas)
     idx = torch.tensor([55, 58, 12, 15]) - 3                                                             # prior.py:63-89
     sgn = torch.tensor([1., -1., -1., -1.], dtype=verts.dtype)
     T['angle'] = torch.sum(torch.exp(full_pose[:, 3:66][:, idx] * sgn)) * (3.17 * w['body_pose']) ** 2    # :596, fit_temp_loadprox_slide.py:524
@@ -72,3 +73,32 @@ def s2_loss(P, ctx, cfg):
     z = rp.enc_forward(xin, ctx.enc_sd)
     T['smooth'] = torch.mean((z[..., 1:] - z[..., :-1]) ** 2) * w['smooth']
     return sum(T.values()), T
+
+
+PKEYS = ['transl', 'global_orient', 'pose_embedding', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression']
+
+
+def fit_window(P_np, ctx, cfg, n_iters, lr=0.005, first_batch_flag=False, trace=None):
+    """FittingMonitor.run_fitting + create_fitting_closure.fitting_func (fitting_temp_slide.py:169-313) for one window with
+    torch.optim.Adam (optim_factory.py:77-80): closure = loss + backward + `grad[0:int(bs*0.15)] = 0` unless it is the first window.
+    Returns (dict of fitted numpy params, last loss)."""
+    P = {k: torch.from_numpy(v).to(ctx.dtype).requires_grad_(k in PKEYS) for k, v in P_np.items()}
+    params = [P[k] for k in PKEYS]
+    opt = torch.optim.Adam(params, lr=lr)
+    bs = P['transl'].shape[0]
+    erase_n = int(bs * 0.15)
+    last = None
+    for _ in range(n_iters):
+        def closure():
+            opt.zero_grad()
+            tot, T = s2_loss(P, ctx, cfg)
+            tot.backward()
+            if not first_batch_flag:
+                for p_ in params:
+                    if p_.grad is not None:
+                        p_.grad[0:erase_n, :] = 0
+            if trace is not None:
+                trace.append({k: float(v) for k, v in T.items()})
+            return tot
+        last = float(opt.step(closure))
+    return {k: v.detach().numpy() for k, v in P.items()}, last

@@ -4,11 +4,16 @@ FINAL markers -- the north-star quantity -- and [T,72] result vectors are compar
   config 3  opt_amass_temp.py:348-455     T = 119 (real clip length) and 120 (nominal), 100 Adam iterations, lr .01 -> .005 after step 60
   config 2  opt_amass_perframe.py:293-361 60 frames x 100 iterations, warm start, lr .1/.01 -> .01 @>60 -> .003 @>80
 
-Each test also measures the spread between the three arithmetic paths (tcgen05 default `wt`, fp32 CUDA cores `simt`, fp32 CPU oracle)
-and writes it to gpurun_out/loop_parity.json so the numbers can be quoted.  Two fp32 implementations of an Adam loop with sign()
-gradients (L1 marker loss) do not stay bitwise together, so the assertion is on where the loop ENDS: markers within a few tenths of a
-millimetre of the oracle's, loss within a fraction of a percent, and the default tensor-core path no further from the oracle than
-the fp32 CUDA-core path is (x3).
+What can be asserted.  These loops are chaotic in floating point: the marker term is an L1 loss (sign() gradients), the contact term
+selects vertices by `velocity > 0.1`, the Enc stack has LeakyReLU kinks, and Adam normalises every gradient to an O(lr) step -- so
+a 1-ulp difference flips a sign somewhere and the trajectories separate.  Measured on B200 (gpurun_out/loop_parity.json, copied to
+profiles/): after 100 iterations the REFERENCE ARITHMETIC ITSELF (the oracle in fp32 vs the oracle in fp64) ends centimetres apart in
+marker space while the loss agrees to a fraction of a percent.  The tests therefore assert
+  (1) short horizon: after 10 iterations (before the separation has grown) parameters agree with the fp32 oracle to ~1e-3;
+  (2) full schedule: the final loss and the residual to the targets agree with the oracle's within 1 % / 5 %, and
+  (3) full schedule: our distance to the fp64 oracle (final markers) is no larger than 3x the fp32 oracle's own distance to it --
+      i.e. the fused engine (tcgen05 default path and fp32 CUDA-core path) sits inside the reference's own numerical spread.
+All measured spreads are written to gpurun_out/loop_parity.json.
 """
 import json
 import os
@@ -37,68 +42,98 @@ def _record(key, val):
 
 def _markers(p72, ctx):
     with torch.no_grad():
-        v, _ = rb.gen_body_mesh(torch.as_tensor(p72, dtype=ctx.dtype), ctx.smplx, ctx.vposer)
-    return v[:, ctx.m67].numpy()
+        v, _ = rb.gen_body_mesh(torch.as_tensor(np.asarray(p72), dtype=ctx.dtype), ctx.smplx, ctx.vposer)
+    return v[:, ctx.m67].double().numpy()
+
+
+def _dist(a, b):
+    d = np.abs(a - b)
+    return float(d.max()), float(d.mean())
 
 
 @pytest.mark.parametrize('T', [119, 120])
 def test_config3_temporal_100_iterations(T):
     from lemo_b200 import _lib
     from lemo_b200.fit import TemporalFitter
-    ctx = oracle_ctx(torch.float32)
+    c32, c64 = oracle_ctx(torch.float32), oracle_ctx(torch.float64)
     clean, init, contact = synth.make_sequence(3, T=T)
-    target = _markers(clean, ctx)
-    tr = []
+    target = _markers(clean, c32).astype(np.float32)
+    sched = dict(lr0=0.01, lr1=0.005, lr_switch=60)
     # faithful=False: the reference's second SMPL-X/VPoser evaluation (opt_amass_temp.py:364) repeats identical arithmetic
-    ref72, _ = rl.fit_temp(init, target, contact, ctx, n_iters=100, lr0=0.01, lr1=0.005, lr_switch=60, faithful=False, trace=tr)
-    m_ref = _markers(ref72, ctx)
-    res = {}
+    ref = {}
+    for name, ctx in (('o32', c32), ('o64', c64)):
+        tr = []
+        p100, _ = rl.fit_temp(init, target, contact, ctx, n_iters=100, faithful=False, trace=tr, **sched)
+        p10, _ = rl.fit_temp(init, target, contact, ctx, n_iters=10, faithful=False, **sched)
+        ref[name] = dict(p100=p100, p10=p10, loss=tr[-1]['loss'], loss0=tr[0]['loss'])
+    ours = {}
     for mode in ('wt', 'simt'):
         _lib.call('lemo_debug_set_conv_tc', _CONV[mode])
-        fit = TemporalFitter(smplx_module(), vposer_module(), 1, T, enc=enc_module(), device=DEV)
-        fit.set_sequence(0, init, target, contact)
-        fit.run(n_iters=100, lr0=0.01, lr1=0.005, lr_switch=60)
-        p72, losses = fit.results()
-        res[mode] = (p72[0].cpu().numpy(), float(losses[0, 0]))
+        out = {}
+        for n in (10, 100):
+            fit = TemporalFitter(smplx_module(), vposer_module(), 1, T, enc=enc_module(), device=DEV)
+            fit.set_sequence(0, init, target, contact)
+            fit.run(n_iters=n, **sched)
+            p72, losses = fit.results()
+            out['p%d' % n] = p72[0].cpu().numpy()
+            out['loss'] = float(losses[0, 0])
+        ours[mode] = out
     _lib.call('lemo_debug_set_conv_tc', -1)
-    m = {k: _markers(v[0], ctx) for k, v in res.items()}
-    spread = {'markers_wt_vs_oracle_m': float(np.abs(m['wt'] - m_ref).max()), 'markers_simt_vs_oracle_m': float(np.abs(m['simt'] - m_ref).max()),
-              'markers_wt_vs_simt_m': float(np.abs(m['wt'] - m['simt']).max()),
-              'p72_wt_vs_oracle': float(np.abs(res['wt'][0] - ref72).max()), 'p72_simt_vs_oracle': float(np.abs(res['simt'][0] - ref72).max()),
-              'loss_oracle': tr[-1]['loss'], 'loss_wt': res['wt'][1], 'loss_simt': res['simt'][1], 'loss_first': tr[0]['loss'],
-              'marker_err_init_m': float(np.abs(_markers(init, ctx) - target).max()),
-              'marker_fit_err_oracle_m': float(np.abs(m_ref - target).mean())}
-    _record('config3_T%d' % T, spread)
-    print(spread)
-    assert tr[-1]['loss'] < 0.5 * tr[0]['loss']
+    m64 = _markers(ref['o64']['p100'], c64)
+    res_t = lambda m: float(np.abs(m - target).mean())
+    spread = {'oracle32_vs_oracle64_markers_max_mean_m': _dist(_markers(ref['o32']['p100'], c32), m64),
+              'loss_first': ref['o32']['loss0'], 'loss_oracle32': ref['o32']['loss'], 'loss_oracle64': ref['o64']['loss'],
+              'residual_to_targets_oracle32_m': res_t(_markers(ref['o32']['p100'], c32)),
+              'p72_after10_oracle32_vs_oracle64': float(np.abs(ref['o32']['p10'] - ref['o64']['p10']).max())}
     for mode in ('wt', 'simt'):
-        assert spread['markers_%s_vs_oracle_m' % mode] < 1e-3, spread             # final markers within 1 mm (bodies span ~2 m)
-        assert abs(res[mode][1] - tr[-1]['loss']) < 1e-2 * abs(tr[-1]['loss']), spread
-    assert spread['markers_wt_vs_oracle_m'] < 3 * spread['markers_simt_vs_oracle_m'] + 1e-4, spread
+        mm = _markers(ours[mode]['p100'], c32)
+        spread['%s_vs_oracle64_markers_max_mean_m' % mode] = _dist(mm, m64)
+        spread['%s_vs_oracle32_markers_max_mean_m' % mode] = _dist(mm, _markers(ref['o32']['p100'], c32))
+        spread['loss_%s' % mode] = ours[mode]['loss']
+        spread['residual_to_targets_%s_m' % mode] = res_t(mm)
+        spread['p72_after10_%s_vs_oracle32' % mode] = float(np.abs(ours[mode]['p10'] - ref['o32']['p10']).max())
+    spread['wt_vs_simt_markers_max_mean_m'] = _dist(_markers(ours['wt']['p100'], c32), _markers(ours['simt']['p100'], c32))
+    _record('config3_T%d' % T, spread)
+    print(json.dumps(spread, indent=1))
+    assert ref['o32']['loss'] < 0.5 * ref['o32']['loss0']
+    own_max, own_mean = spread['oracle32_vs_oracle64_markers_max_mean_m']
+    for mode in ('wt', 'simt'):
+        # (1) short horizon
+        assert spread['p72_after10_%s_vs_oracle32' % mode] < max(5e-3, 5 * spread['p72_after10_oracle32_vs_oracle64']), (mode, spread)
+        # (2) where the loop ends: loss and residual to the targets
+        assert abs(ours[mode]['loss'] - ref['o32']['loss']) < 1e-2 * abs(ref['o32']['loss']), (mode, spread)
+        assert abs(spread['residual_to_targets_%s_m' % mode] - spread['residual_to_targets_oracle32_m']) < 0.05 * spread['residual_to_targets_oracle32_m'], (mode, spread)
+        # (3) inside the reference's own fp32-vs-fp64 spread (x3, floor 2 mm / 0.3 mm)
+        mx, mean = spread['%s_vs_oracle64_markers_max_mean_m' % mode]
+        assert mx < max(3 * own_max, 2e-3) and mean < max(3 * own_mean, 3e-4), (mode, spread)
 
 
 def test_config2_perframe_60_frames_100_iterations():
     from lemo_b200.fit import PerFrameFitter
-    ctx = oracle_ctx(torch.float32)
+    c32, c64 = oracle_ctx(torch.float32), oracle_ctx(torch.float64)
     T = 60
     clean, _, _ = synth.make_sequence(6, T=T)
-    target = _markers(clean, ctx)
-    tr = []
-    ref = rl.fit_perframe(target, clean[0, 6:16], ctx, n_frames=T, n_iters=100, trace=tr)
-    m_ref = _markers(ref, ctx)
+    target = _markers(clean, c32).astype(np.float32)
+    tr32, tr64 = [], []
+    ref32 = rl.fit_perframe(target, clean[0, 6:16], c32, n_frames=T, n_iters=100, trace=tr32)
+    ref64 = rl.fit_perframe(target, clean[0, 6:16], c64, n_frames=T, n_iters=100, trace=tr64)
     fit = PerFrameFitter(smplx_module(), vposer_module(), 1, T, device=DEV)
     fit.set_sequence(0, clean[0, 6:16], target)
     fit.run(n_iters=100)
     p72, losses = fit.results()
     got = p72[0].cpu().numpy()
-    m_got = _markers(got, ctx)
-    per_frame = np.abs(m_got - m_ref).reshape(T, -1).max(1)
-    spread = {'markers_vs_oracle_m_max': float(per_frame.max()), 'markers_vs_oracle_m_median_frame': float(np.median(per_frame)),
-              'p72_vs_oracle_max': float(np.abs(got - ref).max()), 'fit_err_oracle_m': float(np.abs(m_ref - target).mean()),
-              'fit_err_ours_m': float(np.abs(m_got - target).mean()), 'loss_last_oracle': tr[-1], 'loss_last_ours': float(losses[0, 0])}
+    m32, m64, mg = _markers(ref32, c32), _markers(ref64, c64), _markers(got, c32)
+    res_t = lambda m: float(np.abs(m - target).mean())
+    spread = {'oracle32_vs_oracle64_markers_max_mean_m': _dist(m32, m64), 'ours_vs_oracle64_markers_max_mean_m': _dist(mg, m64),
+              'ours_vs_oracle32_markers_max_mean_m': _dist(mg, m32),
+              'residual_to_targets_oracle32_m': res_t(m32), 'residual_to_targets_oracle64_m': res_t(m64), 'residual_to_targets_ours_m': res_t(mg),
+              'loss_last_frame_oracle32': tr32[-1], 'loss_last_frame_oracle64': tr64[-1], 'loss_last_frame_ours': float(losses[0, 0])}
     _record('config2_perframe_60x100', spread)
-    print(spread)
-    # both loops must END at the same fit: same residual to the targets and markers within millimetres of each other frame by frame
-    assert abs(spread['fit_err_ours_m'] - spread['fit_err_oracle_m']) < 0.1 * spread['fit_err_oracle_m'] + 2e-4, spread
-    assert spread['markers_vs_oracle_m_median_frame'] < 3e-3, spread
-    assert spread['markers_vs_oracle_m_max'] < 2e-2, spread
+    print(json.dumps(spread, indent=1))
+    own_max, own_mean = spread['oracle32_vs_oracle64_markers_max_mean_m']
+    mx, mean = spread['ours_vs_oracle64_markers_max_mean_m']
+    # both loops END at an equally good fit, and our distance to the fp64 oracle is within the reference arithmetic's own spread (x3)
+    lo = min(spread['residual_to_targets_oracle32_m'], spread['residual_to_targets_oracle64_m'])
+    hi = max(spread['residual_to_targets_oracle32_m'], spread['residual_to_targets_oracle64_m'])
+    assert 0.8 * lo - 2e-4 < spread['residual_to_targets_ours_m'] < 1.2 * hi + 2e-4, spread
+    assert mx < max(3 * own_max, 5e-3) and mean < max(3 * own_mean, 1e-3), spread

@@ -152,6 +152,43 @@ def test_chamfer_config4_scale_bit_exact():
     assert not ((k1 >= 1000) & (k1 < 2000)).any()
 
 
+def test_static_scene_query_equals_brute_force():
+    """lemo_scene_query (Morton-tiled scene with box pruning, what the fused PROX driver uses for the contact term) returns exactly the
+    brute-force result: bit-exact distances and indices against the C oracle at config-4 scale, incl. duplicated scene points (lowest
+    index wins) and queries far away from the scene."""
+    import ctypes as C
+    from lemo_b200 import _lib
+    g = np.random.default_rng(9)
+    B, n, m = 100, 1121, 100000
+    a = (g.standard_normal((B, n, 3)) * np.array([1.5, 1.5, 0.5])).astype(np.float32)
+    a[3] += 40.0                                                # a whole frame far outside the scene
+    sc = (g.random((m, 3)) * np.array([6, 6, 0.1]) - np.array([3, 3, 0.05])).astype(np.float32)
+    sc[50000:51000] = sc[0:1000]
+    xa, xs = torch.from_numpy(a).to(DEV), torch.from_numpy(sc).to(DEV)
+    h = C.c_void_p()
+    _lib.call('lemo_scene_create', _lib.ptr(xs), m, C.byref(h))
+    d1 = torch.empty(B, n, device=DEV)
+    i1 = torch.empty(B, n, device=DEV, dtype=torch.int32)
+    _lib.call('lemo_scene_query', h, _lib.ptr(xa), B, n, _lib.ptr(d1), _lib.ptr(i1), _lib.cur_stream())
+    torch.cuda.synchronize()
+    _lib.call('lemo_scene_destroy', h)
+    c1, k1 = rc.chamfer_nn(a, sc)
+    assert torch.equal(i1.cpu(), torch.from_numpy(k1))
+    assert torch.equal(d1.cpu(), torch.from_numpy(c1))
+    # ragged / tiny scenes (fewer points than one tile, one point)
+    for m2 in (1, 37, 129):
+        sc2 = g.standard_normal((m2, 3)).astype(np.float32)
+        xs2 = torch.from_numpy(sc2).to(DEV)
+        _lib.call('lemo_scene_create', _lib.ptr(xs2), m2, C.byref(h))
+        d2 = torch.empty(2, 50, device=DEV)
+        i2 = torch.empty(2, 50, device=DEV, dtype=torch.int32)
+        _lib.call('lemo_scene_query', h, _lib.ptr(xa[:2, :50].contiguous()), 2, 50, _lib.ptr(d2), _lib.ptr(i2), _lib.cur_stream())
+        torch.cuda.synchronize()
+        _lib.call('lemo_scene_destroy', h)
+        c2, k2 = rc.chamfer_nn(a[:2, :50], sc2)
+        assert torch.equal(i2.cpu(), torch.from_numpy(k2)) and torch.equal(d2.cpu(), torch.from_numpy(c2))
+
+
 def test_chamfer_identity_property():
     """size-independent property at config-4 scale: a cloud against itself has zero distance and idx = arange."""
     from lemo_b200.temp_prox.dist_chamfer import chamferDist
@@ -216,7 +253,7 @@ def test_aa_outputs_carry_gradient_like_the_reference():
     v, _ = rb.gen_body_mesh(p72, ctx.smplx, ctx.vposer)
     (v[:, ctx.m67] * gv.double()).sum().backward()
     # product: reference call sequence with the drop-in modules
-    body, vp = smplx_module(), vposer_module()
+    body, vp = smplx_module(synth.V, B), vposer_module()
     xd = x75.to(DEV).requires_grad_(True)
     q72 = U.convert_to_3D_rot(xd)
     assert q72.requires_grad

@@ -1,57 +1,165 @@
-"""PROX stage-2 loss (config 4 shape, reduced sizes): value and gradients of every term against the oracle restatement."""
+"""PROX stage-2 window (BASELINE config 4) through the REFERENCE'S OWN CALL SURFACE -- create_loss(**kwargs of
+fit_temp_loadprox_slide.py:431-485), FittingMonitor as a context manager, create_fitting_closure, run_fitting(optimizer, closure,
+params, body_model, pose_embedding=, vposer=, use_vposer=) -- against the oracle restatement (oracle/ref_prox.py):
+
+  * closure level: every loss term and every parameter gradient, for the fused device driver (lemo_fit_prox_eval) AND the eager
+    closure (autograd over the lemo operators), at a reduced size and at the full config-4 size (B=100, 256^3 SDF, 100 000 scene
+    points);
+  * loop level: 20 closure steps with the first-15 % freeze, fused vs eager vs the oracle's torch.optim.Adam loop.
+"""
 import numpy as np
 import pytest
 import torch
 
 from oracle import synth, ref_body as rb, ref_prox
-from gpu_common import DEV, smplx_module, vposer_module, enc_module, oracle_ctx, model_np, rel
+from gpu_common import DEV, smplx_module, vposer_module, enc_module, oracle_ctx, rel
 
 pytestmark = pytest.mark.gpu
-PKEYS = ['transl', 'global_orient', 'pose_embedding', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression']
+PKEYS = ref_prox.PKEYS
+BODY_KEYS = ['transl', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression', 'betas']
+# oracle term -> loss_dict key of the product
+TERMS = {'joint': 'joint_loss', 'pprior': 'pprior_loss', 'shape': 'shape_loss', 'angle': 'angle_prior_loss', 'hand': 'hand_prior_loss',
+         'expr': 'expression_loss', 'jaw': 'jaw_prior_loss', 'sdf': 'sdf_penetration_loss', 'fric_t': 'loss_fric_tangent',
+         'fric_n': 'loss_fric_normal', 'contact': 'contact_loss', 'smooth': 'motion_prior_smooth_loss'}
 
 
-_setup = synth.make_prox_problem
-
-
-def test_s2_loss_value_and_gradients():
+def _reference_call_surface(B, P, cfg, maxiters, first_batch_flag, lr=0.005):
+    """What fit_temp_loadprox_slide.fit_single_frame does (:431-559), with the drop-in modules.  Returns everything the test needs."""
+    import lemo_b200.smplx as smplx
+    from lemo_b200.temp_prox import fitting_temp_slide as fitting
     from lemo_b200.temp_prox.camera import PerspectiveCamera
-    from lemo_b200.temp_prox.fitting_temp_slide import SMPLifyLoss
-    B = 24
-    P, cfg = _setup(B)
+    from lemo_b200.temp_prox.prior import create_prior
+    from lemo_b200.temp_prox.misc_utils import JointMapper
+    w = cfg['w']
+    body_model = smplx.create(synth.make_smplx_model(0), model_type='smplx', gender='male', ext='npz', num_pca_comps=12, batch_size=B,
+                              joint_mapper=JointMapper(cfg['joint_map']), create_body_pose=False).to(DEV)
+    vposer = vposer_module()
+    Rc, tc, fx, fy, cc = cfg['camera']
+    camera = PerspectiveCamera(rotation=Rc[None].repeat(B, 1, 1), translation=tc[None].repeat(B, 1), focal_length_x=fx, focal_length_y=fy,
+                               batch_size=B, center=cc[None].repeat(B, 1)).to(DEV)
+    D = cfg['sdf'].shape[-1]
+    Rw, tw = cfg['cam2world']
+    loss = fitting.create_loss(loss_type='smplify', joint_weights=cfg['joint_weights'].to(DEV), rho=100, use_joints_conf=True, use_face=True,
+                               use_hands=True, vposer=vposer, pose_embedding=None, body_pose_prior=create_prior('l2'),
+                               shape_prior=create_prior('l2'), angle_prior=create_prior('angle'), expr_prior=create_prior('l2'),
+                               left_hand_prior=create_prior('l2'), right_hand_prior=create_prior('l2'), jaw_prior=create_prior('l2'),
+                               interpenetration=False, s2m=False, m2s=False, sdf_penetration=True,
+                               grid_min=cfg['grid_min'].to(DEV).repeat(B, 1).unsqueeze(1), grid_max=cfg['grid_max'].to(DEV).repeat(B, 1).unsqueeze(1),
+                               sdf=cfg['sdf'].to(DEV).view(1, 1, D, D, D),          # (the reference's caller repeats it B times: a view is enough)
+                               R=Rw.to(DEV), t=tw.to(DEV).view(1, 3), contact=True, contact_verts_ids=cfg['contact_ids'].numpy(),
+                               dtype=torch.float32, use_motion_smooth_prior=True, motion_smooth_model=enc_module(), use_friction=True,
+                               contact_fric_verts_ids=cfg['fric_ids'].numpy(), use_motion_infill_prior=False, device=DEV).to(DEV)
+    body_model.reset_params(**{k: P[k] for k in BODY_KEYS})
+    body_model.betas.requires_grad = False
+    pose_embedding = torch.from_numpy(P['pose_embedding']).float().to(DEV).requires_grad_(True)
+    final_params = [p for p in body_model.parameters() if p.requires_grad] + [pose_embedding]
+    optimizer = torch.optim.Adam(final_params, lr=lr, betas=(0.9, 0.999))
+    loss.reset_loss_weights(dict(data_weight=w['data'], body_pose_weight=w['body_pose'], shape_weight=w.get('shape', 0.0),
+                                 bending_prior_weight=3.17 * w['body_pose'], hand_prior_weight=w['hand_prior'], expr_prior_weight=w['expr'],
+                                 jaw_prior_weight=w['jaw'], sdf_penetration_weight=w['sdf'], contact_loss_weight=w['contact'],
+                                 motion_prior_smooth_weight=w['smooth'], friction_normal_weight=w['fric_n'], friction_tangent_weight=w['fric_t']))
+    monitor = fitting.FittingMonitor(maxiters=maxiters, model_type='smplx')
+    closure = monitor.create_fitting_closure(optimizer, body_model, camera=camera, gt_joints=cfg['gt_joints'].to(DEV),
+                                             joints_conf=cfg['joints_conf'].to(DEV), marker_mask=None, joint_weights=cfg['joint_weights'].to(DEV),
+                                             loss=loss, create_graph=False, use_vposer=True, vposer=vposer, pose_embedding=pose_embedding,
+                                             scan_tensor=None, scan_point_num=None, scene_v=cfg['scene_v'].to(DEV).unsqueeze(0),
+                                             return_verts=True, return_full_pose=True, writer=None, first_batch_flag=first_batch_flag)
+    return dict(body_model=body_model, vposer=vposer, loss=loss, monitor=monitor, closure=closure, optimizer=optimizer,
+                final_params=final_params, pose_embedding=pose_embedding)
+
+
+def _params_of(s):
+    d = {k: getattr(s['body_model'], k).detach().cpu().numpy().copy() for k in BODY_KEYS}
+    d['pose_embedding'] = s['pose_embedding'].detach().cpu().numpy().copy()
+    return d
+
+
+@pytest.mark.parametrize('B,D,m_scene,tol_t,tol_g', [(24, 32, 3000, 2e-3, 5e-3), (100, 256, 100000, 2e-3, 5e-3)])
+def test_closure_terms_and_gradients(B, D, m_scene, tol_t, tol_g):
+    P, cfg = synth.make_prox_problem(B, D=D, m_scene=m_scene, seed=1 if B == 24 else 3)
+    cfg['w']['shape'] = 0.5
     c32 = oracle_ctx(torch.float32)
-    # ---- oracle (CPU, fp32)
     Pt = {k: torch.from_numpy(v).requires_grad_(k in PKEYS) for k, v in P.items()}
     tot_ref, T_ref = ref_prox.s2_loss(Pt, c32, cfg)
     tot_ref.backward()
-    # ---- lemo_b200 operators
-    tab = synth.load_tables()
-    body = smplx_module(synth.V)
-    body.joint_mapper = lambda j: j[:, cfg['joint_map'].to(DEV)]
-    vp, enc = vposer_module(), enc_module()
-    Rc, tc, fx, fy, cc = cfg['camera']
-    cam = PerspectiveCamera(rotation=Rc[None].repeat(B, 1, 1), translation=tc[None].repeat(B, 1), focal_length_x=fx, focal_length_y=fy,
-                            batch_size=B, center=cc[None].repeat(B, 1)).to(DEV)
-    lossf = SMPLifyLoss(cfg['w'], cam, cfg['cam2world'], cfg['sdf'].to(DEV), cfg['grid_min'], cfg['grid_max'], cfg['fric_ids'].to(DEV),
-                        cfg['contact_ids'].to(DEV), cfg['scene_v'].to(DEV), torch.from_numpy(tab['markers81']).long().to(DEV), enc,
-                        torch.from_numpy(tab['smooth_Xmean']).view(1, 1, 243).to(DEV), torch.from_numpy(tab['smooth_Xstd']).to(DEV),
-                        cfg['joint_weights'].to(DEV))
-    Pg = {k: torch.from_numpy(v).to(DEV).requires_grad_(k in PKEYS) for k, v in P.items()}
-    R_body = vp.decode(Pg['pose_embedding'], 'matrot').reshape(B, 21, 9)
-    kw = {k: Pg[k] for k in ('transl', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose', 'leye_pose', 'reye_pose', 'expression', 'betas')}
-    out = body(return_verts=True, return_full_pose=True, R_body=R_body, **kw)
-    mapper = body.joint_mapper
-    body.joint_mapper = None
-    raw = body(return_verts=True, R_body=R_body, **kw).joints
-    body.joint_mapper = mapper
-    tot, T = lossf(out, raw, cfg['gt_joints'].to(DEV), cfg['joints_conf'].to(DEV), Pg['pose_embedding'])
-    tot.backward()
-    body.joint_mapper = None
-    for k in T_ref:
-        a, b = float(T[k]), float(T_ref[k])
-        assert abs(a - b) <= 2e-3 * abs(b) + 1e-7, (k, a, b)
-    assert float(T_ref['sdf']) > 0 and float(T_ref['contact']) > 0 and float(T_ref['fric_t']) > 0          # the terms are exercised
+    assert float(T_ref['sdf']) > 0 and float(T_ref['contact']) > 0 and float(T_ref['fric_t']) > 0 and float(T_ref['fric_n']) > 0
+    erase_n = int(B * 0.15)
+    # ---- eager closure through the reference surface (first_batch_flag=False: the closure erases the first 15 % of every gradient)
+    s = _reference_call_surface(B, P, cfg, maxiters=1, first_batch_flag=False)
+    total = s['closure'](backward=True)
+    ld = s['closure'].last_loss_dict
+    for k, name in TERMS.items():
+        a, b = float(ld[name]), float(T_ref[k])
+        assert abs(a - b) <= tol_t * abs(b) + 1e-7, ('eager', k, a, b)
+    assert abs(float(total) - float(tot_ref)) <= tol_t * abs(float(tot_ref))
+    g_eager = {k: (s['pose_embedding'] if k == 'pose_embedding' else getattr(s['body_model'], k)).grad for k in PKEYS}
+    # ---- fused driver: one closure evaluation
+    fit = s['monitor']._fitter(s['closure'].lemo_spec, s['body_model'], s['pose_embedding'], s['vposer'])
+    fit.set_weights(s['loss'].weight_dict(), erase_n, True)
+    Pd = {k: getattr(s['body_model'], k) for k in BODY_KEYS}
+    Pd['pose_embedding'] = s['pose_embedding']
+    fit.set_window(Pd, cfg['gt_joints'], cfg['joints_conf'], cfg['joint_weights'])
+    fit.eval()
+    lf, gf = fit.losses(), fit.grads()
+    for k, name in TERMS.items():
+        a, b = float(lf[name]), float(T_ref[k])
+        assert abs(a - b) <= tol_t * abs(b) + 1e-7, ('fused', k, a, b)
+    assert abs(float(lf['total_loss']) - float(tot_ref)) <= tol_t * abs(float(tot_ref))
     for k in PKEYS:
-        if Pt[k].grad is None:
-            continue
-        e = rel(Pg[k].grad, Pt[k].grad)
-        assert e < 5e-3, (k, e)
+        ref = Pt[k].grad.clone()
+        ref[:erase_n] = 0
+        assert float(gf[k][:erase_n].abs().max()) == 0.0 and float(g_eager[k][:erase_n].abs().max()) == 0.0
+        assert rel(gf[k], ref) < tol_g, ('fused', k, rel(gf[k], ref))
+        assert rel(g_eager[k], ref) < tol_g, ('eager', k, rel(g_eager[k], ref))
+
+
+def test_run_fitting_20_steps_with_freeze_fused_eager_oracle(monkeypatch):
+    B, n_it = 24, 20
+    P, cfg = synth.make_prox_problem(B, D=32, m_scene=3000, seed=2)
+    cfg['w']['shape'] = 0.5
+    c32 = oracle_ctx(torch.float32)
+    tr = []
+    P_ref, last_ref = ref_prox.fit_window(P, c32, cfg, n_it, lr=0.005, first_batch_flag=False, trace=tr)
+    res = {}
+    for mode in ('fused', 'eager'):
+        monkeypatch.setenv('LEMO_PROX_FUSED', '1' if mode == 'fused' else '0')
+        s = _reference_call_surface(B, P, cfg, maxiters=n_it, first_batch_flag=False)
+        with s['monitor'] as monitor:
+            final = monitor.run_fitting(s['optimizer'], s['closure'], s['final_params'], s['body_model'], pose_embedding=s['pose_embedding'],
+                                        vposer=s['vposer'], use_vposer=True)
+        assert monitor.last_path.startswith(mode), monitor.last_path
+        assert monitor.steps == n_it
+        res[mode] = (_params_of(s), final)
+    erase_n = int(B * 0.15)
+    for mode, (Pm, final) in res.items():
+        assert abs(final - last_ref) < 2e-3 * abs(last_ref), (mode, final, last_ref)
+        for k in PKEYS:
+            assert np.array_equal(Pm[k][:erase_n], P[k][:erase_n]), (mode, k)          # frozen frames keep their parameters bit for bit
+            # 20 Adam steps of lr .005 move a parameter by <= 0.1; the implementations must agree to a small fraction of that
+            assert np.abs(Pm[k] - P_ref[k]).max() < 3e-3, (mode, k, np.abs(Pm[k] - P_ref[k]).max())
+        assert np.abs(Pm['transl'] - P['transl']).max() > 1e-2                           # the free frames did move
+    assert tr[-1]['joint'] < tr[0]['joint']
+
+
+def test_fused_window_is_bitwise_reproducible():
+    B = 24
+    P, cfg = synth.make_prox_problem(B, D=32, m_scene=3000, seed=5)
+    outs = []
+    for _ in range(2):
+        s = _reference_call_surface(B, P, cfg, maxiters=8, first_batch_flag=True)
+        s['monitor'].run_fitting(s['optimizer'], s['closure'], s['final_params'], s['body_model'], pose_embedding=s['pose_embedding'],
+                                 vposer=s['vposer'], use_vposer=True)
+        assert s['monitor'].last_path == 'fused'
+        outs.append(_params_of(s))
+    for k in PKEYS:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_unsupported_terms_fall_back_to_the_eager_closure():
+    B = 12
+    P, cfg = synth.make_prox_problem(B, D=16, m_scene=500, seed=7)
+    s = _reference_call_surface(B, P, cfg, maxiters=2, first_batch_flag=True)
+    lbfgs_like = torch.optim.SGD(s['final_params'], lr=1e-4)
+    s['monitor'].run_fitting(lbfgs_like, s['closure'], s['final_params'], s['body_model'], pose_embedding=s['pose_embedding'],
+                             vposer=s['vposer'], use_vposer=True)
+    assert s['monitor'].last_path.startswith('eager'), s['monitor'].last_path

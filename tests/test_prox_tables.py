@@ -77,9 +77,10 @@ def test_create_loss_dispatch():
     assert fs.create_loss.__doc__
 
 
-def test_fitting_monitor_adam_loop_semantics(capsys):
-    """FittingMonitor.run_fitting (fitting_temp_slide.py:169-313, Adam branch) on a toy problem: `maxiters` steps, the first 15 % of
-    the batch keeps its values when erase_first is set (:281-288), and a non-finite loss stops the run with the reference's message (:197-203)."""
+def test_fitting_monitor_closure_protocol(capsys):
+    """FittingMonitor with the reference's signatures (fitting_temp_slide.py:137-217) on a toy closure (host tensors, so the eager
+    `optimizer.step(closure)` protocol is what runs): `maxiters` steps inside the context manager, the float of the last finite loss is
+    returned, a non-finite loss stops the run with the reference's message (:197-203)."""
     from lemo_b200.temp_prox.fitting_temp_slide import FittingMonitor
     target = torch.arange(20.).view(20, 1).expand(20, 3).clone()
     p = torch.zeros(20, 3, requires_grad=True)
@@ -87,18 +88,66 @@ def test_fitting_monitor_adam_loop_semantics(capsys):
     calls = []
 
     def closure():
-        calls.append(1)
-        return ((p - target) ** 2).sum()
-    loss = FittingMonitor(maxiters=25, erase_first=True).run_fitting(opt, closure, [p])
-    assert len(calls) == 25 and torch.isfinite(loss)
-    assert float(p[:3].detach().abs().sum()) == 0.0 and float(p[3:].detach().abs().sum()) > 0.0       # int(20 * 0.15) = 3 frames frozen
+        opt.zero_grad()
+        loss = ((p - target) ** 2).sum()
+        loss.backward()
+        calls.append(float(loss))
+        return loss
+    with FittingMonitor(summary_steps=1, maxiters=25, ftol=2e-9, gtol=1e-5, model_type='smplx', unknown_kwarg=1) as monitor:
+        final = monitor.run_fitting(opt, closure, [p], None, use_vposer=True, pose_embedding=None, vposer=None)
+    assert 'total steps:' in capsys.readouterr().out
+    assert len(calls) == 25 and isinstance(final, float) and final == calls[-1] and calls[-1] < calls[0]
+    assert monitor.last_path.startswith('eager')
     q = torch.zeros(4, requires_grad=True)
     n_calls = []
-    FittingMonitor(maxiters=40, check_every=10).run_fitting(torch.optim.Adam([q], lr=0.1),
-                                                            lambda: (n_calls.append(1), (q * float('nan')).sum())[1], [q])
-    assert 'NaN loss value, stopping!' in capsys.readouterr().out and len(n_calls) == 10
-    q = torch.zeros(4, requires_grad=True)                 # (the NaN run above poisoned the old one, as it does in the reference)
-    FittingMonitor(maxiters=3).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: (q * 0).sum() + float('inf'), [q])
+    r = FittingMonitor(maxiters=40).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: (n_calls.append(1), (q * float('nan')).sum())[1], [q], None)
+    assert 'NaN loss value, stopping!' in capsys.readouterr().out and len(n_calls) == 1 and r is None
+    q = torch.zeros(4, requires_grad=True)
+    FittingMonitor(maxiters=3).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: (q * 0).sum() + float('inf'), [q], None)
     assert 'Infinite loss value, stopping!' in capsys.readouterr().out
-    with pytest.raises(RuntimeError, match='capturable'):
-        FittingMonitor(maxiters=10, use_cuda_graph=True).run_fitting(torch.optim.Adam([q], lr=0.1), lambda: q.sum(), [q])
+
+
+def test_smplify_loss_reference_signature():
+    """SMPLifyLoss(**the kwargs fit_temp_loadprox_slide.py:431-485 passes) constructs, exposes the reference's weight buffers, accepts
+    reset_loss_weights (:548-562) with floats and tensors, and reports which configurations the fused driver covers."""
+    import inspect
+    from lemo_b200.temp_prox.fitting_temp_slide import SMPLifyLoss, FittingMonitor, create_loss
+    from lemo_b200.temp_prox.prior import create_prior
+    ref_init = ['search_tree', 'pen_distance', 'tri_filtering_module', 'body_pose_prior', 'shape_prior', 'expr_prior', 'angle_prior', 'jaw_prior',
+                'use_joints_conf', 'use_face', 'use_hands', 'left_hand_prior', 'right_hand_prior', 'interpenetration', 'dtype', 'data_weight',
+                'body_pose_weight', 'shape_weight', 'bending_prior_weight', 'hand_prior_weight', 'expr_prior_weight', 'jaw_prior_weight',
+                'coll_loss_weight', 's2m', 'm2s', 'rho_s2m', 'rho_m2s', 's2m_weight', 'm2s_weight', 'head_mask', 'body_mask', 'sdf_penetration',
+                'voxel_size', 'grid_min', 'grid_max', 'sdf', 'sdf_normals', 'sdf_penetration_weight', 'R', 't', 'contact', 'contact_loss_weight',
+                'contact_verts_ids', 'smooth_acc', 'smooth_acc_weight', 'smooth_vel', 'smooth_vel_weight', 'use_motion_smooth_prior',
+                'motion_prior_smooth_weight', 'motion_smooth_model', 'use_friction', 'friction_normal_weight', 'friction_tangent_weight',
+                'contact_fric_verts_ids', 'use_motion_infill_prior', 'motion_infill_rec_weight', 'motion_infill_contact_weight',
+                'motion_infill_model', 'infill_pretrain_weights', 'device']
+    assert list(inspect.signature(SMPLifyLoss.__init__).parameters)[1:-1] == ref_init
+    fwd = list(inspect.signature(SMPLifyLoss.forward).parameters)[1:]
+    assert fwd == ['body_model', 'body_model_output', 'smplx_joints', 'camera', 'gt_joints', 'joints_conf', 'marker_mask', 'body_model_faces',
+                   'joint_weights', 'use_vposer', 'pose_embedding', 'scan_tensor', 'scan_point_num', 'scene_v', 'opt_step', 'kwargs']
+    assert list(inspect.signature(FittingMonitor.run_fitting).parameters)[1:] == ['optimizer', 'closure', 'params', 'body_model', 'use_vposer',
+                                                                                  'pose_embedding', 'vposer', 'kwargs']
+    cl = list(inspect.signature(FittingMonitor.create_fitting_closure).parameters)[1:]
+    assert cl == ['optimizer', 'body_model', 'camera', 'gt_joints', 'loss', 'joints_conf', 'marker_mask', 'joint_weights', 'return_verts',
+                  'return_full_pose', 'use_vposer', 'vposer', 'pose_embedding', 'scan_tensor', 'scan_point_num', 'scene_v', 'create_graph',
+                  'writer', 'first_batch_flag', 'kwargs']
+    loss = create_loss(loss_type='smplify', rho=100, vposer=None, pose_embedding=None, body_pose_prior=create_prior('l2'),
+                       shape_prior=create_prior('l2'), angle_prior=create_prior('angle'), expr_prior=create_prior('l2'),
+                       left_hand_prior=create_prior('l2'), right_hand_prior=create_prior('l2'), jaw_prior=create_prior('l2'),
+                       interpenetration=False, sdf_penetration=True, sdf=torch.zeros(2, 1, 4, 4, 4), grid_min=torch.zeros(2, 1, 3),
+                       grid_max=torch.ones(2, 1, 3), R=torch.eye(3), t=torch.zeros(1, 3), contact=True, contact_verts_ids=np.arange(5),
+                       use_friction=True, contact_fric_verts_ids=np.arange(3), use_motion_smooth_prior=True, motion_smooth_model=None,
+                       device='cpu')
+    assert tuple(loss.sdf.shape) == (4, 4, 4) and tuple(loss.grid_min.shape) == (3,)          # one volume kept, not B replicas
+    loss.reset_loss_weights({'data_weight': 2.0, 'contact_loss_weight': torch.tensor(0.5), 'hand_weight': 1.0, 'not_an_attribute': 3})
+    assert float(loss.data_weight) == 2.0 and float(loss.contact_loss_weight) == 0.5
+    assert loss.weight_dict()['data_weight'] == 2.0 and loss.weight_dict()['friction_normal_weight'] == 0.0
+    assert loss.fusable(use_vposer=True)[0]
+    assert not loss.fusable(use_vposer=False)[0]
+    loss2 = create_loss(smooth_vel=True, smooth_vel_weight=1.0, angle_prior=create_prior('angle'), interpenetration=False, R=torch.eye(3), t=torch.zeros(1, 3))
+    assert not loss2.fusable(use_vposer=True)[0]
+    with pytest.raises(ValueError):
+        create_loss(loss_type='camera_init')
+
+

@@ -19,7 +19,7 @@ for step in "$@"; do
               timeout 120 python tools/diag_lbs.py 120 300 > gpurun_out/diag_lbs.log 2>&1 ;;
     stages)   # launch lists of the secondary stages (infill pre-stage, per-frame, PROX window) for planning
               timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_stages.csv \
-                python tools/run_stage.py infill perframe prox > gpurun_out/stages_under_ncu.log 2>&1; tail -3 gpurun_out/stages_under_ncu.log ;;
+                python tools/run_stage.py prox perframe > gpurun_out/stages_under_ncu.log 2>&1; tail -3 gpurun_out/stages_under_ncu.log ;;
     *) echo "unknown step $step" ;;
   esac
 done

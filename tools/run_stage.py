@@ -42,7 +42,11 @@ if 'perframe' in stages:
     print('PERFRAME done', flush=True)
 
 if 'prox' in stages:
-    from lemo_b200.temp_prox.fitting_temp_slide import run_synthetic_window
-    run_synthetic_window(body, vp, B=100, D=256, m_scene=100000, n_iters=2, device=dev)
+    from lemo_b200.temp_prox.synthetic import make_window
+    from lemo_b200.fit import load_smooth_prior
+    fit, _, _ = make_window(body, vp, load_smooth_prior().to(dev), B=100, D=256, m_scene=100000, device=dev, use_cuda_graph=False)
+    torch.cuda.synchronize()
+    print('PROX BEGIN', flush=True)
+    fit.run(3)
     torch.cuda.synchronize()
     print('PROX done', flush=True)
