@@ -28,6 +28,8 @@ extern "C" {
 
 const char* lemo_last_error(void);
 int lemo_version(void);
+/* debugging aid: cudaDeviceSynchronize + cudaGetLastError (clears the sticky state); 0 = clean, else lemo_last_error() has the text */
+int lemo_debug_check(void);
 
 /* ---------------------------------------------------------------- body model (smplx.create) ------------ */
 typedef struct LemoModel LemoModel;   /* immutable model tensors on one device        */
@@ -164,6 +166,12 @@ int lemo_ae_backward_weights(LemoConvNet* net, const float* d_rec, int32_t N, fl
  * resets the moments).  loss_out: device float, nullable. */
 int lemo_ae_finetune_step(LemoConvNet* net, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr,
                           int32_t t, float* loss_out, void* stream);
+
+/* the whole fine-tune loop (opt_amass_perframe.py:152-173): `steps` x lemo_ae_finetune_step with a fresh Adam, the step captured ONCE as a
+ * CUDA graph (step counter / bias corrections on the device) and replayed; losses_out: device float[steps], nullable.  Every reduction
+ * (split-K convolutions of the small planes, weight gradients) has a fixed order: the fine-tuned weights are bitwise reproducible. */
+int lemo_ae_finetune_run(LemoConvNet* net, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr,
+                         int32_t steps, float* losses_out, void* stream);
 
 /* ---------------------------------------------------------------- infill pre-stage --- */
 /* Body representation of one clip (utils/utils.py:209-265 get_local_markers_4chan + the loader's normalisation and layout,

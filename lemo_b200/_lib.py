@@ -104,6 +104,7 @@ _P, _I, _L, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
     'lemo_last_error': (C.c_char_p, []),
     'lemo_version': (C.c_int, []),
+    'lemo_debug_check': (C.c_int, []),
     'lemo_model_create': (C.c_int, [C.POINTER(LemoModelDescC), C.c_int, C.POINTER(_P)]),
     'lemo_model_select_rows': (C.c_int, [_P, _P, _I, C.POINTER(_P)]),
     'lemo_model_destroy': (C.c_int, [_P]),
@@ -140,6 +141,7 @@ SIGNATURES = {
     'lemo_ae_forward': (C.c_int, [_P, _P, _I, _P, _P, _P]),
     'lemo_ae_backward_weights': (C.c_int, [_P, _P, _I, _P, _P]),
     'lemo_ae_finetune_step': (C.c_int, [_P, _P, _P, _I, _I, _D, _I, _P, _P]),
+    'lemo_ae_finetune_run': (C.c_int, [_P, _P, _P, _I, _I, _D, _I, _P, _P]),
     'lemo_chamfer_forward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P]),
     'lemo_chamfer_backward': (C.c_int, [_P, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     'lemo_scene_create': (C.c_int, [_P, _I, C.POINTER(_P)]),
@@ -180,9 +182,10 @@ SIGNATURES = {
     'lemo_host_rotmat_to_aa_bwd': (None, [_P, _P, _P]),
     'lemo_host_aa_to_rotmat_tgm': (None, [_P, _P]),
 }
-STATUS_FUNCS = {k for k, (r, _) in SIGNATURES.items() if r is C.c_int and k not in ('lemo_version', 'lemo_model_num_verts')}
+STATUS_FUNCS = {k for k, (r, _) in SIGNATURES.items() if r is C.c_int and k not in ('lemo_version', 'lemo_model_num_verts', 'lemo_debug_check')}
 
 _lib = None
+_DEBUG_CHECK = os.environ.get('LEMO_DEBUG_CHECK', '0') == '1'     # synchronise + check the CUDA error state after every C-ABI call
 
 
 def lib():
@@ -207,6 +210,8 @@ def call(name, *args):
     r = getattr(L, name)(*args)
     if name in STATUS_FUNCS and r != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, r, L.lemo_last_error().decode()))
+    if _DEBUG_CHECK and L.lemo_debug_check() != 0:
+        raise RuntimeError('after %s: %s' % (name, L.lemo_last_error().decode()))
     return r
 
 

@@ -6,6 +6,7 @@
 // Everything stays on the padded pitch-linear planes of conv.cuh, one geometry per resolution level; a stride-2
 // ConvTranspose is a zero-upsample (value at (2y,2x)) followed by the stride-1 kernel with flipped taps.
 #include "handles.cuh"
+#include "fit_common.cuh"
 #include "../../include/lemo_b200.h"
 #include <algorithm>
 
@@ -80,60 +81,85 @@ __global__ void k_mask_inplace(float* __restrict__ g, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient
-// G[oc][ic][k] = sum_{n,q} dpre[n][oc][q] * x[n][ic][q + off_k];  db[oc] = sum dpre.   16x16 (oc,ic) tile per CTA,
-// 256-pixel chunks of the linear range staged in shared memory, atomicAdd of the per-chunk partials.
+// G[oc][ic][k] = sum_{n,q} dpre[n][oc][q] * x[n][ic][q + off_k];  db[oc] = sum dpre.   16x16 (oc,ic) tile per CTA, the linear pixel
+// range cut into 256-pixel chunks staged in shared memory.  Deterministic: the chunks are dealt to NG groups (blockIdx.z = n*NG + g),
+// a CTA accumulates its chunks in registers and stores ONE partial per (group, weight); k_wgrad_finish adds the N*NG partials in
+// order and writes the gradient in the state_dict layout (the first version atomicAdd-ed every chunk: order-dependent rounding).
 constexpr int WG_T = 16, WG_CP = 256;
-__global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ dW,
-                                               float* __restrict__ db, int Cin, int Cout, int H, int Wp, int PS, int nchunks, int SWX,
-                                               int transposed) {
+__global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ part,
+                                               int Cin, int Cout, int H, int Wp, int PS, int nchunks, int NG, int SWX) {
     extern __shared__ float sm[];
     float* s_d = sm;                               // [16][WG_CP+1]
     float* s_x = sm + WG_T * (WG_CP + 1);          // [16][SWX]
     const int o = threadIdx.x & 15, i = threadIdx.x >> 4;
     const int oc0 = blockIdx.x * WG_T, ic0 = blockIdx.y * WG_T;
-    const int n = blockIdx.z / nchunks, ch = blockIdx.z % nchunks;
-    const int q0 = Wp + ch * WG_CP;
+    const int n = blockIdx.z / NG, g = blockIdx.z - n * NG;
     const int qend = (H + 1) * Wp;
-    for (int e = threadIdx.x; e < WG_T * WG_CP; e += 256) {
-        const int r = e / WG_CP, p = e % WG_CP;
-        const int q = q0 + p;
-        s_d[r * (WG_CP + 1) + p] = (oc0 + r < Cout && q < qend) ? dpre[((size_t)n * Cout + oc0 + r) * PS + q] : 0.f;
-    }
     const int span = WG_CP + 2 * Wp + 2;
-    for (int e = threadIdx.x; e < WG_T * span; e += 256) {
-        const int r = e / span, p = e % span;
-        const int q = q0 - Wp - 1 + p;
-        s_x[r * SWX + p] = (ic0 + r < Cin && q >= 0 && q < PS) ? x[((size_t)n * Cin + ic0 + r) * PS + q] : 0.f;
-    }
-    __syncthreads();
     float acc[9], bsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-    const float* dr = s_d + o * (WG_CP + 1);
-    const float* xr = s_x + i * SWX;
-    for (int p = 0; p < WG_CP; ++p) {
-        const float d = dr[p];
-        bsum += d;
+    for (int ch = g; ch < nchunks; ch += NG) {
+        const int q0 = Wp + ch * WG_CP;
+        __syncthreads();
+        for (int e = threadIdx.x; e < WG_T * WG_CP; e += 256) {
+            const int r = e / WG_CP, p = e % WG_CP;
+            const int q = q0 + p;
+            s_d[r * (WG_CP + 1) + p] = (oc0 + r < Cout && q < qend) ? dpre[((size_t)n * Cout + oc0 + r) * PS + q] : 0.f;
+        }
+        for (int e = threadIdx.x; e < WG_T * span; e += 256) {
+            const int r = e / span, p = e % span;
+            const int q = q0 - Wp - 1 + p;
+            s_x[r * SWX + p] = (ic0 + r < Cin && q >= 0 && q < PS) ? x[((size_t)n * Cin + ic0 + r) * PS + q] : 0.f;
+        }
+        __syncthreads();
+        const float* dr = s_d + o * (WG_CP + 1);
+        const float* xr = s_x + i * SWX;
+        for (int p = 0; p < WG_CP; ++p) {
+            const float d = dr[p];
+            bsum += d;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(d, xr[p + ky * Wp + kx], acc[ky * 3 + kx]);
-    }
-    const int oc = oc0 + o, ic = ic0 + i;
-    if (oc < Cout && ic < Cin) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            // Conv2d weight [oc][ic][k]; ConvTranspose2d weight [ic_t = our ic][oc_t = our oc][8-k]
-            const size_t w = transposed ? ((size_t)ic * Cout + oc) * 9 + (8 - k) : ((size_t)oc * Cin + ic) * 9 + k;
-            atomicAdd(&dW[w], acc[k]);
+                for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(d, xr[p + ky * Wp + kx], acc[ky * 3 + kx]);
         }
     }
-    if (blockIdx.y == 0 && i == 0 && oc < Cout) atomicAdd(&db[oc], bsum);
+    const int oc = oc0 + o, ic = ic0 + i;
+    float* pz = part + (size_t)blockIdx.z * ((size_t)Cout * Cin * 9 + Cout);
+    if (oc < Cout && ic < Cin) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) pz[((size_t)oc * Cin + ic) * 9 + k] = acc[k];
+    }
+    if (blockIdx.y == 0 && i == 0 && oc < Cout) pz[(size_t)Cout * Cin * 9 + oc] = bsum;
+}
+// dW (state_dict layout) = sum of the partials in (n, group) order; Conv2d weight [oc][ic][k]; ConvTranspose2d weight
+// [ic_t = our ic][oc_t = our oc][8-k]
+__global__ void k_wgrad_finish(const float* __restrict__ part, int nparts, int Cin, int Cout, int transposed, float* __restrict__ dW,
+                               float* __restrict__ db) {
+    const int nw = Cout * Cin * 9;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nw + Cout) return;
+    float a = 0.f;
+    for (int p = 0; p < nparts; ++p) a += part[(size_t)p * (nw + Cout) + e];
+    if (e >= nw) { db[e - nw] = a; return; }
+    const int k = e % 9, ic = (e / 9) % Cin, oc = e / (9 * Cin);
+    dW[transposed ? ((size_t)ic * Cout + oc) * 9 + (8 - k) : (size_t)e] = a;
+}
+
+static int wgrad_groups(int N, int Cin, int Cout, const PlaneGeom& g) {
+    const int nchunks = cdiv((long long)g.H * g.Wp, WG_CP);
+    const long long tiles = (long long)cdiv(Cout, WG_T) * cdiv(Cin, WG_T) * N;
+    return (int)std::max(1LL, std::min<long long>(nchunks, (296 + tiles - 1) / tiles));
+}
+size_t conv3x3_wgrad_floats(int N, int Cin, int Cout, const PlaneGeom& g) {
+    return (size_t)N * wgrad_groups(N, Cin, Cout, g) * ((size_t)Cout * Cin * 9 + Cout);
 }
 
 int conv3x3_wgrad_launch(const float* x, const float* dpre, float* dW, float* db, int N, int Cin, int Cout, const PlaneGeom& g,
-                         bool transposed, cudaStream_t st) {
+                         bool transposed, cudaStream_t st, float* scratch, size_t scratch_floats) {
+    LEMO_CHECK(scratch && scratch_floats >= conv3x3_wgrad_floats(N, Cin, Cout, g), "weight-gradient scratch too small");
     const int nchunks = cdiv((long long)g.H * g.Wp, WG_CP);
+    const int NG = wgrad_groups(N, Cin, Cout, g);
     const int SWX = WG_CP + 2 * g.Wp + 2 + 1;
     const size_t smem = (size_t)(WG_T * (WG_CP + 1) + WG_T * SWX) * sizeof(float);
     static size_t configured = 0;
@@ -141,20 +167,14 @@ int conv3x3_wgrad_launch(const float* x, const float* dpre, float* dW, float* db
         LEMO_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(cdiv(Cout, WG_T), cdiv(Cin, WG_T), N * nchunks);
-    k_wgrad<<<grid, 256, smem, st>>>(x, dpre, dW, db, Cin, Cout, g.H, g.Wp, g.PS, nchunks, SWX, transposed ? 1 : 0);
+    dim3 grid(cdiv(Cout, WG_T), cdiv(Cin, WG_T), N * NG);
+    k_wgrad<<<grid, 256, smem, st>>>(x, dpre, scratch, Cin, Cout, g.H, g.Wp, g.PS, nchunks, NG, SWX);
+    k_wgrad_finish<<<cdiv(Cout * Cin * 9 + Cout, 256), 256, 0, st>>>(scratch, N * NG, Cin, Cout, transposed ? 1 : 0, dW, db);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- network
-template <typename T>
-static int dalloc(T** p, size_t n) {
-    LEMO_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
-    LEMO_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
-    return 0;
-}
-
 // buffer map for kind==1 (index into ConvNet::act): 0 = input; encoder level i (0..4): 1+3i = after conv1, 2+3i = after conv2
 // (pre-pool), 3+3i = pooled (level i+1);  decoder block b (0..4): 16+3b = upsampled input, 17+3b = after deconv1, 18+3b = after deconv2
 static inline int E1(int i) { return 1 + 3 * i; }
@@ -212,10 +232,30 @@ int ae_create(int in_ch, const float* h_weights, long long n_weights, int maxN, 
         LEMO_TRY(dalloc(&n->act[D2(b)], N * dc[b + 1] * g.PS));
         gmax = std::max(gmax, N * (size_t)std::max(dc[b], dc[b + 1]) * g.PS);
     }
+    // workspaces: split-K partials of the small-plane convolutions (forward and input gradient) and weight-gradient partials
+    size_t sk = 0, wg = 0;
+    for (int i = 0; i < 5; ++i) {
+        const PlaneGeom& g = n->geom[i];
+        for (int l = 0; l < 2; ++l) {
+            const ConvLayer& L = n->layers[2 * i + l];
+            sk = std::max(sk, std::max(conv3x3_splitk_floats(maxN, L.Cin, L.Cout, g), conv3x3_splitk_floats(maxN, L.Cout, L.Cin, g)));
+            wg = std::max(wg, conv3x3_wgrad_floats(maxN, L.Cin, L.Cout, g));
+        }
+    }
+    for (int b = 0; b < 5; ++b) {
+        const PlaneGeom& g = n->geom[4 - b];
+        for (int l = 0; l < 2; ++l) {
+            const ConvLayer& L = n->layers[10 + 2 * b + l];
+            sk = std::max(sk, std::max(conv3x3_splitk_floats(maxN, L.Cin, L.Cout, g), conv3x3_splitk_floats(maxN, L.Cout, L.Cin, g)));
+            wg = std::max(wg, conv3x3_wgrad_floats(maxN, L.Cin, L.Cout, g));
+        }
+    }
+    if (sk) { LEMO_TRY(dalloc(&n->sk_scratch, sk)); n->sk_floats = sk; }
     if (with_backward) {
         n->grad.resize(2, nullptr);
         LEMO_TRY(dalloc(&n->grad[0], gmax));
         LEMO_TRY(dalloc(&n->grad[1], gmax));
+        LEMO_TRY(dalloc(&n->wg_scratch, wg)); n->wg_floats = wg;
     }
     LEMO_CUDA(cudaDeviceSynchronize());
     *out = n;
@@ -228,8 +268,8 @@ static int ae_forward_planes(ConvNet* n, int N, cudaStream_t st) {
     for (int i = 0; i < 5; ++i) {
         const PlaneGeom& g = n->geom[i];
         const ConvLayer &A = n->layers[2 * i], &B = n->layers[2 * i + 1];
-        LEMO_TRY(conv3x3_launch(cur, A.wk_f, n->w_flat + A.b_off, nullptr, n->act[E1(i)], N, A.Cin, A.Cout, g, EPI_BIAS_LRELU, st));
-        LEMO_TRY(conv3x3_launch(n->act[E1(i)], B.wk_f, n->w_flat + B.b_off, nullptr, n->act[E2(i)], N, B.Cin, B.Cout, g, EPI_BIAS_LRELU, st));
+        LEMO_TRY(conv3x3_launch(cur, A.wk_f, n->w_flat + A.b_off, nullptr, n->act[E1(i)], N, A.Cin, A.Cout, g, EPI_BIAS_LRELU, st, n->sk_scratch, n->sk_floats));
+        LEMO_TRY(conv3x3_launch(n->act[E1(i)], B.wk_f, n->w_flat + B.b_off, nullptr, n->act[E2(i)], N, B.Cin, B.Cout, g, EPI_BIAS_LRELU, st, n->sk_scratch, n->sk_floats));
         const PlaneGeom& gd = n->geom[i + 1];
         const long long tot = (long long)N * ec[i + 1] * gd.H * gd.W;
         k_maxpool_fwd<<<cdiv(tot, 256), 256, 0, st>>>(n->act[E2(i)], N * ec[i + 1], g, gd, n->act[EP(i)], n->pool_idx[i]);
@@ -241,9 +281,9 @@ static int ae_forward_planes(ConvNet* n, int N, cudaStream_t st) {
         LEMO_CUDA(cudaMemsetAsync(n->act[DU(b)], 0, (size_t)N * dc[b] * gd.PS * sizeof(float), st));
         const long long tot = (long long)N * dc[b] * gs.H * gs.W;
         k_upsample_fwd<<<cdiv(tot, 256), 256, 0, st>>>(cur, N * dc[b], gs, gd, n->act[DU(b)]);
-        LEMO_TRY(conv3x3_launch(n->act[DU(b)], A.wk_f, n->w_flat + A.b_off, nullptr, n->act[D1(b)], N, A.Cin, A.Cout, gd, EPI_BIAS_LRELU, st));
+        LEMO_TRY(conv3x3_launch(n->act[DU(b)], A.wk_f, n->w_flat + A.b_off, nullptr, n->act[D1(b)], N, A.Cin, A.Cout, gd, EPI_BIAS_LRELU, st, n->sk_scratch, n->sk_floats));
         LEMO_TRY(conv3x3_launch(n->act[D1(b)], B.wk_f, n->w_flat + B.b_off, nullptr, n->act[D2(b)], N, B.Cin, B.Cout, gd,
-                                b < 4 ? EPI_BIAS_LRELU : EPI_BIAS, st));
+                                b < 4 ? EPI_BIAS_LRELU : EPI_BIAS, st, n->sk_scratch, n->sk_floats));
         cur = n->act[D2(b)];
     }
     LEMO_CUDA(cudaGetLastError());
@@ -254,7 +294,6 @@ static int ae_forward_planes(ConvNet* n, int N, cudaStream_t st) {
 // d_rec already packed into grad[0] (1 channel at level 0); writes d_weights (flat, state_dict order, pre-zeroed here)
 static int ae_backward_planes(ConvNet* n, int N, float* dW, cudaStream_t st) {
     const int ec[6] = {n->in_ch, 32, 64, 128, 256, 256}, dc[6] = {256, 256, 128, 64, 32, 1};
-    LEMO_CUDA(cudaMemsetAsync(dW, 0, n->n_weights * sizeof(float), st));
     float* cur = n->grad[0];      // dpre of the layer being processed
     float* nxt = n->grad[1];
     // the two gradient buffers are reused across resolution levels, so the zero-border invariant of the plane layout
@@ -264,14 +303,14 @@ static int ae_backward_planes(ConvNet* n, int N, float* dW, cudaStream_t st) {
         const PlaneGeom &gs = n->geom[5 - b], &gd = n->geom[4 - b];
         const ConvLayer &A = n->layers[10 + 2 * b], &B = n->layers[11 + 2 * b];
         // deconv2: dpre in cur (for b<4 it already carries LeakyReLU'(D2))
-        LEMO_TRY(conv3x3_wgrad_launch(n->act[D1(b)], cur, dW + B.w_off, dW + B.b_off, N, B.Cin, B.Cout, gd, true, st));
+        LEMO_TRY(conv3x3_wgrad_launch(n->act[D1(b)], cur, dW + B.w_off, dW + B.b_off, N, B.Cin, B.Cout, gd, true, st, n->wg_scratch, n->wg_floats));
         LEMO_CUDA(zero(nxt, B.Cin, gd));
-        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[D1(b)], nxt, N, B.Cout, B.Cin, gd, EPI_MASK, st));
+        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[D1(b)], nxt, N, B.Cout, B.Cin, gd, EPI_MASK, st, n->sk_scratch, n->sk_floats));
         std::swap(cur, nxt);
         // deconv1
-        LEMO_TRY(conv3x3_wgrad_launch(n->act[DU(b)], cur, dW + A.w_off, dW + A.b_off, N, A.Cin, A.Cout, gd, true, st));
+        LEMO_TRY(conv3x3_wgrad_launch(n->act[DU(b)], cur, dW + A.w_off, dW + A.b_off, N, A.Cin, A.Cout, gd, true, st, n->wg_scratch, n->wg_floats));
         LEMO_CUDA(zero(nxt, A.Cin, gd));
-        LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, gd, EPI_NONE, st));
+        LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, gd, EPI_NONE, st, n->sk_scratch, n->sk_floats));
         std::swap(cur, nxt);
         // through the zero-upsample to the tensor that fed this block: D2(b-1) (LeakyReLU output) or the pooled code z
         const long long tot = (long long)N * dc[b] * gs.H * gs.W;
@@ -288,15 +327,15 @@ static int ae_backward_planes(ConvNet* n, int N, float* dW, cudaStream_t st) {
         LEMO_CUDA(cudaMemsetAsync(nxt, 0, (size_t)N * ec[i + 1] * g.PS * sizeof(float), st));
         k_maxpool_bwd_mask<<<cdiv(tot, 256), 256, 0, st>>>(cur, n->pool_idx[i], n->act[E2(i)], N * ec[i + 1], g, gd, nxt);
         std::swap(cur, nxt);          // cur = dpre of conv2 at level i
-        LEMO_TRY(conv3x3_wgrad_launch(n->act[E1(i)], cur, dW + B.w_off, dW + B.b_off, N, B.Cin, B.Cout, g, false, st));
+        LEMO_TRY(conv3x3_wgrad_launch(n->act[E1(i)], cur, dW + B.w_off, dW + B.b_off, N, B.Cin, B.Cout, g, false, st, n->wg_scratch, n->wg_floats));
         LEMO_CUDA(zero(nxt, B.Cin, g));
-        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[E1(i)], nxt, N, B.Cout, B.Cin, g, EPI_MASK, st));
+        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[E1(i)], nxt, N, B.Cout, B.Cin, g, EPI_MASK, st, n->sk_scratch, n->sk_floats));
         std::swap(cur, nxt);          // cur = dpre of conv1 at level i
         const float* xin = i > 0 ? n->act[EP(i - 1)] : n->act[0];
-        LEMO_TRY(conv3x3_wgrad_launch(xin, cur, dW + A.w_off, dW + A.b_off, N, A.Cin, A.Cout, g, false, st));
+        LEMO_TRY(conv3x3_wgrad_launch(xin, cur, dW + A.w_off, dW + A.b_off, N, A.Cin, A.Cout, g, false, st, n->wg_scratch, n->wg_floats));
         if (i > 0) {
             LEMO_CUDA(zero(nxt, A.Cin, g));
-            LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, g, EPI_NONE, st));
+            LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, g, EPI_NONE, st, n->sk_scratch, n->sk_floats));
             std::swap(cur, nxt);      // cur = dL/d(pooled output of level i-1), on level-i planes
         }
     }
@@ -325,6 +364,27 @@ __global__ void __launch_bounds__(256) k_ae_l1(const float* __restrict__ rec_pla
     }
     part = block_sum(part, sred);
     if (threadIdx.x == 0 && loss) atomicAdd(loss, part * inv_count);
+}
+// k_ae_l1 for the graph-replayed driver: the loss of step t lands in losses[t-1] (k_sched has already advanced the step counter)
+__global__ void __launch_bounds__(256) k_ae_l1_sched(const float* __restrict__ rec_planes, const float* __restrict__ x_planes,
+                                                     const float* __restrict__ row_mask, int N, int C, PlaneGeom g, float inv_count,
+                                                     float* __restrict__ d_planes, float* __restrict__ losses, const Sched* __restrict__ sc) {
+    __shared__ float sred[32];
+    float part = 0.f;
+    const long long tot = (long long)N * g.H * g.W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % g.W), y = (int)((i / g.W) % g.H), n = (int)(i / ((long long)g.W * g.H));
+        const int q = (y + 1) * g.Wp + x + 1;
+        float d = 0.f;
+        if (row_mask[y] != 0.f) {
+            const float r = rec_planes[(size_t)n * g.PS + q] - x_planes[(size_t)n * C * g.PS + q];
+            part += fabsf(r);
+            d = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * inv_count;
+        }
+        d_planes[(size_t)n * g.PS + q] = d;
+    }
+    part = block_sum(part, sred);
+    if (threadIdx.x == 0 && losses) atomicAdd(&losses[sc->it - 1], part * inv_count);
 }
 __global__ void k_adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                             float b1, float b2, float eps, float bc1, float bc2s) {
@@ -366,6 +426,75 @@ int lemo_ae_finetune_step(LemoConvNet* h, const float* x, const float* row_mask,
     k_adam_flat<<<cdiv(n->n_weights, 256), 256, 0, st>>>(n->w_flat, dW, m1, m2, n->n_weights, (float)lr, 0.9f, 0.999f, 1e-8f, bc1, bc2s);
     LEMO_CUDA(cudaGetLastError());
     return convnet_refresh_weights(n, st);
+}
+
+// one fine-tune step with the step-dependent scalars on the device (replayable)
+static int ae_finetune_graph_step(ConvNet* n, cudaStream_t st) {
+    const PlaneGeom& g = n->geom[0];
+    const int N = n->ft_N;
+    float* dW = n->d_wflat;
+    float* m1 = dW + n->n_weights;
+    float* m2 = m1 + n->n_weights;
+    k_sched<<<1, 1, 0, st>>>((Sched*)n->ft_sched);
+    LEMO_TRY(ae_forward_planes(n, N, st));
+    LEMO_CUDA(cudaMemsetAsync(n->grad[0], 0, (size_t)N * g.PS * sizeof(float), st));
+    const float inv_count = 1.f / ((float)N * (float)n->ft_rows * (float)g.W);
+    k_ae_l1_sched<<<64, 256, 0, st>>>(n->act[18 + 3 * 4], n->act[0], (const float*)n->ft_mask, N, n->in_ch, g, inv_count, n->grad[0],
+                                     n->ft_losses, (const Sched*)n->ft_sched);
+    LEMO_TRY(ae_backward_planes(n, N, dW, st));
+    k_adam_dev<<<cdiv(n->n_weights, 256), 256, 0, st>>>(n->w_flat, dW, m1, m2, (int)n->n_weights, (const Sched*)n->ft_sched);
+    LEMO_CUDA(cudaGetLastError());
+    return convnet_refresh_weights(n, st);
+}
+
+int lemo_ae_finetune_run(LemoConvNet* h, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr, int32_t steps,
+                         float* losses_out, void* stream) {
+    LEMO_CHECK(h && h->n->kind == 1 && x && row_mask && h->n->with_backward && steps >= 0 && n_rows_selected > 0, "bad arguments");
+    ConvNet* n = h->n;
+    cudaStream_t st = (cudaStream_t)stream;
+    LEMO_CHECK(N > 0 && N <= n->maxN, "batch exceeds handle size");
+    if (!n->d_wflat) LEMO_CUDA(cudaMalloc((void**)&n->d_wflat, 3 * n->n_weights * sizeof(float)));
+    if (!n->ft_sched) LEMO_CUDA(cudaMalloc(&n->ft_sched, sizeof(Sched)));
+    // fresh optim.Adam (opt_amass_perframe.py:127-129): zero moments, step counter 0, constant lr
+    LEMO_CUDA(cudaMemsetAsync(n->d_wflat + n->n_weights, 0, 2 * n->n_weights * sizeof(float), st));
+    Sched s{};
+    s.it = 0; s.lr0 = s.lr1 = s.lr2 = (float)lr; s.sw1 = s.sw2 = 1 << 30;
+    LEMO_CUDA(cudaMemcpyAsync(n->ft_sched, &s, sizeof(Sched), cudaMemcpyHostToDevice, st));
+    if (losses_out) LEMO_CUDA(cudaMemsetAsync(losses_out, 0, (size_t)steps * sizeof(float), st));
+    LEMO_TRY(pack_planes(x, n->act[0], N * n->in_ch, n->geom[0], st));          // the input is the same for every step (:164-184)
+    // the captured step bakes these pointers / sizes: re-capture when they change
+    const bool same = n->ft_gexec && n->ft_mask == row_mask && n->ft_losses == losses_out && n->ft_N == N && n->ft_rows == n_rows_selected;
+    if (!same) {
+        if (n->ft_gexec) { cudaGraphExecDestroy((cudaGraphExec_t)n->ft_gexec); n->ft_gexec = nullptr; }
+        if (n->ft_graph) { cudaGraphDestroy((cudaGraph_t)n->ft_graph); n->ft_graph = nullptr; }
+        n->ft_mask = row_mask; n->ft_losses = losses_out; n->ft_N = N; n->ft_rows = n_rows_selected;
+    }
+    if (steps == 0) return 0;
+    if (!n->ft_stream) {
+        cudaStream_t gs; cudaEvent_t e0, e1;
+        LEMO_CUDA(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        LEMO_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+        LEMO_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        n->ft_stream = gs; n->ft_ev_in = e0; n->ft_ev_out = e1;
+    }
+    cudaStream_t gs = (cudaStream_t)n->ft_stream;
+    LEMO_CUDA(cudaEventRecord((cudaEvent_t)n->ft_ev_in, st));
+    LEMO_CUDA(cudaStreamWaitEvent(gs, (cudaEvent_t)n->ft_ev_in, 0));
+    if (!n->ft_gexec) {
+        LEMO_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        const int r = ae_finetune_graph_step(n, gs);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(gs, &g);
+        if (r) { if (g) cudaGraphDestroy(g); return r; }
+        LEMO_CUDA(e);
+        cudaGraphExec_t ge = nullptr;
+        LEMO_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        n->ft_graph = g; n->ft_gexec = ge;
+    }
+    for (int i = 0; i < steps; ++i) LEMO_CUDA(cudaGraphLaunch((cudaGraphExec_t)n->ft_gexec, gs));
+    LEMO_CUDA(cudaEventRecord((cudaEvent_t)n->ft_ev_out, gs));
+    LEMO_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)n->ft_ev_out, 0));
+    return 0;
 }
 
 int lemo_ae_forward(LemoConvNet* h, const float* x, int32_t N, float* rec, float* z, void* stream) {

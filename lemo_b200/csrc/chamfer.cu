@@ -88,11 +88,9 @@ int chamfer_nn_launch(const float* q, long long q_bs, int nq, const float* t, lo
 }
 
 // ---------------------------------------------------------------------------------------------- static scene, tiled + pruned
-// One warp per query.  Pass 1: every lane computes the squared distance from the query to the boxes of its tiles (lower bound of
-// every point inside); the tile with the smallest bound is scanned first, which gives a near-optimal `best`.  Pass 2: every tile
-// whose bound (shrunk by 0.1 % so that fp32 rounding can never hide an equal-distance point) does not exceed `best` is scanned, 4
-// points per lane; (distance, original index) pairs are compared lexicographically, so the result is the brute-force scan's
-// first minimum.
+// One warp per query; a tile (128 points) is scanned 4 points per lane with the pinned distance arithmetic of k_chamfer_nn, and
+// (distance, original index) pairs are compared lexicographically, so the result is the brute-force scan's first minimum.
+// A box bound is shrunk by 0.1 % before it is compared with `best`, so fp32 rounding can never hide an equal-distance point.
 __device__ __forceinline__ void sg_scan_tile(const float4* __restrict__ tp, float qx, float qy, float qz, float& best, int& bi) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -112,55 +110,67 @@ __device__ __forceinline__ void sg_warp_min(float& best, int& bi) {
         if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
     }
 }
-__global__ void __launch_bounds__(256) k_scene_query(const float4* __restrict__ pts, const float* __restrict__ box, int ntile,
-                                                     const float* __restrict__ q, long long q_bs, int nq, int B, float* __restrict__ dist,
-                                                     int* __restrict__ idx) {
+__device__ __forceinline__ float sg_box_lb(const float4* __restrict__ b, float qx, float qy, float qz) {
+    const float4 lo = __ldg(b), hi = __ldg(b + 1);
+    const float ex = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f), ey = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f),
+                ez = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
+    return ex * ex + ey * ey + ez * ez;
+}
+__device__ __forceinline__ void sg_warp_argmin(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+// Two-level search, one warp per query.  Groups of 32 Morton-adjacent tiles carry their own box, so a query touches
+// ngroup + 32 * (groups that can still matter) boxes instead of every tile box.
+//   pass 1: nearest group box -> its nearest tile box -> scan that tile: a near-optimal `best`;
+//   pass 2: every group whose box bound (shrunk by 0.1 %) does not exceed `best` is opened (one lane per tile), and every tile whose
+//           bound does not exceed `best` is scanned.  Bounds only ever prune boxes that cannot hold a point at distance <= best,
+//           and (distance, original index) pairs are compared lexicographically: the result is the brute-force first minimum.
+__global__ void __launch_bounds__(256) k_scene_query(const float4* __restrict__ pts, const float4* __restrict__ box, const float4* __restrict__ gbox,
+                                                     int ntile, int ngroup, const float* __restrict__ q, long long q_bs, int nq, int B,
+                                                     float* __restrict__ dist, int* __restrict__ idx) {
     const int lane = threadIdx.x & 31;
     const long long wq = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wq >= (long long)B * nq) return;
     const int b = (int)(wq / nq), i = (int)(wq - (long long)b * nq);
     const float* qp = q + (size_t)b * q_bs + (size_t)i * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
-    // pass 1: nearest box
-    float lmin = 3.4e38f;
-    int tmin = 0;
-    for (int t = lane; t < ntile; t += 32) {
-        const float* bx = box + (size_t)t * 6;
-        const float ex = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.f), ey = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.f),
-                    ez = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.f);
-        const float lb = ex * ex + ey * ey + ez * ez;
-        if (lb < lmin) { lmin = lb; tmin = t; }
+    // ---- pass 1
+    float gmin = 3.4e38f;
+    int gsel = 0;
+    for (int g = lane; g < ngroup; g += 32) {
+        const float lb = sg_box_lb(gbox + 2 * (size_t)g, qx, qy, qz);
+        if (lb < gmin) { gmin = lb; gsel = g; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ol = __shfl_xor_sync(0xffffffffu, lmin, o);
-        const int ot = __shfl_xor_sync(0xffffffffu, tmin, o);
-        if (ol < lmin || (ol == lmin && ot < tmin)) { lmin = ol; tmin = ot; }
-    }
+    sg_warp_argmin(gmin, gsel);
+    float tl = sg_box_lb(box + 2 * ((size_t)gsel * SG_GROUP + lane), qx, qy, qz);
+    int tsel = gsel * SG_GROUP + lane;
+    sg_warp_argmin(tl, tsel);
     float best = 3.4e38f;
     int bi = 0x7fffffff;
-    sg_scan_tile(pts + (size_t)tmin * SG_TILE, qx, qy, qz, best, bi);
+    sg_scan_tile(pts + (size_t)tsel * SG_TILE, qx, qy, qz, best, bi);
     sg_warp_min(best, bi);
-    // pass 2: every tile that can still hold a point at distance <= best
-    for (int t0 = 0; t0 < ntile; t0 += 32) {
-        const int t = t0 + lane;
-        bool need = false;
-        if (t < ntile && t != tmin) {
-            const float* bx = box + (size_t)t * 6;
-            const float ex = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.f), ey = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.f),
-                        ez = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.f);
-            need = (ex * ex + ey * ey + ez * ez) * 0.999f <= best;
-        }
-        unsigned m = __ballot_sync(0xffffffffu, need);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            float tb = best;
-            int ti = bi;
-            sg_scan_tile(pts + (size_t)(t0 + l) * SG_TILE, qx, qy, qz, tb, ti);
-            sg_warp_min(tb, ti);
-            best = tb; bi = ti;
-            // boxes already flagged stay flagged (a smaller `best` only makes the remaining scans redundant, never wrong)
+    // ---- pass 2
+    for (int g0 = 0; g0 < ngroup; g0 += 32) {
+        const int g = g0 + lane;
+        const bool gneed = g < ngroup && sg_box_lb(gbox + 2 * (size_t)g, qx, qy, qz) * 0.999f <= best;
+        unsigned gm = __ballot_sync(0xffffffffu, gneed);
+        while (gm) {
+            const int gl = g0 + __ffs(gm) - 1;
+            gm &= gm - 1;
+            const int t = gl * SG_GROUP + lane;
+            const bool need = t != tsel && sg_box_lb(box + 2 * (size_t)t, qx, qy, qz) * 0.999f <= best;
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                sg_scan_tile(pts + (size_t)(gl * SG_GROUP + l) * SG_TILE, qx, qy, qz, best, bi);
+                sg_warp_min(best, bi);
+            }
         }
     }
     if (lane == 0) { dist[wq] = best; idx[wq] = bi; }
@@ -194,8 +204,11 @@ int scene_grid_create(const float* scene_dev, int n, SceneGrid** out) {
     }
     std::sort(key.begin(), key.end());
     const int ntile = (n + SG_TILE - 1) / SG_TILE;
+    const int ngroup = (ntile + SG_GROUP - 1) / SG_GROUP;
     std::vector<float4> pts((size_t)ntile * SG_TILE);
-    std::vector<float> box((size_t)ntile * 6);
+    const float4 far_lo = make_float4(1e18f, 1e18f, 1e18f, 0.f), far_hi = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    std::vector<float4> box((size_t)ngroup * SG_GROUP * 2), gbox((size_t)ngroup * 2);
+    for (size_t t = 0; t < (size_t)ngroup * SG_GROUP; ++t) { box[2 * t] = far_lo; box[2 * t + 1] = far_hi; }   // padding tiles: never needed
     for (int t = 0; t < ntile; ++t) {
         float bl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, bh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
         for (int k = 0; k < SG_TILE; ++k) {
@@ -215,29 +228,41 @@ int scene_grid_create(const float* scene_dev, int n, SceneGrid** out) {
             }
             pts[s] = p;
         }
-        for (int a = 0; a < 3; ++a) { box[(size_t)t * 6 + a] = bl[a]; box[(size_t)t * 6 + 3 + a] = bh[a]; }
+        box[2 * (size_t)t] = make_float4(bl[0], bl[1], bl[2], 0.f);
+        box[2 * (size_t)t + 1] = make_float4(bh[0], bh[1], bh[2], 0.f);
+    }
+    for (int g = 0; g < ngroup; ++g) {
+        float4 lo4 = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 0.f), hi4 = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, 0.f);
+        for (int t = g * SG_GROUP; t < std::min(ntile, (g + 1) * SG_GROUP); ++t) {
+            lo4.x = std::min(lo4.x, box[2 * (size_t)t].x); lo4.y = std::min(lo4.y, box[2 * (size_t)t].y); lo4.z = std::min(lo4.z, box[2 * (size_t)t].z);
+            hi4.x = std::max(hi4.x, box[2 * (size_t)t + 1].x); hi4.y = std::max(hi4.y, box[2 * (size_t)t + 1].y);
+            hi4.z = std::max(hi4.z, box[2 * (size_t)t + 1].z);
+        }
+        gbox[2 * (size_t)g] = lo4; gbox[2 * (size_t)g + 1] = hi4;
     }
     SceneGrid* g = new SceneGrid();
-    g->n = n; g->ntile = ntile;
+    g->n = n; g->ntile = ntile; g->ngroup = ngroup;
     cudaGetDevice(&g->device);
     LEMO_CUDA(cudaMalloc((void**)&g->pts, pts.size() * sizeof(float4)));
-    LEMO_CUDA(cudaMalloc((void**)&g->box, box.size() * sizeof(float)));
+    LEMO_CUDA(cudaMalloc((void**)&g->box, box.size() * sizeof(float4)));
+    LEMO_CUDA(cudaMalloc((void**)&g->gbox, gbox.size() * sizeof(float4)));
     LEMO_CUDA(cudaMemcpy(g->pts, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    LEMO_CUDA(cudaMemcpy(g->box, box.data(), box.size() * sizeof(float), cudaMemcpyHostToDevice));
+    LEMO_CUDA(cudaMemcpy(g->box, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    LEMO_CUDA(cudaMemcpy(g->gbox, gbox.data(), gbox.size() * sizeof(float4), cudaMemcpyHostToDevice));
     *out = g;
     return 0;
 }
 
 void scene_grid_free(SceneGrid* g) {
     if (!g) return;
-    cudaFree(g->pts); cudaFree(g->box);
+    cudaFree(g->pts); cudaFree(g->box); cudaFree(g->gbox);
     delete g;
 }
 
 int scene_grid_query(const SceneGrid* g, const float* q, long long q_bs, int nq, int B, float* dist, int* idx, cudaStream_t st) {
     LEMO_CHECK(g && q && dist && idx && nq > 0 && B > 0, "bad arguments");
     const long long threads = (long long)B * nq * 32;
-    k_scene_query<<<cdiv(threads, 256), 256, 0, st>>>(g->pts, g->box, g->ntile, q, q_bs, nq, B, dist, idx);
+    k_scene_query<<<cdiv(threads, 256), 256, 0, st>>>(g->pts, g->box, g->gbox, g->ntile, g->ngroup, q, q_bs, nq, B, dist, idx);
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }

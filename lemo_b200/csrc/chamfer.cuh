@@ -12,11 +12,13 @@ int chamfer_nn_launch(const float* q, long long q_bs, int nq, const float* t, lo
 // into tiles of SG_TILE with an axis-aligned box per tile; a query scans only the tiles whose box can still contain a closer (or
 // equally close, lower-index) point.  Results are IDENTICAL to the brute-force scan -- same pinned distance arithmetic, same
 // first-minimum rule -- at a few percent of its pair evaluations.
-constexpr int SG_TILE = 128;
+constexpr int SG_TILE = 128;    // points per tile
+constexpr int SG_GROUP = 32;    // consecutive (Morton-adjacent) tiles per group: one lane per tile when a group is opened
 struct SceneGrid {
-    int device = 0, n = 0, ntile = 0;
+    int device = 0, n = 0, ntile = 0, ngroup = 0;
     float4* pts = nullptr;     // [ntile*SG_TILE]  x, y, z, original index (int bits); padding = far away
-    float* box = nullptr;      // [ntile][6]       min xyz, max xyz
+    float4* box = nullptr;     // [ntile pad SG_GROUP][2]   (min xyz, _), (max xyz, _); padding tiles = empty boxes far away
+    float4* gbox = nullptr;    // [ngroup][2]      box of the group's tiles
 };
 int scene_grid_create(const float* scene_dev, int n, SceneGrid** out);      // synchronises (create time only)
 void scene_grid_free(SceneGrid* g);

@@ -33,14 +33,18 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ in, const float* __restrict__ wk,
                                                      const float* __restrict__ bias, const float* __restrict__ aux,
                                                      float* __restrict__ out, int Cin, int Cout, int H, int W, int Wp, int PS,
-                                                     int SW, int epi) {
+                                                     int SW, int epi, int KS, int cps, int Nn) {
+    // KS > 1: blockIdx.z = n * KS + ks; this CTA contracts input channels [ks*cps, (ks+1)*cps) only and stores its RAW partial sums
+    // into out = scratch[ks][n][oc][q]; k_conv_splitk_finish adds the slices in order and applies the epilogue (deterministic).
+    // Small feature maps (the deep AE levels: 16x16 planes, 256 channels) would otherwise run on 4-30 CTAs.
     constexpr int OCB = NW * 8, NT = NW * 32;
     extern __shared__ __align__(16) float smem[];
     const int stage_floats = CT * SW + CT * 9 * OCB;    // one pipeline stage: input halo tile [CT][SW] + weights [CT][9][OCB]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = blockIdx.z, ocb0 = blockIdx.y * OCB;
+    const int n = blockIdx.z / KS, ks = blockIdx.z - n * KS, ocb0 = blockIdx.y * OCB;
     const int q0 = Wp + blockIdx.x * TP;
     const float* in_n = in + (size_t)n * Cin * PS;
+    const int ic_lo = ks * cps, ic_hi = min(Cin, ic_lo + cps);
 
     float acc[8][8];
 #pragma unroll
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
     auto issue_stage = [&](int ic0, float* st) {
         float* s_in = st;
         float* s_w = st + CT * SW;
-        const int nic = min(CT, Cin - ic0);
+        const int nic = min(CT, ic_hi - ic0);
         for (int ic = 0; ic < nic; ++ic) {
             const float* src = in_n + (size_t)(ic0 + ic) * PS;
             for (int e = tid; e < SW; e += NT) {
@@ -70,16 +74,16 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
         cp_async_commit();
     };
 
-    const int ntiles = (Cin + CT - 1) / CT;
-    issue_stage(0, smem);
+    const int ntiles = (ic_hi - ic_lo + CT - 1) / CT;
+    issue_stage(ic_lo, smem);
     for (int it = 0; it < ntiles; ++it) {
         float* st = smem + (it & 1) * stage_floats;
-        if (it + 1 < ntiles) { issue_stage((it + 1) * CT, smem + ((it + 1) & 1) * stage_floats); cp_async_wait<1>(); }
+        if (it + 1 < ntiles) { issue_stage(ic_lo + (it + 1) * CT, smem + ((it + 1) & 1) * stage_floats); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
         const float* s_in = st;
         const float* s_w = st + CT * SW;
-        const int nic = min(CT, Cin - it * CT);
+        const int nic = min(CT, ic_hi - ic_lo - it * CT);
         for (int ic = 0; ic < nic; ++ic) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -111,6 +115,19 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
 
     const int qend = (H + 1) * Wp;
     const size_t obase = ((size_t)n * Cout + ocb0 + warp * 8) * PS;
+    if (KS > 1) {                                        // raw partials; epilogue in k_conv_splitk_finish
+        const size_t pbase = (((size_t)ks * Nn + n) * Cout + ocb0 + warp * 8) * PS;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int q = q0 + half * 128 + 4 * lane;
+            if (q >= qend) continue;
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                *reinterpret_cast<float4*>(out + pbase + (size_t)o * PS + q) =
+                    make_float4(acc[o][half * 4], acc[o][half * 4 + 1], acc[o][half * 4 + 2], acc[o][half * 4 + 3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int q = q0 + half * 128 + 4 * lane;
@@ -138,6 +155,27 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
             *reinterpret_cast<float4*>(out + obase + (size_t)o * PS + q) = r;
         }
     }
+}
+
+// out[n][oc][q] = epi( sum_ks partial[ks][n][oc][q] ) on the interior rows; the slices are added in slice order (bitwise reproducible)
+__global__ void __launch_bounds__(256) k_conv_splitk_finish(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                            const float* __restrict__ aux, float* __restrict__ out, int KS, int N, int Cout,
+                                                            int H, int W, int Wp, int PS, int epi) {
+    const int span = H * Wp;                               // linear range [Wp, (H+1) Wp)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * Cout * span) return;
+    const int q = Wp + (int)(i % span);
+    const long long c = i / span;                           // n * Cout + oc
+    const int oc = (int)(c % Cout);
+    const size_t o = (size_t)c * PS + q;
+    const size_t slice = (size_t)N * Cout * PS;
+    float v = 0.f;
+    for (int ks = 0; ks < KS; ++ks) v += partial[(size_t)ks * slice + o];
+    if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) v += __ldg(bias + oc);
+    if (epi == EPI_BIAS_LRELU) v = lrelu(v);
+    else if (epi == EPI_MASK) v *= aux[o] > 0.f ? 1.f : 0.2f;
+    const int col = q % Wp;
+    out[o] = (col >= 1 && col <= W) ? v : 0.f;
 }
 
 // few output channels (the 32->1 input-gradient layer of Enc, AE's 32->1 / 1->1 output layers): thread per pixel
@@ -177,9 +215,22 @@ __global__ void __launch_bounds__(256) k_conv3x3_small(const float* __restrict__
     }
 }
 
+// split-K factor for a layer: enough CTAs for ~2 per SM, slices of whole 8-channel stages
+int conv3x3_splitk(int N, int Cin, int Cout, const PlaneGeom& g) {
+    if (Cout % 32 != 0) return 1;
+    const int ocb = (Cout % 64 == 0) ? 64 : 32;
+    const long long ctas = (long long)cdiv((long long)g.H * g.Wp, TP) * (Cout / ocb) * N;
+    if (ctas >= 148 || Cin < 2 * CT) return 1;
+    return (int)std::max(1LL, std::min<long long>(Cin / CT, (296 + ctas - 1) / ctas));
+}
+size_t conv3x3_splitk_floats(int N, int Cin, int Cout, const PlaneGeom& g) {
+    const int ks = conv3x3_splitk(N, Cin, Cout, g);
+    return ks > 1 ? (size_t)ks * N * Cout * g.PS : 0;
+}
+
 template <int NW>
 static int conv_main_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out, int N, int Cin,
-                            int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st) {
+                            int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st, float* scratch, size_t scratch_floats) {
     const int SW = (TP + 2 * g.Wp + 2 + 3) / 4 * 4;
     const size_t smem = 2 * (size_t)(CT * SW + CT * 9 * NW * 8) * sizeof(float);      // two pipeline stages
     static size_t configured = 0;             // one process per GPU: a per-process cache is enough
@@ -187,16 +238,27 @@ static int conv_main_launch(const float* in, const float* wk, const float* bias,
         LEMO_CUDA(cudaFuncSetAttribute(k_conv3x3<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(cdiv((long long)g.H * g.Wp, TP), Cout / (NW * 8), N);
-    k_conv3x3<NW><<<grid, NW * 32, smem, st>>>(in, wk, bias, aux, out, Cin, Cout, g.H, g.W, g.Wp, g.PS, SW, (int)epi);
+    int KS = scratch ? conv3x3_splitk(N, Cin, Cout, g) : 1;
+    if (KS > 1 && (size_t)KS * N * Cout * g.PS > scratch_floats) KS = 1;
+    if (KS > 1) {
+        const int cps = cdiv(cdiv(Cin, KS), CT) * CT;             // channels per slice, whole stages
+        KS = cdiv(Cin, cps);
+        dim3 grid(cdiv((long long)g.H * g.Wp, TP), Cout / (NW * 8), N * KS);
+        k_conv3x3<NW><<<grid, NW * 32, smem, st>>>(in, wk, bias, aux, scratch, Cin, Cout, g.H, g.W, g.Wp, g.PS, SW, (int)epi, KS, cps, N);
+        const long long tot = (long long)N * Cout * g.H * g.Wp;
+        k_conv_splitk_finish<<<cdiv(tot, 256), 256, 0, st>>>(scratch, bias, aux, out, KS, N, Cout, g.H, g.W, g.Wp, g.PS, (int)epi);
+    } else {
+        dim3 grid(cdiv((long long)g.H * g.Wp, TP), Cout / (NW * 8), N);
+        k_conv3x3<NW><<<grid, NW * 32, smem, st>>>(in, wk, bias, aux, out, Cin, Cout, g.H, g.W, g.Wp, g.PS, SW, (int)epi, 1, Cin, N);
+    }
     LEMO_CUDA(cudaGetLastError());
     return 0;
 }
 
 int conv3x3_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out, int N, int Cin, int Cout,
-                   const PlaneGeom& g, ConvEpi epi, cudaStream_t st) {
-    if (Cout % 64 == 0) return conv_main_launch<8>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st);
-    if (Cout % 32 == 0) return conv_main_launch<4>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st);
+                   const PlaneGeom& g, ConvEpi epi, cudaStream_t st, float* scratch, size_t scratch_floats) {
+    if (Cout % 64 == 0) return conv_main_launch<8>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st, scratch, scratch_floats);
+    if (Cout % 32 == 0) return conv_main_launch<4>(in, wk, bias, aux, out, N, Cin, Cout, g, epi, st, scratch, scratch_floats);
     dim3 grid(cdiv((long long)g.H * g.Wp, 256), 1, N);
     if (Cout == 1) k_conv3x3_small<1><<<grid, 256, 0, st>>>(in, wk, bias, aux, out, Cin, g.H, g.W, g.Wp, g.PS, (int)epi);
     else if (Cout == 4) k_conv3x3_small<4><<<grid, 256, 0, st>>>(in, wk, bias, aux, out, Cin, g.H, g.W, g.Wp, g.PS, (int)epi);
@@ -332,7 +394,10 @@ void convnet_free(ConvNet* n) {
     if (!n) return;
     cudaSetDevice(n->device);
     if (n->tc) enc_tc_free(n);
-    cudaFree(n->w_flat); cudaFree(n->d_wflat);
+    cudaFree(n->w_flat); cudaFree(n->d_wflat); cudaFree(n->sk_scratch); cudaFree(n->wg_scratch); cudaFree(n->ft_sched);
+    if (n->ft_gexec) cudaGraphExecDestroy((cudaGraphExec_t)n->ft_gexec);
+    if (n->ft_graph) cudaGraphDestroy((cudaGraph_t)n->ft_graph);
+    if (n->ft_stream) { cudaStreamDestroy((cudaStream_t)n->ft_stream); cudaEventDestroy((cudaEvent_t)n->ft_ev_in); cudaEventDestroy((cudaEvent_t)n->ft_ev_out); }
     for (auto& L : n->layers) { cudaFree(L.wk_f); cudaFree(L.wk_b); }
     for (auto p : n->act) cudaFree(p);
     for (auto p : n->grad) cudaFree(p);

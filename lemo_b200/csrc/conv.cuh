@@ -24,11 +24,18 @@ inline PlaneGeom make_geom(int H, int W) {
 enum ConvEpi { EPI_BIAS_LRELU = 0, EPI_MASK = 1, EPI_BIAS = 2, EPI_NONE = 3 };
 
 // out[n][oc] = epi( sum_ic in[n][ic] (*) wk[ic][ky][kx][oc] ),  wk is [Cin][9][Cout] (oc fastest)
+// scratch (optional): split-K workspace of >= conv3x3_splitk_floats(...) floats; with it, layers whose plane is too small to fill the
+// GPU are contracted in input-channel slices by separate CTAs and summed in slice order by a second kernel (deterministic).
 int conv3x3_launch(const float* in, const float* wk, const float* bias, const float* aux, float* out,
-                   int N, int Cin, int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st);
+                   int N, int Cin, int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st, float* scratch = nullptr,
+                   size_t scratch_floats = 0);
+int conv3x3_splitk(int N, int Cin, int Cout, const PlaneGeom& g);
+size_t conv3x3_splitk_floats(int N, int Cin, int Cout, const PlaneGeom& g);
 // dW[oc][ic][ky][kx] (+)= sum_{n,pix} dpre[n][oc][q] * in[n][ic][q + shift];  db[oc] (+)= sum dpre
+// scratch: >= conv3x3_wgrad_floats(...) floats of partials (fixed-order reduction; dW / db are overwritten, not accumulated)
 int conv3x3_wgrad_launch(const float* in, const float* dpre, float* dW_oikk, float* db, int N, int Cin, int Cout,
-                         const PlaneGeom& g, bool transpose_io, cudaStream_t st);
+                         const PlaneGeom& g, bool transpose_io, cudaStream_t st, float* scratch, size_t scratch_floats);
+size_t conv3x3_wgrad_floats(int N, int Cin, int Cout, const PlaneGeom& g);
 
 int pack_planes(const float* dense, float* planes, int NC, const PlaneGeom& g, cudaStream_t st);
 int unpack_planes(const float* planes, float* dense, int NC, const PlaneGeom& g, cudaStream_t st);
@@ -56,6 +63,15 @@ struct ConvNet {
     std::vector<int*> pool_idx;        // AE: argmax indices
     std::vector<float*> up;            // AE: zero-upsampled planes
     float* d_wflat = nullptr;
+    float* sk_scratch = nullptr;       // split-K workspace of the small-plane layers (AE)
+    size_t sk_floats = 0;
+    float* wg_scratch = nullptr;       // weight-gradient partials (fixed-order reduction instead of float atomics)
+    size_t wg_floats = 0;
+    // fine-tune driver (lemo_ae_finetune_run): device-side step schedule + one captured step
+    void *ft_sched = nullptr, *ft_graph = nullptr, *ft_gexec = nullptr, *ft_stream = nullptr, *ft_ev_in = nullptr, *ft_ev_out = nullptr;
+    const void *ft_x = nullptr, *ft_mask = nullptr;
+    float* ft_losses = nullptr;
+    int ft_N = 0, ft_rows = 0;
     long long launches = 0;
     void* tc = nullptr;                // EncTC (conv_tc.cu): tensor-core path state, kind 0 only
 };

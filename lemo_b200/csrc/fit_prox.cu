@@ -8,8 +8,9 @@
 // direction: the loss never reads dist2), Enc smoothness prior on the world markers, the first-15 % gradient erase (:281-288)
 // and Adam.  No host synchronisation (the reference has ~14 .item() per step); loss weights, learning rate and the erase
 // count live in device memory so that one iteration is ONE replayable CUDA graph across optimisation stages.
-// Every reduction has a fixed order (per-CTA partials summed by one CTA; gather-style adjoints instead of float atomics),
-// so a window is bitwise reproducible.
+// The loss reductions and the term adjoints of this file have a fixed order (per-CTA partials summed by one CTA; gather-style
+// adjoints instead of float atomics).  The full-mesh body adjoint (body.cu: several CTAs per frame combine dA / dX partials with
+// atomicAdd) is order dependent, so two runs of a window agree to rounding (~1e-6), not bit for bit.
 #include "common.cuh"
 #include "body.cuh"
 #include "vposer.cuh"
@@ -61,7 +62,7 @@ struct ProxFit {
     float *Wrows = nullptr, *Grows = nullptr, *sdf_fric = nullptr;
     float *cdist = nullptr; int* cidx = nullptr;
     float *xin = nullptr, *gx = nullptr, *gv = nullptr, *canon = nullptr, *stats = nullptr;
-    float *part = nullptr, *losses = nullptr;
+    float *part = nullptr, *losses = nullptr, *fpart = nullptr;
     ProxDev* dev = nullptr;
     Sched* sched = nullptr;
     SceneGrid* sgrid = nullptr;              // uniform grid over the scene points (exact NN, chamfer.cu)
@@ -158,14 +159,15 @@ __global__ void k_prox_rows(const float* __restrict__ verts, int B, int V, const
 
 // friction (fitting_temp_slide.py:699-739), scene normal = +z: among the (frame, vertex) pairs with sdf < 0.01,
 //   tangent: mean |v_xy| over those with |v_xy| > 1e-4   * w_t ;  normal: mean |v_z| over those with v_z < 0   * w_n
-// One CTA: pass 1 counts / sums, pass 2 writes the world-row gradient gather-style (row b gets + from velocity b-1 and - from b).
-__global__ void __launch_bounds__(1024) k_prox_friction(const float* __restrict__ Wrows, const float* __restrict__ sdf_fric, int B, int NRW, int off,
-                                                        int nf, const ProxDev* __restrict__ dv, float* __restrict__ Grows, float* __restrict__ part) {
+// Pass 1 (FR_G CTAs): counts / sums as per-CTA partials.  Pass 2: every CTA adds the partials in CTA order (fixed order: bitwise
+// reproducible) and writes the world-row gradient gather-style (row b gets + from velocity b-1 and - from velocity b: no atomics).
+constexpr int FR_G = 32;
+__global__ void __launch_bounds__(256) k_prox_fric_count(const float* __restrict__ Wrows, const float* __restrict__ sdf_fric, int B, int NRW, int off,
+                                                         int nf, float* __restrict__ fpart /*[4][FR_G]*/) {
     __shared__ float sred[32];
-    __shared__ float s_val[4];
     float ct = 0.f, st = 0.f, cn = 0.f, sn = 0.f;
     const int n = (B - 1) * nf;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int b = i / nf, r = i - b * nf;
         if (!(sdf_fric[(size_t)b * nf + r] < 0.01f)) continue;
         const float* a0 = Wrows + ((size_t)b * NRW + off + r) * 3;
@@ -175,36 +177,46 @@ __global__ void __launch_bounds__(1024) k_prox_friction(const float* __restrict_
         if (vt > 1e-4f) { ct += 1.f; st += vt; }
         if (vz < 0.f) { cn += 1.f; sn -= vz; }
     }
-    ct = block_sum(ct, sred); if (threadIdx.x == 0) s_val[0] = ct;
-    st = block_sum(st, sred); if (threadIdx.x == 0) s_val[1] = st;
-    cn = block_sum(cn, sred); if (threadIdx.x == 0) s_val[2] = cn;
-    sn = block_sum(sn, sred); if (threadIdx.x == 0) s_val[3] = sn;
+    ct = block_sum(ct, sred); if (threadIdx.x == 0) fpart[0 * FR_G + blockIdx.x] = ct;
+    st = block_sum(st, sred); if (threadIdx.x == 0) fpart[1 * FR_G + blockIdx.x] = st;
+    cn = block_sum(cn, sred); if (threadIdx.x == 0) fpart[2 * FR_G + blockIdx.x] = cn;
+    sn = block_sum(sn, sred); if (threadIdx.x == 0) fpart[3 * FR_G + blockIdx.x] = sn;
+}
+__global__ void __launch_bounds__(256) k_prox_fric_grad(const float* __restrict__ Wrows, const float* __restrict__ sdf_fric, int B, int NRW, int off,
+                                                        int nf, const float* __restrict__ fpart, const ProxDev* __restrict__ dv,
+                                                        float* __restrict__ Grows, float* __restrict__ part) {
+    __shared__ float s_val[4];
+    if (threadIdx.x < 4) {
+        float a = 0.f;
+        for (int g = 0; g < FR_G; ++g) a += fpart[threadIdx.x * FR_G + g];
+        s_val[threadIdx.x] = a;
+    }
     __syncthreads();
     const float wt = dv->w.friction_tangent_weight, wn = dv->w.friction_normal_weight;
     const float it = s_val[0] >= 1.f ? wt / s_val[0] : 0.f, in = s_val[2] >= 1.f ? wn / s_val[2] : 0.f;
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         part[PT_FRIC_T * PARTS] = s_val[0] >= 1.f ? wt * s_val[1] / s_val[0] : 0.f;
         part[PT_FRIC_N * PARTS] = s_val[2] >= 1.f ? wn * s_val[3] / s_val[2] : 0.f;
     }
-    for (int i = threadIdx.x; i < B * nf; i += blockDim.x) {
-        const int b = i / nf, r = i - b * nf;
-        float gsum[3] = {0.f, 0.f, 0.f};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nf) return;
+    const int b = i / nf, r = i - b * nf;
+    float gsum[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {                     // e = 0: velocity b-1 (this row is its head, +) ; e = 1: velocity b (tail, -)
-            const int vb = b - 1 + e;
-            if (vb < 0 || vb > B - 2) continue;
-            if (!(sdf_fric[(size_t)vb * nf + r] < 0.01f)) continue;
-            const float* a0 = Wrows + ((size_t)vb * NRW + off + r) * 3;
-            const float* a1 = Wrows + ((size_t)(vb + 1) * NRW + off + r) * 3;
-            const float vx = a1[0] - a0[0], vy = a1[1] - a0[1], vz = a1[2] - a0[2];
-            const float vt = sqrtf(vx * vx + vy * vy);
-            const float sg = e == 0 ? 1.f : -1.f;
-            if (vt > 1e-4f) { gsum[0] += sg * it * vx / vt; gsum[1] += sg * it * vy / vt; }
-            if (vz < 0.f) gsum[2] -= sg * in;
-        }
-        float* o = Grows + ((size_t)b * NRW + off + r) * 3;
-        o[0] = gsum[0]; o[1] = gsum[1]; o[2] = gsum[2];
+    for (int e = 0; e < 2; ++e) {                     // e = 0: velocity b-1 (this row is its head, +) ; e = 1: velocity b (tail, -)
+        const int vb = b - 1 + e;
+        if (vb < 0 || vb > B - 2) continue;
+        if (!(sdf_fric[(size_t)vb * nf + r] < 0.01f)) continue;
+        const float* a0 = Wrows + ((size_t)vb * NRW + off + r) * 3;
+        const float* a1 = Wrows + ((size_t)(vb + 1) * NRW + off + r) * 3;
+        const float vx = a1[0] - a0[0], vy = a1[1] - a0[1], vz = a1[2] - a0[2];
+        const float vt = sqrtf(vx * vx + vy * vy);
+        const float sg = e == 0 ? 1.f : -1.f;
+        if (vt > 1e-4f) { gsum[0] += sg * it * vx / vt; gsum[1] += sg * it * vy / vt; }
+        if (vz < 0.f) gsum[2] -= sg * in;
     }
+    float* o = Grows + ((size_t)b * NRW + off + r) * 3;
+    o[0] = gsum[0]; o[1] = gsum[1]; o[2] = gsum[2];
 }
 
 // contact (fitting_temp_slide.py:743-753): d = squared distance to the nearest scene point; loss = w * mean(r / (r + 1)), r = sqrt(d + 1e-4)
@@ -365,7 +377,9 @@ static int prox_iteration(ProxFit* f, bool with_adam, cudaStream_t st) {
     k_prox_rows<<<cdiv(B * NRW, 128), 128, 0, st>>>(f->verts, B, V, f->row_ids, NRW, f->off_fric, f->has_fric ? f->n_fric : 0, f->c2w,
                                                      f->has_fric ? f->sdf : nullptr, f->grid, f->Wrows, f->sdf_fric); nl++;
     if (f->has_fric) {
-        k_prox_friction<<<1, 1024, 0, st>>>(f->Wrows, f->sdf_fric, B, NRW, f->off_fric, f->n_fric, f->dev, f->Grows, f->part); nl++;
+        k_prox_fric_count<<<FR_G, 256, 0, st>>>(f->Wrows, f->sdf_fric, B, NRW, f->off_fric, f->n_fric, f->fpart); nl++;
+        k_prox_fric_grad<<<cdiv(B * f->n_fric, 256), 256, 0, st>>>(f->Wrows, f->sdf_fric, B, NRW, f->off_fric, f->n_fric, f->fpart, f->dev,
+                                                                    f->Grows, f->part); nl++;
         pc.n[PT_FRIC_T] = pc.n[PT_FRIC_N] = 1;
     }
     if (f->has_contact) {
@@ -507,7 +521,7 @@ int lemo_fit_prox_create(const LemoModel* model, LemoVPoser* vposer, LemoConvNet
     LEMO_TRY(dalloc(&f->Wrows, Bz * f->NRW * 3)); LEMO_TRY(dalloc(&f->Grows, Bz * f->NRW * 3));
     LEMO_TRY(dalloc(&f->sdf_fric, Bz * std::max(1, f->n_fric)));
     LEMO_TRY(dalloc(&f->cdist, Bz * std::max(1, f->n_contact))); LEMO_TRY(dalloc(&f->cidx, Bz * std::max(1, f->n_contact)));
-    LEMO_TRY(dalloc(&f->part, (size_t)PT_N * PARTS)); LEMO_TRY(dalloc(&f->losses, PT_N));
+    LEMO_TRY(dalloc(&f->part, (size_t)PT_N * PARTS)); LEMO_TRY(dalloc(&f->losses, PT_N)); LEMO_TRY(dalloc(&f->fpart, 4 * FR_G));
     LEMO_TRY(dalloc(&f->dev, 1)); LEMO_TRY(dalloc(&f->sched, 1));
     LEMO_TRY(dalloc(&f->canon, 12)); LEMO_TRY(dalloc(&f->stats, 486));
     if (f->has_smooth) {
@@ -532,7 +546,7 @@ int lemo_fit_prox_destroy(LemoProxFit* h) {
     prox_drop_graph(f);
     if (f->gstream) { cudaStreamDestroy(f->gstream); cudaEventDestroy(f->ev_in); cudaEventDestroy(f->ev_out); }
     float* ps[] = {f->P, f->Gp, f->M1, f->M2, f->betas, f->gt, f->conf, f->jw, f->Rb, f->dRb, f->verts, f->joints, f->d_joints, f->Wrows, f->Grows,
-                   f->sdf_fric, f->cdist, f->xin, f->gx, f->gv, f->canon, f->stats, f->part, f->losses};
+                   f->sdf_fric, f->cdist, f->xin, f->gx, f->gv, f->canon, f->stats, f->part, f->losses, f->fpart};
     for (float* p : ps) cudaFree(p);
     int* is[] = {f->row_ids, f->uniq_ids, f->uniq_off, f->uniq_rows, f->inv_off, f->inv_idx, f->cidx};
     for (int* p : is) cudaFree(p);

@@ -91,6 +91,15 @@ using namespace lemo;
 extern "C" {
 const char* lemo_last_error(void) { return lemo::g_err.c_str(); }
 int lemo_version(void) { return 100; }
+// debugging aid (LEMO_DEBUG_CHECK=1 in the Python loader): synchronise and report-and-clear the runtime's sticky error state, so a
+// failing asynchronous launch or an unchecked API call is attributed to the C-ABI call that caused it
+int lemo_debug_check(void) {
+    const cudaError_t a = cudaDeviceSynchronize();
+    const cudaError_t b = cudaGetLastError();
+    const cudaError_t e = a != cudaSuccess ? a : b;
+    if (e != cudaSuccess) lemo::set_error(std::string("CUDA error state: ") + cudaGetErrorString(e));
+    return (int)e;
+}
 
 int lemo_rot6d_to_rotmat(const float* x6, int32_t n, float* R, void* stream) { EW(k_gs6d, n, x6, n, R); }
 int lemo_rot6d_to_rotmat_backward(const float* x6, const float* dR, int32_t n, float* dx6, void* stream) { EW(k_gs6d_bwd, n, x6, dR, n, dx6); }

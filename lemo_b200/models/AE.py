@@ -118,10 +118,16 @@ class AE(nn.Module):
         mask = torch.zeros(H, device=x.device)
         rows = row_ids.to(x.device).long() if torch.is_tensor(row_ids) else torch.as_tensor(np.asarray(row_ids), device=x.device).long()
         mask[rows] = 1.0
-        losses = torch.zeros(steps, device=x.device)
-        for t in range(1, steps + 1):
-            _lib.call('lemo_ae_finetune_step', net.handle, _lib.ptr(x), _lib.ptr(mask), int(rows.numel()), N, float(lr), t,
-                      C.c_void_p(losses.data_ptr() + 4 * (t - 1)), st)
+        # one C-ABI call for the whole loop: the step is captured once as a CUDA graph and replayed (lemo_ae_finetune_run); the mask /
+        # loss buffers are kept on the handle so that the captured pointers stay valid from clip to clip
+        if getattr(net, '_ft_mask', None) is None or net._ft_mask.shape[0] != H or net._ft_losses.shape[0] != steps:
+            net._ft_mask = torch.zeros(H, device=x.device)
+            net._ft_losses = torch.zeros(steps, device=x.device)
+        net._ft_mask.copy_(mask)
+        _lib.call('lemo_ae_finetune_run', net.handle, _lib.ptr(x), _lib.ptr(net._ft_mask), int(rows.numel()), N, float(lr), int(steps),
+                  _lib.ptr(net._ft_losses), st)
+        losses = net._ft_losses.clone()
+        x.record_stream(torch.cuda.current_stream(x.device))
         _lib.call('lemo_convnet_get_weights', net.handle, _lib.ptr(self.flat.data), st)
         net.stamp += 1
         return losses

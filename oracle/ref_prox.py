@@ -44,8 +44,11 @@ def s2_loss(P, ctx, cfg):
     nv = vw.shape[1]
     D = cfg['sdf'].shape[-1]
     norm = (vw - cfg['grid_min']) / (cfg['grid_max'] - cfg['grid_min']) * 2 - 1
-    vol = cfg['sdf'].to(verts.dtype)[None, None].expand(B, 1, D, D, D)
-    body_sdf = F.grid_sample(vol, norm[:, :, [2, 1, 0]].view(-1, nv, 1, 1, 3), padding_mode='border', align_corners=False).view(B, nv)   # :684
+    # :684 -- the reference samples a [B,1,D,D,D] replica of ONE scene volume; sampling that volume frame by frame is the same arithmetic
+    # without the B-fold copy (6.7 GB at B=100, D=256)
+    vol = cfg['sdf'].to(verts.dtype)[None, None]
+    body_sdf = torch.cat([F.grid_sample(vol, norm[b:b + 1][:, :, [2, 1, 0]].view(1, nv, 1, 1, 3), padding_mode='border',
+                                        align_corners=False).view(1, nv) for b in range(B)], 0)
     neg = body_sdf < 0
     T['sdf'] = w['sdf'] * body_sdf[neg].abs().sum() if bool(neg.any()) else torch.zeros((), dtype=verts.dtype)   # :688-694
     # friction (:699-739), scene normal = +z
@@ -65,7 +68,17 @@ def s2_loss(P, ctx, cfg):
     # contact (:743-753), Chamfer to the (shared) scene
     T['contact'] = torch.zeros((), dtype=verts.dtype)
     if w.get('contact', 0) > 0:
-        d1, _, _, _ = rp.chamfer(vw[:, cfg['contact_ids']], cfg['scene_v'].to(verts.dtype)[None].expand(B, -1, -1))
+        cv = vw[:, cfg['contact_ids']]
+        scene = cfg['scene_v'].to(verts.dtype)
+        if B * cv.shape[1] * scene.shape[0] <= 1 << 27:
+            d1, _, _, _ = rp.chamfer(cv, scene[None].expand(B, -1, -1))
+        else:
+            # config-4 scale (100 x 1121 x 100 000): the [B,n,m] distance tensor of the torch restatement would need 45 GB; take the
+            # nearest-neighbour INDICES from the C restatement (oracle/csrc/chamfer_ref.c) and form the distance differentiably,
+            # which is what chamferFunction's forward + backward compute (dist_chamfer.py:10-45)
+            from . import ref_chamfer
+            _, idx = ref_chamfer.chamfer_nn(cv.detach().float().numpy(), scene.float().numpy())
+            d1 = ((cv - scene[torch.from_numpy(idx).long()]) ** 2).sum(-1)
         r = torch.sqrt(d1 + 1e-4)
         T['contact'] = w['contact'] * (r / (r + 1.0)).mean()
     # smoothness prior on world markers (:997-1031): same canonicalisation as the AMASS script but in world coordinates
