@@ -211,7 +211,7 @@ int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* 
                           const int32_t* idx1, const int32_t* idx2, float* d_xyz1, float* d_xyz2, void* stream);
 
 /* Static scene accelerator for the PROX contact term (fitting_temp_slide.py:743-753): the scene mesh of a recording is fixed
- * (fit_temp_loadprox_slide.py:366-372), so its points are Morton-sorted once into boxed tiles and a query scans only the tiles that
+ * (fit_temp_loadprox_slide.py:366-372), so its points are k-d sorted once (median splits of the longest axis) into boxed tiles and a query scans only the tiles that
  * can still hold a closer point.  dist1 / idx1 are IDENTICAL to lemo_chamfer_forward's against the same scene (same pinned
  * arithmetic, same first-minimum rule; idx1 = index into the ORIGINAL scene array).  lemo_scene_create synchronises (create time). */
 typedef struct LemoScene LemoScene;

@@ -22,6 +22,16 @@
 
 namespace lemo {
 
+constexpr int SKB_TV = 256;                 // vertices per tile of k_skin_bwd
+constexpr int SKB_PART = NJ * 12 + 3;       // per-CTA partial: dA[55][12] + dtransl[3]
+static inline int skin_bwd_tiles(int V, int B) {
+    const int ntile = cdiv(V, SKB_TV);
+    return ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 720)));
+}
+static inline int skin_bwd_ctas(int V, int B) { return cdiv(cdiv(V, SKB_TV), skin_bwd_tiles(V, B)); }
+static inline int dx_slices(int V) { return std::max(1, std::min(64, (3 * V) / 2048)); }
+
+
 // =============================================================================================
 // model
 // =============================================================================================
@@ -153,6 +163,26 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
         LEMO_TRY(dev_upload(&m->lmk_tri, tri.data(), tri.size()));
         LEMO_TRY(dev_upload(&m->lmk_bary, d->h_lmk_bary, (size_t)m->n_lmk * 3));
     }
+    {   // inverse map vertex -> (output joint, weight) for the deterministic joint adjoint (k_joints_bwd)
+        std::vector<std::pair<int, std::pair<int, float>>> ent;          // (vertex, (q, w))
+        for (int e = 0; e < m->n_extra; ++e) ent.push_back({d->h_extra_joint_vids[e], {NJ + e, 1.f}});
+        for (int l = 0; l < m->n_lmk; ++l)
+            for (int k = 0; k < 3; ++k)
+                ent.push_back({d->h_faces[(size_t)d->h_lmk_faces_idx[l] * 3 + k], {NJ + m->n_extra + l, d->h_lmk_bary[l * 3 + k]}});
+        std::stable_sort(ent.begin(), ent.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        std::vector<int> vid, off(1, 0), q;
+        std::vector<float> w;
+        for (size_t i = 0; i < ent.size(); ++i) {
+            if (i == 0 || ent[i].first != ent[i - 1].first) { if (i) off.push_back((int)q.size()); vid.push_back(ent[i].first); }
+            q.push_back(ent[i].second.first); w.push_back(ent[i].second.second);
+        }
+        off.push_back((int)q.size());
+        m->n_jv = (int)vid.size();
+        if (m->n_jv) {
+            LEMO_TRY(dev_upload(&m->jv_vid, vid.data(), vid.size())); LEMO_TRY(dev_upload(&m->jv_off, off.data(), off.size()));
+            LEMO_TRY(dev_upload(&m->jv_q, q.data(), q.size())); LEMO_TRY(dev_upload(&m->jv_w, w.data(), w.size()));
+        }
+    }
     *out = m;
     return 0;
 }
@@ -177,6 +207,7 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
     s->is_sub = true;
     s->V = n;
     s->n_extra = 0; s->n_lmk = 0; s->extra_vids = nullptr; s->lmk_tri = nullptr; s->lmk_bary = nullptr;
+    s->n_jv = 0; s->jv_vid = nullptr; s->jv_off = nullptr; s->jv_q = nullptr; s->jv_w = nullptr;
     int* rows_dev = nullptr;
     LEMO_TRY(dev_upload(&rows_dev, rows_host, n));
     LEMO_TRY(dev_alloc(&s->v_template, (size_t)n * 3));
@@ -202,6 +233,7 @@ void model_free(Model* m) {
         cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth);
         cudaFree(m->hand_l); cudaFree(m->hand_r); cudaFree(m->pose_mean);
         cudaFree(m->extra_vids); cudaFree(m->lmk_tri); cudaFree(m->lmk_bary);
+        cudaFree(m->jv_vid); cudaFree(m->jv_off); cudaFree(m->jv_q); cudaFree(m->jv_w);
     }
     delete m;
 }
@@ -210,7 +242,7 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
     LEMO_CHECK(m && out && maxB > 0, "bad arguments");
     LEMO_CUDA(cudaSetDevice(m->device));
     BodyCtx* c = new BodyCtx();
-    c->m = m; c->maxB = maxB;
+    c->m = m; c->maxB = maxB; c->device = m->device;
     const size_t B = maxB, V = m->V;
     LEMO_TRY(dev_alloc(&c->full_pose, B * 165));
     LEMO_TRY(dev_alloc(&c->R, B * NJ * 9));
@@ -235,6 +267,11 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
         LEMO_TRY(dev_alloc(&c->dR, B * NJ * 9));
         LEMO_TRY(dev_alloc(&c->dJp, B * NJ * 3));
         LEMO_TRY(dev_alloc(&c->dtr, B * 3));
+        const int ntile = cdiv(m->V, SKB_TV);
+        if (ntile > 2) {          // full meshes: several CTAs per frame in k_skin_bwd and a sliced dX GEMM, combined in a fixed order
+            c->part_floats = std::max((size_t)skin_bwd_ctas(m->V, maxB) * B * SKB_PART, (size_t)dx_slices(m->V) * B * XK);
+            LEMO_TRY(dev_alloc(&c->part, c->part_floats));
+        }
     }
     *out = c;
     return 0;
@@ -242,8 +279,8 @@ int bodyctx_create(const Model* m, int maxB, bool with_backward, BodyCtx** out) 
 
 void bodyctx_free(BodyCtx* c) {
     if (!c) return;
-    cudaSetDevice(c->m->device);
-    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->A2, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->dA, c->dX, c->dR, c->dJp, c->dtr};
+    cudaSetDevice(c->device);
+    float* ptrs[] = {c->full_pose, c->R, c->X, c->X2, c->G, c->A, c->A2, c->Jrest, c->Jposed, c->VP, c->Gv, c->DVP, c->dA, c->dX, c->dR, c->dJp, c->dtr, c->part};
     for (float* p : ptrs) cudaFree(p);
     delete c;
 }
@@ -573,10 +610,10 @@ __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ A, c
 // per tile, phase A computes dvp and parks dT in shared memory, phase B lets thread t accumulate outputs t, t+256, t+512 of the 660
 // (joint, 3x4 entry) pairs over the tile.  A CTA that owns all vertices of its frame (the loss-row sub-models: V = 253) adds in a fixed
 // order => bitwise reproducible; several CTAs per frame (full mesh) combine with atomicAdd like the split-K GEMM did.
-constexpr int SKB_TV = 256;
 __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, const float* __restrict__ w_jm,
                                                   const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B, int tiles,
-                                                  float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr) {
+                                                  float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr,
+                                                  float* __restrict__ part) {
     __shared__ float sA[NJ * 12];
     __shared__ __align__(16) float s_dt[SKB_TV * 12];
     __shared__ float s_w[NJ][33];
@@ -659,15 +696,36 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
         for (int k = 0; k < 12; ++k) s_dt[sB * (NJ * 12) + jB * 12 + k] = acc[k];
     }
     __syncthreads();
+    // one CTA per frame (loss-row sub-models): add straight into dA / dtr (single contribution per address: deterministic).
+    // several CTAs per frame (full mesh): park this CTA's 660 + 3 sums in part[blockIdx.x][b][.]; k_skin_bwd_reduce adds them in CTA order.
+    float* pz = part ? part + ((size_t)blockIdx.x * B + b) * SKB_PART : nullptr;
     for (int t = threadIdx.x; t < NJ * 12; t += 256) {
         const float v = (s_dt[t] + s_dt[NJ * 12 + t]) + (s_dt[2 * NJ * 12 + t] + s_dt[3 * NJ * 12 + t]);
         const int j = t / 12, k = t - j * 12;
-        atomicAdd(&dA[(size_t)j * B * 12 + (size_t)b * 12 + k], v);
+        if (pz) pz[t] = v;
+        else atomicAdd(&dA[(size_t)j * B * 12 + (size_t)b * 12 + k], v);
     }
     float s;
-    s = block_sum(gs0, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3], s);
-    s = block_sum(gs1, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 1], s);
-    s = block_sum(gs2, sred); if (threadIdx.x == 0) atomicAdd(&dtr[b * 3 + 2], s);
+    s = block_sum(gs0, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12] = s; else atomicAdd(&dtr[b * 3], s); }
+    s = block_sum(gs1, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 1] = s; else atomicAdd(&dtr[b * 3 + 1], s); }
+    s = block_sum(gs2, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 2] = s; else atomicAdd(&dtr[b * 3 + 2], s); }
+}
+__global__ void k_skin_bwd_reduce(const float* __restrict__ part, int nparts, int B, float* __restrict__ dA, float* __restrict__ dtr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * SKB_PART) return;
+    const int b = i / SKB_PART, t = i - b * SKB_PART;
+    float a = 0.f;
+    for (int p = 0; p < nparts; ++p) a += part[((size_t)p * B + b) * SKB_PART + t];
+    if (t < NJ * 12) { const int j = t / 12, k = t - j * 12; dA[(size_t)j * B * 12 + (size_t)b * 12 + k] += a; }
+    else dtr[b * 3 + (t - NJ * 12)] += a;
+}
+// C[M,N] += sum over slices of the partial products parked by a splitk == 2 GEMM, in slice order
+__global__ void k_slices_reduce(const float* __restrict__ part, int nz, long long mn, float* __restrict__ C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mn) return;
+    float a = 0.f;
+    for (int z = 0; z < nz; ++z) a += part[(size_t)z * mn + i];
+    C[i] += a;
 }
 
 // =============================================================================================
@@ -698,26 +756,32 @@ __global__ void k_joints_fwd(const float* __restrict__ Jposed, const float* __re
     for (int k = 0; k < 3; ++k) joints[((size_t)b * nout + q) * 3 + k] = o[k];
 }
 
-__global__ void k_joints_bwd(const float* __restrict__ dj, const int* __restrict__ extra, int n_extra, const int* __restrict__ tri,
-                             const float* __restrict__ bary, int n_lmk, int V, int B, float* __restrict__ Gv,
+// adjoint of k_joints_fwd, gather form (no atomics): (1) the 55 posed joints: dJp = g (single writer) and dtransl += sum_q g in joint
+// order; (2) every distinct vertex referenced by a vertex joint or a landmark adds its entries of the model's inverse map in order.
+__global__ void k_joints_bwd(const float* __restrict__ dj, int nout, int n_jv, const int* __restrict__ jv_vid, const int* __restrict__ jv_off,
+                             const int* __restrict__ jv_q, const float* __restrict__ jv_w, int V, int B, float* __restrict__ Gv,
                              float* __restrict__ dJp, float* __restrict__ dtr) {
-    const int nout = NJ + n_extra + n_lmk;
+    const int per = NJ * 3 + 3 + n_jv;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * nout) return;
-    const int b = i / nout, q = i - b * nout;
-    const float* g = dj + ((size_t)b * nout + q) * 3;
-    if (q < NJ) {
-        for (int k = 0; k < 3; ++k) { atomicAdd(&dJp[((size_t)b * NJ + q) * 3 + k], g[k]); atomicAdd(&dtr[b * 3 + k], g[k]); }
-    } else if (q < NJ + n_extra) {
-        float* d = Gv + ((size_t)b * V + extra[q - NJ]) * 3;
-        for (int k = 0; k < 3; ++k) atomicAdd(&d[k], g[k]);
+    if (i >= B * per) return;
+    const int b = i / per, t = i - b * per;
+    const float* g = dj + (size_t)b * nout * 3;
+    if (t < NJ * 3) dJp[(size_t)b * NJ * 3 + t] += g[t];
+    else if (t < NJ * 3 + 3) {
+        const int k = t - NJ * 3;
+        float a = 0.f;
+        for (int q = 0; q < NJ; ++q) a += g[q * 3 + k];         // posed joints carry + transl directly (vertex joints get it through Gv)
+        dtr[b * 3 + k] += a;
     } else {
-        const int l = q - NJ - n_extra;
-        for (int c = 0; c < 3; ++c) {
-            const float w = bary[l * 3 + c];
-            float* d = Gv + ((size_t)b * V + tri[l * 3 + c]) * 3;
-            for (int k = 0; k < 3; ++k) atomicAdd(&d[k], w * g[k]);
+        const int u = t - NJ * 3 - 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int e = jv_off[u]; e < jv_off[u + 1]; ++e) {
+            const float w = jv_w[e];
+            const float* gq = g + jv_q[e] * 3;
+            a0 += w * gq[0]; a1 += w * gq[1]; a2 += w * gq[2];
         }
+        float* d = Gv + ((size_t)b * V + jv_vid[u]) * 3;
+        d[0] += a0; d[1] += a1; d[2] += a2;
     }
 }
 
@@ -809,14 +873,16 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
     if (d_joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");
         const int nout = NJ + m->n_extra + m->n_lmk;
-        k_joints_bwd<<<cdiv(B * nout, 128), 128, 0, st>>>(d_joints, m->extra_vids, m->n_extra, m->lmk_tri, m->lmk_bary, m->n_lmk, V, B,
-                                                            c->Gv, ps->dJp, ps->dtr);
+        k_joints_bwd<<<cdiv(B * (NJ * 3 + 3 + m->n_jv), 128), 128, 0, st>>>(d_joints, nout, m->n_jv, m->jv_vid, m->jv_off, m->jv_q, m->jv_w, V, B,
+                                                                              c->Gv, ps->dJp, ps->dtr);
     }
     {
         // vertex tiles per CTA: everything in one CTA per frame while that still fills the GPU (sub-models), else ~6 CTAs per frame
         const int ntile = cdiv(V, SKB_TV);
-        const int tiles = ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 720)));
-        k_skin_bwd<<<dim3(cdiv(ntile, tiles), B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr);
+        const int tiles = skin_bwd_tiles(V, B), ctas = cdiv(ntile, tiles);
+        float* part = (ctas > 1 && c->part && (size_t)ctas * B * SKB_PART <= c->part_floats) ? c->part : nullptr;
+        k_skin_bwd<<<dim3(ctas, B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr, part);
+        if (part) k_skin_bwd_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(part, ctas, B, ps->dA, ps->dtr);
     }
     LEMO_CUDA(cudaGetLastError());
     // dX[B,512] += DVP[B,3V] . Wt^T        (contraction over 3V: split-K with atomics)
@@ -825,8 +891,14 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
         g.A = c->DVP; g.B = m->Wt; g.C = ps->dX; g.bias = nullptr;
         g.M = B; g.N = XK; g.K = 3 * V;
         g.sAm = 3 * V; g.sAk = 1; g.sBk = 1; g.sBn = 3 * V; g.sCm = XK; g.sCn = 1;
-        g.splitk = 1; g.nz = std::max(1, std::min(64, (3 * V) / 2048));   // loss-row sub-models: one slice => deterministic
-        LEMO_TRY(gemm_launch(g, st));
+        g.splitk = 1; g.nz = dx_slices(V);                                 // loss-row sub-models: one slice => deterministic
+        if (g.nz > 1 && c->part && (size_t)g.nz * B * XK <= c->part_floats) {
+            // full mesh: every K slice parks its partial product, the slices are added in order (no float atomics)
+            g.splitk = 2; g.C = c->part;
+            LEMO_TRY(gemm_launch(g, st));
+            k_slices_reduce<<<cdiv((long long)B * XK, 256), 256, 0, st>>>(c->part, g.nz, (long long)B * XK, ps->dX);
+            LEMO_CUDA(cudaGetLastError());
+        } else LEMO_TRY(gemm_launch(g, st));
     }
     return 0;
 }

@@ -34,6 +34,11 @@ struct Model {
     int* extra_vids = nullptr;     // [n_extra]
     int* lmk_tri = nullptr;        // [n_lmk,3] vertex ids
     float* lmk_bary = nullptr;     // [n_lmk,3]
+    // adjoint of the vertex-derived output joints as a gather: distinct vertex u receives sum_e jv_w[e] * d_joints[jv_q[e]] over its entries
+    // [jv_off[u], jv_off[u+1]) in output-joint order (fixed order, single writer: no atomics)
+    int n_jv = 0;
+    int *jv_vid = nullptr, *jv_off = nullptr, *jv_q = nullptr;
+    float* jv_w = nullptr;
     int h_parents[NJ];
     int h_depth[NJ];
 };
@@ -74,6 +79,7 @@ struct PoseGrad {                            // all nullable; written (not accum
 struct BodyCtx {
     const Model* m = nullptr;
     int maxB = 0;
+    int device = 0;              // copy of m->device: the model may already be gone when this context is freed (Python GC order)
     float* full_pose = nullptr;  // [B,165]
     float* R = nullptr;          // [B,55,9]
     float* X = nullptr;          // [B,512]
@@ -94,6 +100,8 @@ struct BodyCtx {
     float* dR = nullptr;         // [B,55,9]
     float* dJp = nullptr;        // [B,55,3]
     float* dtr = nullptr;        // [B,3]
+    float* part = nullptr;       // full meshes: per-CTA partials of k_skin_bwd [ctas][B*663] and slice partials of the dX GEMM [nz][B*512]
+    size_t part_floats = 0;
 };
 
 int model_create_from_host(const ::LemoModelDescC* d, int device, Model** out);

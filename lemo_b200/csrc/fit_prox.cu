@@ -8,9 +8,9 @@
 // direction: the loss never reads dist2), Enc smoothness prior on the world markers, the first-15 % gradient erase (:281-288)
 // and Adam.  No host synchronisation (the reference has ~14 .item() per step); loss weights, learning rate and the erase
 // count live in device memory so that one iteration is ONE replayable CUDA graph across optimisation stages.
-// The loss reductions and the term adjoints of this file have a fixed order (per-CTA partials summed by one CTA; gather-style
-// adjoints instead of float atomics).  The full-mesh body adjoint (body.cu: several CTAs per frame combine dA / dX partials with
-// atomicAdd) is order dependent, so two runs of a window agree to rounding (~1e-6), not bit for bit.
+// Every reduction has a fixed order (per-CTA partials summed in CTA order, gather-style adjoints instead of float atomics, the body
+// adjoint's per-frame partials and dX K-slices added in order -- body.cu), so a window is bitwise reproducible; the one exception is
+// the reported smoothness LOSS VALUE (float atomics in the Enc loss kernel), which does not feed back into the parameters.
 #include "common.cuh"
 #include "body.cuh"
 #include "vposer.cuh"

@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(GBM * 4) k_gemm(GemmP p) {
             if (gn >= p.N) continue;
             float* c = C + gm * p.sCm + gn * p.sCn;
             float v = acc[i][j];
-            if (p.splitk) {
+            if (p.splitk == 2) {                 // slice z parks its partial in C[z][M][N] (row-major); the caller adds the slices in order
+                C[((size_t)blockIdx.z * p.M + gm) * p.N + gn] = v;
+            } else if (p.splitk) {
                 if (p.bias && blockIdx.z == 0) v += p.bias[gn];
                 atomicAdd(c, v);
             } else {

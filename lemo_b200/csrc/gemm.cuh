@@ -13,7 +13,7 @@ struct GemmP {
     long long sAm, sAk, sBk, sBn, sCm, sCn;
     long long bA, bB, bC;      // batch strides (nz batches) -- used when splitk == 0
     int nz;                    // number of batches or of K slices
-    int splitk;                // 1: blockIdx.z slices K and the epilogue is atomicAdd into C
+    int splitk;                // 1: blockIdx.z slices K and the epilogue is atomicAdd into C; 2: slice z stores its partial at C[z][M][N]
     int act;                   // 0 none, 1 LeakyReLU(0.2), 2 multiply by LeakyReLU'(mask_src) (ignored for splitk)
     const float* mask_src;     // act==2: same layout as C; factor = mask_src>0 ? 1 : 0.2
     int accumulate;            // non-split: C += result instead of C = result

@@ -1,5 +1,6 @@
 """CPU restatement of the PROX stage-2 loss (reference temp_prox/fitting_temp_slide.py:564-1062, terms active in
 cfg_files/PROXD_temp_S2.yaml plus the `contact` term BASELINE.json's config 4 switches on).  TEST INFRASTRUCTURE ONLY."""
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -95,7 +96,8 @@ def fit_window(P_np, ctx, cfg, n_iters, lr=0.005, first_batch_flag=False, trace=
     """FittingMonitor.run_fitting + create_fitting_closure.fitting_func (fitting_temp_slide.py:169-313) for one window with
     torch.optim.Adam (optim_factory.py:77-80): closure = loss + backward + `grad[0:int(bs*0.15)] = 0` unless it is the first window.
     Returns (dict of fitted numpy params, last loss)."""
-    P = {k: torch.from_numpy(v).to(ctx.dtype).requires_grad_(k in PKEYS) for k, v in P_np.items()}
+    # .copy(): torch.from_numpy shares memory with the caller's arrays and Adam updates in place
+    P = {k: torch.from_numpy(np.array(v, copy=True)).to(ctx.dtype).requires_grad_(k in PKEYS) for k, v in P_np.items()}
     params = [P[k] for k in PKEYS]
     opt = torch.optim.Adam(params, lr=lr)
     bs = P['transl'].shape[0]

@@ -153,7 +153,7 @@ def test_chamfer_config4_scale_bit_exact():
 
 
 def test_static_scene_query_equals_brute_force():
-    """lemo_scene_query (Morton-tiled scene with box pruning, what the fused PROX driver uses for the contact term) returns exactly the
+    """lemo_scene_query (k-d tiled scene with box pruning, what the fused PROX driver uses for the contact term) returns exactly the
     brute-force result: bit-exact distances and indices against the C oracle at config-4 scale, incl. duplicated scene points (lowest
     index wins) and queries far away from the scene."""
     import ctypes as C

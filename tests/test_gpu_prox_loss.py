@@ -167,7 +167,7 @@ def test_run_fitting_20_steps_with_freeze_fused_eager_oracle(monkeypatch):
                                        params_max_abs_dev={m: {k: float(np.abs(res[m][0][k] - P_ref[k]).max()) for k in PKEYS} for m in res}))
     print(dev)
     assert max(dev[:3]) < 2e-3, dev                       # together at the start (closure-level parity)
-    assert max(dev) < 5e-2, dev                           # and still at the same loss level after 20 steps
+    assert max(dev) < 2e-2, dev                           # and still at the same loss level after 20 steps
     assert curve_ref[-1] < curve_ref[0] and curve[-1] < curve[0]
     erase_n = int(B * 0.15)
     for mode, (Pm, final) in res.items():
@@ -177,13 +177,14 @@ def test_run_fitting_20_steps_with_freeze_fused_eager_oracle(monkeypatch):
             # 20 Adam steps of lr .005 move a parameter by <= 0.1
             assert np.abs(Pm[k] - P_ref[k]).max() < 2e-2, (mode, k, np.abs(Pm[k] - P_ref[k]).max())
         assert np.abs(Pm['transl'] - P['transl']).max() > 1e-2                           # the free frames did move
-    for k in PKEYS:                                        # chunked (resume) run == single run, up to the float-atomic order of the body adjoint
-        assert np.abs(stepped[k] - res['fused'][0][k]).max() < 1e-3, k
+    for k in PKEYS:                                        # chunked (resume) run == single run, bit for bit
+        assert np.array_equal(stepped[k], res['fused'][0][k]), k
 
 
-def test_fused_window_is_reproducible():
-    """Two identical fused runs agree to rounding: the loss reductions and the term adjoints have a fixed order; the full-mesh body
-    adjoint (body.cu: per-frame partials of dA / dX combined with float atomics) is the one order-dependent piece."""
+def test_fused_window_is_bitwise_reproducible():
+    """Two identical fused runs give bitwise identical parameters: every reduction of the closure has a fixed order (per-CTA partials
+    added in CTA order, gather-form adjoints, K slices of the dX GEMM added in slice order) -- Adam turns any order-dependent rounding
+    of a near-zero gradient into an O(lr) parameter difference, so this matters for reproducible fits."""
     B = 24
     P, cfg = synth.make_prox_problem(B, D=32, m_scene=3000, seed=5)
     outs = []
@@ -194,7 +195,7 @@ def test_fused_window_is_reproducible():
         assert s['monitor'].last_path == 'fused'
         outs.append(_params_of(s))
     for k in PKEYS:
-        assert np.abs(outs[0][k] - outs[1][k]).max() < 1e-4, (k, np.abs(outs[0][k] - outs[1][k]).max())
+        assert np.array_equal(outs[0][k], outs[1][k]), (k, np.abs(outs[0][k] - outs[1][k]).max())
 
 
 def test_unsupported_terms_fall_back_to_the_eager_closure():
