@@ -13,6 +13,9 @@
 #include "conv.cuh"
 #include "gemm.cuh"
 #include "fit_common.cuh"
+#include "perframe_mega.cuh"
+#include <cstdlib>
+#include <cstring>
 #include "../../include/lemo_b200.h"
 #include <vector>
 
@@ -40,7 +43,7 @@ struct Fit {
     float *stats = nullptr;                  // Xmean[243] Xstd[243]
     float *acc = nullptr;                    // [S,16] loss accumulators
     float *p72 = nullptr;                    // [S,T,72] snapshot of the last forward
-    float *pf_state = nullptr;               // per-frame: nothing extra
+    float *pf_ws = nullptr;                  // per-frame persistent kernel: per-CTA partials [S][8][512 + 512 + 664]
     Sched* sched = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -372,7 +375,7 @@ int lemo_fit_destroy(LemoFit* h) {
     if (f->graph) cudaGraphDestroy(f->graph);
     if (f->gstream) { cudaStreamDestroy(f->gstream); cudaEventDestroy(f->ev_in); cudaEventDestroy(f->ev_out); }
     float* ps[] = {f->P, f->Gp, f->M1, f->M2, f->betas, f->mrec, f->contact, f->Rg, f->Rb, f->dRg, f->dRb, f->Vr, f->Grows, f->xin, f->gx,
-                   f->gv, f->canon, f->stats, f->acc, f->p72};
+                   f->gv, f->canon, f->stats, f->acc, f->p72, f->pf_ws};
     for (float* p : ps) cudaFree(p);
     cudaFree(f->sched);
     bodyctx_free(f->ctx);
@@ -455,10 +458,46 @@ int lemo_fit_run(LemoFit* h, int32_t n_iters, float lr0, float lr1, int32_t lr_s
     return fit_run_iters(f, n_iters, st);
 }
 
+// LEMO_PERFRAME=graph selects the round-1 path (one CUDA graph of ~23 kernels per step); default = the persistent cluster kernel
+static bool perframe_mega_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("LEMO_PERFRAME"); on = (e && strcmp(e, "graph") == 0) ? 0 : 1; }
+    return on != 0;
+}
+
+static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
+    const int S = f->S;
+    if (!f->pf_ws) LEMO_TRY(dalloc(&f->pf_ws, (size_t)S * PM_CL * (512 + 512 + PM_PART)));
+    LEMO_CHECK(f->sub->V <= PM_CL * PM_VPC, "per-frame kernel: more loss rows than the cluster covers");
+    MegaArgs a{};
+    const Model* m = f->sub;
+    a.vt = m->v_template; a.Wt = m->Wt; a.wjm = m->w_jm; a.Jt = m->J_template; a.Jd = m->J_dirs; a.hand_l = m->hand_l; a.hand_r = m->hand_r;
+    a.pose_mean = m->pose_mean; a.parents = m->parents; a.depth = m->depth; a.max_depth = m->max_depth; a.V = m->V; a.npc = m->npc;
+    VPoser* v = f->vp;
+    a.W1 = v->W1; a.b1 = v->b1; a.W2 = v->W2; a.b2 = v->b2; a.W3 = v->W3; a.b3 = v->b3;
+    a.h1 = v->h1; a.h2 = v->h2; a.o = v->o; a.dh2 = v->dh2;
+    a.dh1p = f->pf_ws; a.dXp = a.dh1p + (size_t)S * PM_CL * 512; a.dAp = a.dXp + (size_t)S * PM_CL * 512;
+    BodyCtx* c = f->ctx;
+    a.full_pose = c->full_pose; a.R = c->R; a.X = c->X; a.G = c->G; a.A = c->A; a.Jrest = c->Jrest; a.Jposed = c->Jposed;
+    a.dA = c->dA; a.dX = c->dX; a.dR = c->dR;
+    a.Rg = f->Rg; a.Rb = f->Rb; a.dRg = f->dRg; a.dRb = f->dRb;
+    a.P = f->P; a.Gp = f->Gp; a.betas = f->betas; a.mrec = f->mrec; a.p72 = f->p72; a.acc = f->acc;
+    a.acc_n = ACC_N; a.acc_rec = ACC_REC; a.acc_vp = ACC_VP; a.acc_shape = ACC_SHAPE; a.acc_hand = ACC_HAND;
+    a.S = S; a.T = f->T; a.n_iters = n_iters;
+    a.w_rec = f->cfg.w_rec; a.w_vp = f->cfg.w_vposer; a.w_shape = f->cfg.w_shape; a.w_hand = f->cfg.w_hand;
+    LEMO_CUDA(cudaMemsetAsync(f->acc, 0, (size_t)S * ACC_N * sizeof(float), st));
+    const int nclusters = std::min(S, 16);           // 8-CTA clusters: two per GPC; more sequences than that are walked in turn
+    k_perframe_mega<<<PM_CL * nclusters, PM_NT, 0, st>>>(a);
+    LEMO_CUDA(cudaGetLastError());
+    f->launches += 1;
+    return 0;
+}
+
 int lemo_fit_run_perframe(LemoFit* h, int32_t n_iters, void* stream) {
     LEMO_CHECK(h && h->f.mode == 1 && n_iters >= 0, "lemo_fit_run_perframe is the per-frame-mode driver");
     Fit* f = &h->f;
     cudaStream_t st = (cudaStream_t)stream;
+    if (perframe_mega_enabled() && n_iters > 0) return perframe_mega_run(f, n_iters, st);
     for (int t = 0; t < f->T; ++t) {
         // lr .1 for frame 0 else .01; ->.01 @step>60, ->.003 @step>80 (opt_amass_perframe.py:315-330); warm start = P carried over
         LEMO_TRY(fit_begin_run(f, t == 0 ? 0.1f : 0.01f, 0.01f, 0.003f, 60, 80, t, st));

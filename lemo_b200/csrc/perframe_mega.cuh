@@ -1,0 +1,347 @@
+// Persistent per-frame fitting kernel (reference opt_amass_perframe.py:293-361; SURVEY.md section 7 "hard part 1").
+//
+// The per-frame stage is T sequential B=1 Adam problems x 100 steps per sequence, warm-started frame to frame: as a graph of
+// ~23 small kernels per step it is pure launch/dependency latency (127 us per step for 8 chains, every kernel on 1-8 CTAs).
+// Here ONE launch runs the whole stage -- all frames, all steps -- with one thread-block CLUSTER of 8 CTAs per sequence:
+//   * the VPoser MLP (32 -> 512 -> 512 -> 126, 1.4 MB of fp32 weights) is split by output rows across the 8 CTAs, which stream their
+//     slices from L2 every step (22 MB per step for 8 sequences: L2 bandwidth, not HBM) and exchange activations through small
+//     per-sequence global (L2-resident) buffers between cluster barriers; the adjoint W^T products are computed as per-CTA partial
+//     vectors that every CTA adds in rank order (deterministic);
+//   * pose -> rotations -> kinematic chain and its adjoint are the SAME device bodies the stand-alone kernels run (body_dev.cuh),
+//     executed redundantly by each CTA (55 joints: latency, not work), so no barrier is spent on them;
+//   * the 81 marker rows of the body model are dealt 11 per CTA: fp32 blend (243 of the 512 x 31425 blend-shape columns), skinning,
+//     L1 marker loss and their adjoints; dA / dX / dtransl partials are combined like the MLP partials;
+//   * parameters and Adam moments (65 per frame) are replicated in every CTA's shared memory: all CTAs apply the identical update,
+//     nothing is broadcast; the learning-rate schedule (.1/.01 -> .01 @>60 -> .003 @>80) and bias corrections are computed in-kernel.
+// Six cluster barriers per step, no host involvement until the last frame is done.
+#pragma once
+#include "body_dev.cuh"
+#include <cooperative_groups.h>
+
+namespace lemo {
+namespace cgx = cooperative_groups;
+
+constexpr int PM_CL = 8;          // CTAs per cluster = per sequence
+constexpr int PM_NT = 256;        // threads per CTA
+constexpr int PM_VPC = 11;        // marker rows per CTA (8 x 11 >= 81)
+constexpr int PM_PART = 664;      // dA[660] + dtransl[3] + loss partial
+
+struct MegaArgs {
+    // loss-row sub-model (V = 81 marker rows)
+    const float *vt, *Wt, *wjm, *Jt, *Jd, *hand_l, *hand_r, *pose_mean;
+    const int *parents, *depth;
+    int max_depth, V, npc;
+    // VPoser decoder, nn.Linear layout [out][in]
+    const float *W1, *b1, *W2, *b2, *W3, *b3;
+    float *h1, *h2, *o, *dh2;                    // [S,512] [S,512] [S,126] [S,512]
+    float *dh1p, *dXp, *dAp;                     // per-CTA partials: [S][8][512], [S][8][512], [S][8][PM_PART]
+    // body scratch, one row per sequence (the fitter's BodyCtx)
+    float *full_pose, *R, *X, *G, *A, *Jrest, *Jposed, *dA, *dX, *dR;
+    float *Rg, *Rb, *dRg, *dRb;
+    // fit state
+    float *P, *Gp;
+    const float *betas, *mrec;
+    float *p72, *acc;
+    int acc_n, acc_rec, acc_vp, acc_shape, acc_hand;
+    int S, T, n_iters;
+    float w_rec, w_vp, w_shape, w_hand;
+};
+
+__device__ __forceinline__ size_t pm_poff(int i, int S, int s) {      // flat parameter vector P = [tr S*3 | r6 S*6 | z S*32 | lh S*12 | rh S*12]
+    if (i < 3) return (size_t)s * 3 + i;
+    if (i < 9) return (size_t)S * 3 + (size_t)s * 6 + (i - 3);
+    if (i < 41) return (size_t)S * 9 + (size_t)s * 32 + (i - 9);
+    if (i < 53) return (size_t)S * 41 + (size_t)s * 12 + (i - 41);
+    return (size_t)S * 53 + (size_t)s * 12 + (i - 53);
+}
+
+__global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perframe_mega(MegaArgs a) {
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncl = gridDim.x / PM_CL, cid = blockIdx.x / PM_CL;
+    const int S = a.S, V = a.V, NC = 3 * a.V;
+    __shared__ float s_p[65], s_m[65], s_v[65], s_g[65];
+    __shared__ __align__(16) float s_vec[512];          // staging: X / dh2 / dh1
+    __shared__ __align__(16) float s_h1[512];
+    __shared__ __align__(16) float s_h2[512];
+    __shared__ float s_A[NJ * 12];
+    __shared__ float s_red[8][64];
+    __shared__ float s_T[PM_VPC][12], s_dT[PM_VPC][12], s_vp[PM_VPC][3], s_gv[PM_VPC][3], s_dvp[3 * PM_VPC];
+    __shared__ float s_tgt[201], s_do[128], s_sc[8];
+
+    PoseK pk;
+    pk.in = PoseIn();
+    pk.in.transl = a.P; pk.in.R_global = a.Rg; pk.in.R_body = a.Rb;
+    pk.in.lhand = a.P + (size_t)S * 41; pk.in.rhand = a.P + (size_t)S * 53;
+    pk.in.betas = a.betas; pk.in.betas_stride = 10; pk.in.hand_is_pca = 1;
+    pk.hand_l = a.hand_l; pk.hand_r = a.hand_r; pk.pose_mean = a.pose_mean; pk.npc = a.npc;
+    PoseGrad pg;
+    pg.R_global = a.dRg; pg.R_body = a.dRb; pg.lhand = a.Gp + (size_t)S * 41; pg.rhand = a.Gp + (size_t)S * 53;
+
+    const int v0 = PM_VPC * rank, nv = max(0, min(PM_VPC, V - v0)), c0 = 3 * v0, ncol = 3 * nv;
+
+    for (int s = cid; s < S; s += ncl) {
+        if (tid < 65) s_p[tid] = a.P[pm_poff(tid, S, s)];
+        __syncthreads();
+        for (int t = 0; t < a.T; ++t) {
+            if (tid < 65) { s_m[tid] = 0.f; s_v[tid] = 0.f; }                      // fresh optim.Adam per frame (:319)
+            if (tid < 201) s_tgt[tid] = a.mrec[((size_t)s * a.T + t) * 201 + tid];
+            const float lr0 = t == 0 ? 0.1f : 0.01f;                               // :315-318
+            for (int it = 0; it < a.n_iters; ++it) {
+                const bool last = it == a.n_iters - 1;
+                if (tid == 0) {
+                    s_sc[0] = it > 80 ? 0.003f : (it > 60 ? 0.01f : lr0);          // `if step > 60` / `if step > 80` (:323-330)
+                    const double tt = (double)(it + 1);
+                    s_sc[1] = (float)(1.0 - pow(0.9, tt));
+                    s_sc[2] = (float)sqrt(1.0 - pow(0.999, tt));
+                }
+                // ------------------------------------------------ P1: global 6D -> R ; fc1 rows [64 rank, +64)
+                if (tid == 0) {
+                    float r[9];
+                    gs6d_fwd(s_p + 3, r);
+                    for (int k = 0; k < 9; ++k) a.Rg[(size_t)s * 9 + k] = r[k];
+                }
+                {
+                    const int r = tid >> 2, q = tid & 3, n = 64 * rank + r;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(a.W1 + (size_t)n * 32 + q * 8 + k), s_p[9 + q * 8 + k], acc);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    if (q == 0) a.h1[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b1 + n));
+                }
+                cluster.sync();
+                // ------------------------------------------------ P2: fc2 rows [64 rank, +64), one warp per row
+                s_h1[tid] = a.h1[(size_t)s * 512 + tid]; s_h1[tid + 256] = a.h1[(size_t)s * 512 + tid + 256];
+                __syncthreads();
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int n = 64 * rank + warp * 8 + rr;
+                    const float4* w = reinterpret_cast<const float4*>(a.W2 + (size_t)n * 512);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 wv = __ldg(w + i * 32 + lane);
+                        const float4 x = *reinterpret_cast<const float4*>(&s_h1[(i * 32 + lane) * 4]);
+                        acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) a.h2[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b2 + n));
+                }
+                cluster.sync();
+                // ------------------------------------------------ P3: output rows [16 rank, +16)
+                s_h2[tid] = a.h2[(size_t)s * 512 + tid]; s_h2[tid + 256] = a.h2[(size_t)s * 512 + tid + 256];
+                __syncthreads();
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int n = 16 * rank + warp * 2 + rr;
+                    if (n < 126) {
+                        const float4* w = reinterpret_cast<const float4*>(a.W3 + (size_t)n * 512);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 wv = __ldg(w + i * 32 + lane);
+                            const float4 x = *reinterpret_cast<const float4*>(&s_h2[(i * 32 + lane) * 4]);
+                            acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+                        }
+                        acc = warp_sum(acc);
+                        if (lane == 0) a.o[(size_t)s * 126 + n] = acc + __ldg(a.b3 + n);
+                    }
+                }
+                cluster.sync();
+                // ------------------------------------------------ P4 (every CTA): Gram-Schmidt, pose -> R -> chain (shared device body)
+                if (tid < NBODY) {
+                    float x6[6], r[9];
+                    for (int k = 0; k < 6; ++k) x6[k] = a.o[(size_t)s * 126 + tid * 6 + k];
+                    gs6d_fwd(x6, r);
+                    for (int k = 0; k < 9; ++k) a.Rb[((size_t)s * NBODY + tid) * 9 + k] = r[k];
+                }
+                if (tid < 65) a.P[pm_poff(tid, S, s)] = s_p[tid];                   // every CTA stores the same values
+                __syncthreads();
+                pose_chain_fwd_body(pk, a.Jt, a.Jd, a.parents, a.depth, a.max_depth, a.full_pose, a.R, a.X, nullptr, a.G, a.A, a.Jrest,
+                                    a.Jposed, nullptr, s);
+                __syncthreads();
+                if (last && rank == 0 && tid < 72) {                               // the [T,72] row the script saves: parameters of the LAST forward
+                    float v;
+                    if (tid < 3) v = s_p[tid];
+                    else if (tid < 6) v = a.full_pose[(size_t)s * 165 + (tid - 3)];
+                    else if (tid < 16) v = a.betas[(size_t)s * 10 + (tid - 6)];
+                    else v = s_p[9 + (tid - 16)];
+                    a.p72[((size_t)s * a.T + t) * 72 + tid] = v;
+                }
+                // ------------------------------------------------ P5: blend + skinning + L1 loss on this CTA's marker rows
+                for (int i = tid; i < NJ * 12; i += PM_NT) s_A[i] = a.A[(size_t)s * NJ * 12 + i];
+                s_vec[tid] = a.X[(size_t)s * XK + tid]; s_vec[tid + 256] = a.X[(size_t)s * XK + tid + 256];
+                __syncthreads();
+                {
+                    const int grp = tid >> 6, cc = tid & 63;
+                    float acc = 0.f;
+                    if (cc < ncol)
+                        for (int k = grp; k < XK; k += 4) acc = fmaf(s_vec[k], __ldg(a.Wt + (size_t)k * NC + c0 + cc), acc);
+                    s_red[grp][cc] = acc;
+                }
+                if (tid < nv * 12) {
+                    const int i = tid / 12, k = tid - i * 12;
+                    float acc = 0.f;
+                    for (int j = 0; j < NJ; ++j) acc = fmaf(__ldg(a.wjm + (size_t)j * V + v0 + i), s_A[j * 12 + k], acc);
+                    s_T[i][k] = acc;
+                }
+                __syncthreads();
+                if (tid < ncol) s_vp[tid / 3][tid % 3] = __ldg(a.vt + c0 + tid) + ((s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]));
+                __syncthreads();
+                float lpart = 0.f;
+                if (tid < ncol) {
+                    const int i = tid / 3, r = tid - i * 3;
+                    const float v = s_T[i][r * 4] * s_vp[i][0] + s_T[i][r * 4 + 1] * s_vp[i][1] + s_T[i][r * 4 + 2] * s_vp[i][2] + s_T[i][r * 4 + 3] + s_p[r];
+                    float g = 0.f;
+                    if (v0 + i < 67) {                                              // F.l1_loss on the 67 SSM2 markers (:337-340)
+                        const float d = v - s_tgt[(v0 + i) * 3 + r];
+                        lpart = fabsf(d) * (1.f / 201.f);
+                        g = a.w_rec * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * (1.f / 201.f);
+                    }
+                    s_gv[i][r] = g;
+                }
+                if (warp < 2) {                                                     // ncol <= 33: warps 0 and 1 hold the loss parts
+                    lpart = warp_sum(lpart);
+                    if (lane == 0) s_sc[4 + warp] = lpart;
+                }
+                __syncthreads();
+                // ------------------------------------------------ P6: adjoint on this CTA's rows -> partials of dA, dtransl, dX
+                if (tid < ncol) {
+                    const int i = tid / 3, c = tid - i * 3;
+                    s_dvp[tid] = s_T[i][c] * s_gv[i][0] + s_T[i][4 + c] * s_gv[i][1] + s_T[i][8 + c] * s_gv[i][2];
+                }
+                if (tid < nv * 12) {
+                    const int i = tid / 12, k = tid - i * 12, row = k >> 2, col = k & 3;
+                    s_dT[i][k] = s_gv[i][row] * (col < 3 ? s_vp[i][col] : 1.f);
+                }
+                __syncthreads();
+                {
+                    float* pz = a.dAp + ((size_t)s * PM_CL + rank) * PM_PART;
+                    for (int e = tid; e < NJ * 12; e += PM_NT) {
+                        const int j = e / 12, k = e - j * 12;
+                        float acc = 0.f;
+                        for (int i = 0; i < nv; ++i) acc = fmaf(__ldg(a.wjm + (size_t)j * V + v0 + i), s_dT[i][k], acc);
+                        pz[e] = acc;
+                    }
+                    if (tid < 3) {
+                        float acc = 0.f;
+                        for (int i = 0; i < nv; ++i) acc += s_gv[i][tid];
+                        pz[NJ * 12 + tid] = acc;
+                    }
+                    if (tid == 3) pz[NJ * 12 + 3] = s_sc[4] + s_sc[5];
+                    float* px = a.dXp + ((size_t)s * PM_CL + rank) * XK;
+                    for (int k = tid; k < XK; k += PM_NT) {
+                        const float* w = a.Wt + (size_t)k * NC + c0;
+                        float acc = 0.f;
+                        for (int cc = 0; cc < ncol; ++cc) acc = fmaf(__ldg(w + cc), s_dvp[cc], acc);
+                        px[k] = acc;
+                    }
+                }
+                cluster.sync();
+                // ------------------------------------------------ P7 (every CTA): combine partials in rank order, chain adjoint
+                for (int e = tid; e < PM_PART; e += PM_NT) {
+                    float acc = 0.f;
+                    for (int r = 0; r < PM_CL; ++r) acc += a.dAp[((size_t)s * PM_CL + r) * PM_PART + e];
+                    if (e < NJ * 12) { const int j = e / 12, k = e - j * 12; a.dA[((size_t)j * S + s) * 12 + k] = acc; }
+                    else if (e < NJ * 12 + 3) s_g[e - NJ * 12] = acc;               // d loss / d transl
+                    else s_sc[3] = acc;                                             // marker loss value
+                }
+                for (int k = tid; k < XK; k += PM_NT) {
+                    float acc = 0.f;
+                    for (int r = 0; r < PM_CL; ++r) acc += a.dXp[((size_t)s * PM_CL + r) * XK + k];
+                    a.dX[(size_t)s * XK + k] = acc;
+                }
+                __syncthreads();
+                chain_bwd_body(a.R, a.G, a.Jrest, a.dA, nullptr, a.dX, a.Jd, a.parents, a.depth, a.max_depth, S, 10, a.dR, nullptr, nullptr, s);
+                __syncthreads();
+                pose_to_rot_bwd_body(pk, pg, S, a.full_pose, a.dR, s);
+                __syncthreads();
+                if (tid == 0) gs6d_bwd(s_p + 3, a.dRg + (size_t)s * 9, s_g + 3);
+                if (tid < NBODY) {
+                    float x6[6];
+                    for (int k = 0; k < 6; ++k) x6[k] = a.o[(size_t)s * 126 + tid * 6 + k];
+                    gs6d_bwd(x6, a.dRb + ((size_t)s * NBODY + tid) * 9, s_do + tid * 6);
+                }
+                if (tid >= 32 && tid < 32 + 24) {
+                    const int c = tid - 32;
+                    s_g[41 + c] = c < 12 ? pg.lhand[(size_t)s * 12 + c] : pg.rhand[(size_t)s * 12 + (c - 12)];
+                }
+                __syncthreads();
+                // ------------------------------------------------ P8: dh2 columns [64 rank, +64) = (W3^T d_o) * lrelu'(h2)
+                {
+                    const int nn = tid & 63, og = tid >> 6, n = 64 * rank + nn;
+                    float acc = 0.f;
+                    for (int o = og; o < 126; o += 4) acc = fmaf(__ldg(a.W3 + (size_t)o * 512 + n), s_do[o], acc);
+                    s_red[og][nn] = acc;
+                }
+                __syncthreads();
+                if (tid < 64) {
+                    const int n = 64 * rank + tid;
+                    const float v = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+                    a.dh2[(size_t)s * 512 + n] = v * (s_h2[n] > 0.f ? 1.f : 0.2f);
+                }
+                cluster.sync();
+                // ------------------------------------------------ P9: partial of dh1 = W2^T dh2 over this CTA's rows of W2
+                s_vec[tid] = a.dh2[(size_t)s * 512 + tid]; s_vec[tid + 256] = a.dh2[(size_t)s * 512 + tid + 256];
+                __syncthreads();
+                {
+                    float acc0 = 0.f, acc1 = 0.f;
+                    for (int r = 0; r < 64; ++r) {
+                        const int n = 64 * rank + r;
+                        const float d = s_vec[n];
+                        acc0 = fmaf(__ldg(a.W2 + (size_t)n * 512 + tid), d, acc0);
+                        acc1 = fmaf(__ldg(a.W2 + (size_t)n * 512 + tid + 256), d, acc1);
+                    }
+                    float* ph = a.dh1p + ((size_t)s * PM_CL + rank) * 512;
+                    ph[tid] = acc0; ph[tid + 256] = acc1;
+                }
+                cluster.sync();
+                // ------------------------------------------------ P10 (every CTA): dh1, dz = W1^T dh1, priors, Adam
+                __syncthreads();
+                for (int c = tid; c < 512; c += PM_NT) {
+                    float acc = 0.f;
+                    for (int r = 0; r < PM_CL; ++r) acc += a.dh1p[((size_t)s * PM_CL + r) * 512 + c];
+                    s_vec[c] = acc * (s_h1[c] > 0.f ? 1.f : 0.2f);
+                }
+                __syncthreads();
+                {
+                    const int c = tid & 31, kg = tid >> 5;
+                    float acc = 0.f;
+                    for (int k = kg; k < 512; k += 8) acc = fmaf(__ldg(a.W1 + (size_t)k * 32 + c), s_vec[k], acc);
+                    s_red[kg][c] = acc;
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    float acc = 0.f;
+                    for (int kg = 0; kg < 8; ++kg) acc += s_red[kg][tid];
+                    s_g[9 + tid] = acc + a.w_vp * 2.f * s_p[9 + tid] * (1.f / 32.f);      // + d/dz of w_vposer * mean(z^2)  (:343-346)
+                } else if (tid < 32 + 24) {
+                    const int c = tid - 32;
+                    s_g[41 + c] += a.w_hand * 2.f * s_p[41 + c] * (1.f / 24.f);           // + d of w_hand * mean(hand^2)
+                }
+                __syncthreads();
+                if (last && rank == 0 && tid == 0 && a.acc) {                       // loss terms of the last closure of this frame
+                    float pv = 0.f, ph = 0.f, ps = 0.f;
+                    for (int k = 0; k < 32; ++k) pv += s_p[9 + k] * s_p[9 + k];
+                    for (int k = 0; k < 24; ++k) ph += s_p[41 + k] * s_p[41 + k];
+                    for (int k = 0; k < 10; ++k) { const float b = a.betas[(size_t)s * 10 + k]; ps += b * b; }
+                    float* ac = a.acc + (size_t)s * a.acc_n;
+                    ac[a.acc_rec] = s_sc[3]; ac[a.acc_vp] = pv / 32.f; ac[a.acc_hand] = ph / 24.f; ac[a.acc_shape] = ps / 10.f;
+                }
+                if (tid < 65) {                                                     // torch.optim.Adam.step, identical in every CTA
+                    const float gi = s_g[tid];
+                    const float mi = 0.9f * s_m[tid] + (1.f - 0.9f) * gi;
+                    const float vi = 0.999f * s_v[tid] + (1.f - 0.999f) * gi * gi;
+                    s_m[tid] = mi; s_v[tid] = vi;
+                    s_p[tid] -= (s_sc[0] / s_sc[1]) * (mi / (sqrtf(vi) / s_sc[2] + 1e-8f));
+                }
+                __syncthreads();
+            }
+        }
+        if (tid < 65) a.P[pm_poff(tid, S, s)] = s_p[tid];                           // state after the last step (lemo_fit_get_state)
+        if (tid < 65) a.Gp[pm_poff(tid, S, s)] = s_g[tid];
+        __syncthreads();
+    }
+}
+
+}  // namespace lemo
