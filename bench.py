@@ -530,7 +530,19 @@ def main():
             t0 = time.perf_counter()
             ri.get_local_markers_4chan(body68, con68)
             host_ms = (time.perf_counter() - t0) * 1e3
-        infill = {'workload': 'opt_amass_temp.py:141-325 for one 120-frame clip: get_local_markers_4chan + normalise, mask + reflect pad, 60 AE '
+        # S clips of a batch fine-tuned concurrently (one stage + stream per clip, InfillPool)
+        from lemo_b200.infill import InfillPool
+        pool = InfillPool(load_infill_prior(), n_streams=S, device=dev, stats=st64)
+        clip0, rot00 = body_repr(b_d, c_d, stats=st64, device=dev)
+        pool.run_many([clip0] * S, [rot00] * S)
+        torch.cuda.synchronize(dev)
+        c0.record()
+        pool.run_many([clip0] * S, [rot00] * S)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        pool_ms = c0.elapsed_time(c1) / S
+        del pool
+        infill = {'ms_per_clip_batched': pool_ms, 'clips_per_sec_batched': 1e3 / pool_ms, 'batch': S, 'workload': 'opt_amass_temp.py:141-325 for one 120-frame clip: get_local_markers_4chan + normalise, mask + reflect pad, 60 AE '
                               'fine-tune steps (Adam lr 3e-6, 4.1 M weights), inference, labels, de-normalise, reconstruct_global_body',
                   'ms_per_clip': inf_ms, 'clips_per_sec': 1e3 / inf_ms, 'finetune_steps': 60,
                   'cpu_repr_only_ms': host_ms, 'note': 'AE weights = shipped runs/59547; synthetic marker clip'}

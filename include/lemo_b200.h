@@ -271,7 +271,8 @@ int lemo_fit_set_sequences(LemoFit* fit, const float* init72, const float* marke
 /* n_iters Adam iterations with the script's LR schedule (lr0 until step>lr_switch, then lr1).
  * Entirely on device: no host synchronisation inside. */
 int lemo_fit_run(LemoFit* fit, int32_t n_iters, float lr0, float lr1, int32_t lr_switch, void* stream);
-/* per-frame mode: runs all T frames x n_iters of sequence-parallel B=1 problems (lr .1/.01 -> .01@>60 -> .003@>80) */
+/* per-frame mode: runs all T frames x n_iters of sequence-parallel B=1 problems (lr .1/.01 -> .01@>60 -> .003@>80).  Default: one
+ * persistent kernel launch, one 8-CTA thread-block cluster per sequence, no host involvement until the last frame is done. */
 int lemo_fit_run_perframe(LemoFit* fit, int32_t n_iters, void* stream);
 /* results: params72 [S,T,72] as of the LAST forward (what the scripts save), losses [S,8] of the last iteration
  * (total, rec, vposer, shape, hand, contact, smooth, reserved) */
@@ -280,6 +281,9 @@ int lemo_fit_get(LemoFit* fit, float* params72, float* losses, void* stream);
 int lemo_fit_get_state(LemoFit* fit, float* transl, float* rot6d, float* other, float* g_transl, float* g_rot6d,
                        float* g_other, void* stream);
 int64_t lemo_fit_kernel_launches(const LemoFit* fit);   /* kernels enqueued by this handle so far */
+/* A/B switch for lemo_fit_run_perframe: 1 = persistent cluster kernel (default: ONE launch for all frames x all steps, csrc/perframe_mega.cuh),
+ * 0 = one CUDA graph of ~23 kernels per step (the round-1 path), -1 = back to the default / LEMO_PERFRAME=graph.  Debug/measurement only. */
+int lemo_debug_set_perframe(int32_t mode);
 
 /* ---------------------------------------------------------------- fused PROX stage-2 driver ------------ */
 /* One B-frame sliding window of temp_prox: FittingMonitor.run_fitting + create_fitting_closure.fitting_func

@@ -166,6 +166,7 @@ SIGNATURES = {
     'lemo_fit_get': (C.c_int, [_P, _P, _P, _P]),
     'lemo_fit_get_state': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'lemo_fit_kernel_launches': (_L, [_P]),
+    'lemo_debug_set_perframe': (C.c_int, [_I]),
     'lemo_fit_prox_create': (C.c_int, [_P, _P, _P, C.POINTER(LemoProxConfigC), C.c_int, C.POINTER(_P)]),
     'lemo_fit_prox_destroy': (C.c_int, [_P]),
     'lemo_fit_prox_set_weights': (C.c_int, [_P, C.POINTER(LemoProxWeightsC), _I, _P]),

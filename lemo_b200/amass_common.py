@@ -16,7 +16,7 @@ import torch
 from . import synth
 from . import smplx as smplx_mod
 from .vposer import VPoserDecoder
-from .infill import InfillStage, body_repr, load_infill_prior, load_infill_stats
+from .infill import InfillStage, InfillPool, body_repr, load_infill_prior, load_infill_stats
 from .models.AE import AE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -117,17 +117,25 @@ def synthetic_dataloader(n_clips, T_frames, device):
 def infill_all(args, dataloader, device):
     """The inference stage with self-supervised fine-tuning (opt_amass_temp.py:144-221) + the per-clip post-processing
     (:262-325), on the device.  -> list of dicts(markers_rec [T,67,3], contact [T,4], beta [10], gender int) and the gender array."""
-    stage = InfillStage(load_infill_model(args), device=device, stats=load_infill_stats())
-    clips, genders = [], []
+    pool = InfillPool(load_infill_model(args), n_streams=max(1, min(8, args.seqs_per_batch)), device=device, stats=load_infill_stats())
+    clips, genders, pending = [], [], []
+
+    def flush():
+        outs = pool.run_many([p[0] for p in pending], [p[1] for p in pending])          # a batch of clips fine-tuned concurrently
+        for (clip_img, rot0, beta, gender), (m_rec, con, _) in zip(pending, outs):
+            clips.append(dict(markers_rec=m_rec, contact=con, beta=beta, gender=gender))
+            genders.append(gender)
+        pending.clear()
     for step, data in enumerate(dataloader):
         if step == args.end:
             break
         clip_img, smplx_beta, gender, rot_0_pivot = data[0], data[1], data[2], data[3]
-        clip_img = torch.as_tensor(clip_img).to(device)
-        m_rec, con, _ = stage.run(clip_img[0], torch.as_tensor(rot_0_pivot).reshape(-1)[0:1])
-        clips.append(dict(markers_rec=m_rec, contact=con, beta=torch.as_tensor(smplx_beta).reshape(-1)[:10].float().to(device),
-                          gender=int(torch.as_tensor(gender).reshape(-1)[0])))
-        genders.append(int(torch.as_tensor(gender).reshape(-1)[0]))
+        pending.append((torch.as_tensor(clip_img).to(device)[0], torch.as_tensor(rot_0_pivot).reshape(-1)[0:1],
+                        torch.as_tensor(smplx_beta).reshape(-1)[:10].float().to(device), int(torch.as_tensor(gender).reshape(-1)[0])))
+        if len(pending) == len(pool.stages):
+            flush()
+    if pending:
+        flush()
     return clips, np.asarray(genders).reshape(-1, 1)
 
 

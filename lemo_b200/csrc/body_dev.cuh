@@ -296,22 +296,4 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
 }
 
 
-__global__ void __launch_bounds__(64) k_pose_to_rot_bwd(PoseK p, PoseGrad g, int B, const float* __restrict__ full_pose, const float* __restrict__ dR) {
-    pose_to_rot_bwd_body(p, g, B, full_pose, dR, blockIdx.x);
-}
-__global__ void __launch_bounds__(64) k_pose_chain_fwd(PoseK p, const float* __restrict__ J_template, const float* __restrict__ J_dirs,
-                                                       const int* __restrict__ parents, const int* __restrict__ depth, int max_depth,
-                                                       float* __restrict__ full_pose, float* __restrict__ R, float* __restrict__ X,
-                                                       float* __restrict__ X2, float* __restrict__ G, float* __restrict__ A,
-                                                       float* __restrict__ Jrest, float* __restrict__ Jposed, float* __restrict__ A2) {
-    pose_chain_fwd_body(p, J_template, J_dirs, parents, depth, max_depth, full_pose, R, X, X2, G, A, Jrest, Jposed, A2, blockIdx.x);
-}
-__global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
-                                                  const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
-                                                  const float* __restrict__ J_dirs, const int* __restrict__ parents,
-                                                  const int* __restrict__ depth, int max_depth, int B, int betas_stride,
-                                                  float* __restrict__ dR, float* __restrict__ dbetas, float* __restrict__ dexpr) {
-    chain_bwd_body(R, G, Jrest, dA, dJp, dX, J_dirs, parents, depth, max_depth, B, betas_stride, dR, dbetas, dexpr, blockIdx.x);
-}
-
 }  // namespace lemo

@@ -459,10 +459,10 @@ int lemo_fit_run(LemoFit* h, int32_t n_iters, float lr0, float lr1, int32_t lr_s
 }
 
 // LEMO_PERFRAME=graph selects the round-1 path (one CUDA graph of ~23 kernels per step); default = the persistent cluster kernel
+static int g_perframe_mode = -1;
 static bool perframe_mega_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("LEMO_PERFRAME"); on = (e && strcmp(e, "graph") == 0) ? 0 : 1; }
-    return on != 0;
+    if (g_perframe_mode < 0) { const char* e = getenv("LEMO_PERFRAME"); g_perframe_mode = (e && strcmp(e, "graph") == 0) ? 0 : 1; }
+    return g_perframe_mode != 0;
 }
 
 static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
@@ -492,6 +492,8 @@ static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
     f->launches += 1;
     return 0;
 }
+
+int lemo_debug_set_perframe(int32_t mode) { g_perframe_mode = mode; return 0; }
 
 int lemo_fit_run_perframe(LemoFit* h, int32_t n_iters, void* stream) {
     LEMO_CHECK(h && h->f.mode == 1 && n_iters >= 0, "lemo_fit_run_perframe is the per-frame-mode driver");

@@ -107,3 +107,37 @@ class InfillStage:
         for t in (rec, x, rot0, ws):
             t.record_stream(torch.cuda.current_stream(self.device))
         return (m_rec, con, m_in, losses) if return_losses else (m_rec, con, m_in)
+
+
+class InfillPool:
+    """S InfillStages with their own AE weights, scratch and CUDA stream: the fine-tune of one clip under-fills a B200 (deep AE levels
+    are 16x16 planes), so the clips of a batch are fine-tuned CONCURRENTLY -- each stage's captured step graph replays on its own
+    stream and the SMs interleave them.  Same per-clip arithmetic as InfillStage.run (bitwise: every clip has its own handle)."""
+
+    def __init__(self, ae: AE, n_streams=8, device='cuda', stats=None, finetune_steps=60, lr=3e-6):
+        self.device = torch.device(device)
+        sd = ae.state_dict()
+        self.stages, self.streams = [], []
+        for _ in range(max(1, n_streams)):
+            m = AE(downsample=True, in_channel=ae.in_channel, kernel=3)
+            m.load_state_dict(sd)
+            self.stages.append(InfillStage(m, device=self.device, stats=stats, finetune_steps=finetune_steps, lr=lr))
+            self.streams.append(torch.cuda.Stream(device=self.device))
+
+    def run_many(self, clip_imgs, rot0s):
+        """clip_imgs: sequence of [4,208,T] tensors; rot0s: sequence of rot_0_pivot values.  -> list of (markers_rec, contact, markers_in),
+        in input order.  The caller's current stream waits for all of them."""
+        cur = torch.cuda.current_stream(self.device)
+        outs = [None] * len(clip_imgs)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for i, (clip, rot0) in enumerate(zip(clip_imgs, rot0s)):
+            k = i % len(self.stages)
+            with torch.cuda.stream(self.streams[k]):
+                outs[i] = self.stages[k].run(clip, rot0)
+        for st in self.streams:
+            cur.wait_stream(st)
+        for o in outs:
+            for t in o:
+                t.record_stream(cur)
+        return outs

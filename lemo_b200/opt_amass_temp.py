@@ -80,7 +80,7 @@ class Pipeline:
 
     def __init__(self, smplx_model, vposer, infill_ae, enc, S, T, device='cuda', perframe_steps=100, temporal_steps=100):
         self.S, self.T, self.device = S, T, torch.device(device)
-        self.stage = ac.InfillStage(infill_ae, device=self.device, stats=ac.load_infill_stats())
+        self.pool = ac.InfillPool(infill_ae, n_streams=min(S, 8), device=self.device, stats=ac.load_infill_stats())
         self.pf = PerFrameFitter(smplx_model, vposer, S, T, device=self.device)
         self.tf = TemporalFitter(smplx_model, vposer, S, T, enc=enc, device=self.device)
         self.perframe_steps, self.temporal_steps = perframe_steps, temporal_steps
@@ -88,11 +88,10 @@ class Pipeline:
     def run(self, clip_imgs, rot0s, betas):
         """clip_imgs [S,4,208,T], rot0s [S], betas [S,10] -> (params72 [S,T,72] temporal result, contact [S,T,4]); asynchronous."""
         S = self.S
-        recs, cons = [], []
+        outs = self.pool.run_many([clip_imgs[s] for s in range(S)], [rot0s[s:s + 1] for s in range(S)])     # S clips fine-tuned concurrently
+        recs, cons = [o[0] for o in outs], [o[1] for o in outs]
         for s in range(S):
-            m_rec, con, _ = self.stage.run(clip_imgs[s], rot0s[s:s + 1])
-            recs.append(m_rec); cons.append(con)
-            self.pf.set_sequence(s, betas[s].detach().cpu().numpy() if torch.is_tensor(betas) else betas[s], m_rec)
+            self.pf.set_sequence(s, betas[s].detach().cpu().numpy() if torch.is_tensor(betas) else betas[s], recs[s])
         self.pf.run(n_iters=self.perframe_steps)
         init72, _ = self.pf.results()
         self.tf.set_sequences(init72, torch.stack(recs), torch.stack(cons))

@@ -127,6 +127,61 @@ def test_perframe_tracks_oracle():
             assert float(losses[0, 0]) < 0.5 * tr[0]
 
 
+def test_perframe_persistent_kernel_vs_graph_path():
+    """The persistent cluster kernel (default) and the per-step CUDA-graph path run the same loop: same parameters after a short run
+    (they differ only in the blend arithmetic -- fp32 in the persistent kernel, TF32 tensor cores in the graph path -- and in summation
+    order), the same loss level after a full frame, and every sequence slot of the persistent kernel is bitwise identical."""
+    from lemo_b200 import _lib
+    from lemo_b200.fit import PerFrameFitter
+    c32 = oracle_ctx(torch.float32)
+    clean, _, _ = synth.make_sequence(2, T=4)
+    with torch.no_grad():
+        v, _ = rb.gen_body_mesh(torch.from_numpy(clean), c32.smplx, c32.vposer)
+    mrec = v[:, c32.m67].numpy()
+    res = {}
+    for mode in (1, 0):
+        _lib.call('lemo_debug_set_perframe', mode)
+        out = {}
+        for n_it in (4, 100):
+            fit = PerFrameFitter(smplx_module(), vposer_module(), 3, 4, device=DEV)
+            for s in range(3):
+                fit.set_sequence(s, clean[0, 6:16], mrec)
+            fit.run(n_iters=n_it)
+            p72, losses = fit.results()
+            out[n_it] = (p72.cpu().numpy(), losses.cpu().numpy(), fit.kernel_launches())
+        res[mode] = out
+    _lib.call('lemo_debug_set_perframe', -1)
+    assert res[1][100][2] == 1 and res[0][100][2] > 1000                     # ONE launch for 4 frames x 100 steps vs one graph per step
+    a, b = res[1][4][0], res[0][4][0]
+    assert np.array_equal(a[0], a[1]) and np.array_equal(a[0], a[2])         # slots are independent and identical
+    assert np.abs(a - b).max() < 3e-3, np.abs(a - b).max()                   # 4 steps of lr 0.1: still together
+    ref = rl.fit_perframe(mrec, clean[0, 6:16], c32, n_frames=4, n_iters=4)
+    assert np.abs(a[0] - ref).max() < 3e-3, np.abs(a[0] - ref).max()
+    la, lb = res[1][100][1][0], res[0][100][1][0]
+    assert abs(la[0] - lb[0]) < 0.3 * abs(lb[0]) + 1e-3 and la[0] < 0.05     # same loss level at the end of the last frame
+    assert np.allclose(la[2:5], lb[2:5], rtol=0.3, atol=1e-3)
+
+
+def test_infill_pool_equals_single_stage():
+    """InfillPool (clips of a batch fine-tuned concurrently on their own streams / handles) returns, clip by clip, exactly what one
+    InfillStage returns: the fine-tune is deterministic (fixed-order split-K and weight-gradient reductions)."""
+    from lemo_b200.infill import InfillStage, InfillPool, body_repr, load_infill_prior, load_infill_stats
+    st64 = load_infill_stats()
+    clips = []
+    for s in range(3):
+        b68, c68 = synth.synth_marker_clip(40 + s, T=40)
+        clips.append(body_repr(torch.from_numpy(b68).to(DEV), torch.from_numpy(c68).to(DEV), stats=st64, device=DEV))
+    single = InfillStage(load_infill_prior(), device=DEV, stats=st64, finetune_steps=6)
+    want = [single.run(c, r) for c, r in clips]
+    again = [single.run(c, r) for c, r in clips]
+    pool = InfillPool(load_infill_prior(), n_streams=2, device=DEV, stats=st64, finetune_steps=6)
+    got = pool.run_many([c for c, _ in clips], [r for _, r in clips])
+    torch.cuda.synchronize()
+    for w, a2, g in zip(want, again, got):
+        assert torch.equal(w[0], a2[0])                                      # bitwise repeatable
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1])
+
+
 def test_full_size_property_rest_pose_zero_loss():
     """Size-independent property at BASELINE's full size: targets generated from the init => rec loss 0, grads of rec term vanish,
     and the loss decreases monotonically-ish afterwards."""

@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -80 ) > gpurun_out/pytest_gpu.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_stages.csv python tools/run_stage.py prox infill > gpurun_out/stages_under_ncu.log 2>&1
-timeout 1200 python bench.py --skip-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-tail -c 2500 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench_n1.err
+( timeout 900 python -m pytest tests/test_gpu_fit.py tests/test_scripts_surface.py tests/test_gpu_body.py -m gpu -q 2>&1 | tail -60 ) > gpurun_out/pytest_a.log 2>&1
+tail -c 2500 gpurun_out/pytest_a.log
+( timeout 900 python -m pytest tests/test_gpu_loops_baseline.py -m gpu -q -k perframe 2>&1 | tail -40 ) > gpurun_out/pytest_b.log 2>&1
+tail -c 1500 gpurun_out/pytest_b.log
+timeout 1200 python bench.py --skip-cpu-baseline --skip-prox > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+tail -3 gpurun_out/bench_n1.err
