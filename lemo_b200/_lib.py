@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, '_build', 'liblemo_b200.so')
 HEADER = os.path.join(_HERE, '..', 'include', 'lemo_b200.h')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-shared', '-ldl']
 
 
 def sources():

@@ -403,6 +403,7 @@ extern "C" {
 
 int lemo_ae_finetune_step(LemoConvNet* h, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr, int32_t t,
                           float* loss_out, void* stream) {
+    LEMO_NVTX("lemo_ae_finetune_step");
     LEMO_CHECK(h && h->n->kind == 1 && x && row_mask && h->n->with_backward && t >= 1 && n_rows_selected > 0, "bad arguments");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;
@@ -449,6 +450,7 @@ static int ae_finetune_graph_step(ConvNet* n, cudaStream_t st) {
 
 int lemo_ae_finetune_run(LemoConvNet* h, const float* x, const float* row_mask, int32_t n_rows_selected, int32_t N, double lr, int32_t steps,
                          float* losses_out, void* stream) {
+    LEMO_NVTX("lemo_ae_finetune_run");
     LEMO_CHECK(h && h->n->kind == 1 && x && row_mask && h->n->with_backward && steps >= 0 && n_rows_selected > 0, "bad arguments");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;
@@ -498,6 +500,7 @@ int lemo_ae_finetune_run(LemoConvNet* h, const float* x, const float* row_mask, 
 }
 
 int lemo_ae_forward(LemoConvNet* h, const float* x, int32_t N, float* rec, float* z, void* stream) {
+    LEMO_NVTX("lemo_ae_forward");
     LEMO_CHECK(h && h->n->kind == 1 && x && rec, "bad arguments (need an AE handle)");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;

@@ -58,6 +58,7 @@ int lemo_body_destroy(LemoBody* body) {
 }
 
 int lemo_smplx_forward(LemoBody* body, const LemoPoseC* pose, int32_t B, float* verts, float* joints, float* full_pose, void* stream) {
+    LEMO_NVTX("lemo_smplx_forward");
     LEMO_CHECK(body && pose && verts, "null argument");
     const PoseIn in = to_posein(pose);
     LEMO_CHECK(in.betas_stride != 0 || in.betas, "betas_shared needs a betas pointer");
@@ -70,6 +71,7 @@ int lemo_smplx_forward(LemoBody* body, const LemoPoseC* pose, int32_t B, float* 
 
 int lemo_smplx_backward(LemoBody* body, const LemoPoseC* pose, int32_t B, const float* d_verts, const float* d_joints,
                         const LemoPoseGradC* grads, void* stream) {
+    LEMO_NVTX("lemo_smplx_backward");
     LEMO_CHECK(body && pose && grads, "null argument");
     LEMO_CHECK(B > 0 && B <= body->c->maxB, "batch exceeds the size this body handle was created for");
     const PoseIn in = to_posein(pose);
@@ -110,10 +112,12 @@ int lemo_vposer_destroy(LemoVPoser* vp) {
     return 0;
 }
 int lemo_vposer_decode(LemoVPoser* vp, const float* z, int32_t B, float* R_body, float* aa, void* stream) {
+    LEMO_NVTX("lemo_vposer_decode");
     LEMO_CHECK(vp, "null handle");
     return vposer_decode(vp->v, z, B, R_body, aa, ST(stream));
 }
 int lemo_vposer_decode_backward(LemoVPoser* vp, const float* z, int32_t B, const float* dR_body, float* dz, void* stream) {
+    LEMO_NVTX("lemo_vposer_decode_backward");
     LEMO_CHECK(vp, "null handle");
     return vposer_decode_backward(vp->v, z, B, dR_body, dz, ST(stream));
 }

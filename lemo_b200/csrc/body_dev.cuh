@@ -6,6 +6,15 @@
 
 namespace lemo {
 
+// Barrier of the pose / chain bodies.  SUB64 = false: the whole CTA (stand-alone kernels, 64 threads).  SUB64 = true: named barrier 1
+// over the first 64 threads only -- the persistent per-frame kernel calls the bodies from its warps 0-1 while warps 2-7 wait at the
+// next CTA-wide barrier, so the ~20 level barriers of a chain walk are two-warp barriers instead of eight-warp ones.
+template <bool SUB64>
+__device__ __forceinline__ void body_sync() {
+    if (SUB64) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else body_sync<SUB64>();
+}
+
 // =============================================================================================
 // pose -> rotation matrices        (one thread per (frame, joint))
 // =============================================================================================
@@ -42,6 +51,7 @@ __device__ __forceinline__ void joint_aa(const PoseK& p, int b, int j, float* aa
 }
 
 // adjoint: dR -> parameter gradients.  One block (64 threads) per frame.
+template <bool SUB64 = false>
 __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseGrad& g, int B, const float* __restrict__ full_pose,
                                                      const float* __restrict__ dR, int b) {
     __shared__ float s_daa[NJ * 3];
@@ -74,7 +84,7 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
             if (o) for (int k = 0; k < 3; ++k) o[k] = daa[k];
         }
     }
-    __syncthreads();
+    body_sync<SUB64>();
     if (p.in.hand_is_pca && j < 2 * p.npc) {
         const bool left = j < p.npc;
         const int c = left ? j : j - p.npc;
@@ -99,6 +109,7 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
 // (Two kernels -- one thread per (frame, joint), then this block shape -- cost 5.5 + 8 us per forward at B=120; forking the chain
 // onto a side stream beside the blend GEMM was measured too: the fork/join edges cost what the overlap saves.)
 // =============================================================================================
+template <bool SUB64 = false>
 __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float* __restrict__ J_template,
                                                     const float* __restrict__ J_dirs, const int* __restrict__ parents,
                                                     const int* __restrict__ depth, int max_depth, float* __restrict__ full_pose,
@@ -138,8 +149,8 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
         if (j >= 1)
             for (int k = 0; k < 9; ++k) sX[(j - 1) * 9 + k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < XK; k += blockDim.x) {
+    body_sync<SUB64>();
+    for (int k = threadIdx.x; k < XK; k += (SUB64 ? 64 : blockDim.x)) {
         const float x = sX[k];
         uint32_t t;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));       // round to nearest: k_blend_v2 multiplies most columns by Xhi alone
@@ -160,7 +171,7 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
         }
         par = parents[j]; dep = depth[j];
     }
-    __syncthreads();
+    body_sync<SUB64>();
     for (int lev = 0; lev <= max_depth; ++lev) {
         if (j < NJ && dep == lev) {
             float g[12];
@@ -177,7 +188,7 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
             }
             for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
         }
-        __syncthreads();
+        body_sync<SUB64>();
     }
     if (j < NJ) {
         const float* g = sG[j];
@@ -204,6 +215,7 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
 
 // adjoint of k_chain_fwd.  dA is joint-major [55][B*12]; dJp [B,55,3]; dX [B,512].
 // Writes dR [B,55,9]; betas/expression grads (per frame, or atomically into one row when betas_stride==0).
+template <bool SUB64 = false>
 __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
                                                const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
                                                const float* __restrict__ J_dirs, const int* __restrict__ parents,
@@ -234,7 +246,7 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
         for (int c = 0; c < 3; ++c) sdJ[j][c] = -(gl[c] * dAt[0] + gl[4 + c] * dAt[1] + gl[8 + c] * dAt[2]);
     }
     if (j < NJ) spar[j] = par;
-    __syncthreads();
+    body_sync<SUB64>();
     unsigned long long kids = 0ull;   // children of joint j as a bit mask, walked in ascending order below
     if (j < NJ)
         for (int c = j + 1; c < NJ; ++c)
@@ -263,7 +275,7 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
                 sdJ[j][i] += dt[i];
             }
         }
-        __syncthreads();
+        body_sync<SUB64>();
         if (j < NJ && dep == lev - 1) {
             for (unsigned long long m = kids; m; m &= m - 1) {
                 const int c = __ffsll((long long)m) - 1;
@@ -271,7 +283,7 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
                 for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
             }
         }
-        __syncthreads();
+        body_sync<SUB64>();
     }
     if (j == 0) {
         float* o = dR + ((size_t)b * NJ) * 9;
@@ -280,9 +292,9 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
             sdJ[0][i] += sdG[0][i * 4 + 3];
         }
     }
-    __syncthreads();
-    // betas / expression: direct (X columns) + through Jrest
-    if (j < NBETA) {
+    body_sync<SUB64>();
+    // betas / expression: direct (X columns) + through Jrest (skipped when neither gradient is requested: 165 loads per thread)
+    if (j < NBETA && (dbetas || dexpr)) {
         float acc = dX[(size_t)b * XK + NPF + j];
         for (int q = 0; q < NJ; ++q)
             for (int k = 0; k < 3; ++k) acc = fmaf(J_dirs[(q * 3 + k) * NBETA + j], sdJ[q][k], acc);

@@ -283,12 +283,14 @@ int lemo_scene_destroy(LemoScene* s) {
     return 0;
 }
 int lemo_scene_query(const LemoScene* s, const float* xyz1, int32_t B, int32_t n, float* dist1, int32_t* idx1, void* stream) {
+    LEMO_NVTX("lemo_scene_query");
     LEMO_CHECK(s && s->g, "null scene");
     return scene_grid_query(s->g, xyz1, (long long)n * 3, n, B, dist1, idx1, (cudaStream_t)stream);
 }
 
 int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m, int64_t xyz2_batch_stride, float* dist1,
                          float* dist2, int32_t* idx1, int32_t* idx2, void* stream) {
+    LEMO_NVTX("lemo_chamfer_forward");
     LEMO_CHECK(xyz1 && xyz2 && dist1 && idx1 && B > 0 && n > 0 && m > 0, "bad arguments");
     LEMO_CHECK((dist2 == nullptr) == (idx2 == nullptr), "dist2 and idx2 must both be given or both be NULL");
     LEMO_CHECK(xyz2_batch_stride == 0 || xyz2_batch_stride >= (int64_t)m * 3, "xyz2_batch_stride must be 0 (shared) or >= 3*m");
@@ -304,6 +306,7 @@ int lemo_chamfer_forward(const float* xyz1, int32_t B, int32_t n, const float* x
 int lemo_chamfer_backward(const float* xyz1, int32_t B, int32_t n, const float* xyz2, int32_t m, int64_t xyz2_batch_stride,
                           const float* g_dist1, const float* g_dist2, const int32_t* idx1, const int32_t* idx2, float* d_xyz1,
                           float* d_xyz2, void* stream) {
+    LEMO_NVTX("lemo_chamfer_backward");
     LEMO_CHECK(xyz1 && xyz2 && g_dist1 && idx1 && d_xyz1 && d_xyz2, "null argument");
     LEMO_CHECK((g_dist2 == nullptr) == (idx2 == nullptr), "g_dist2 and idx2 must both be given or both be NULL");
     cudaStream_t st = (cudaStream_t)stream;

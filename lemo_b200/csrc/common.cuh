@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string>
+#include <nvtx3/nvToolsExt.h>
 
 #ifndef __CUDACC__
 #define __host__
@@ -49,6 +50,14 @@ void set_error(const std::string& s);
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// NVTX range over a C-ABI entry point (header-only nvtx3: a no-op unless a tool such as nsys / ncu --nvtx is attached), so a timeline
+// shows the reference-level operations (lemo_fit_run, lemo_fit_prox_run, lemo_ae_finetune_run, ...) around the kernels they enqueue.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define LEMO_NVTX(name) lemo::NvtxRange _lemo_nvtx_range(name)
 
 // ---------------------------------------------------------------- 3x3 helpers (row-major float[9])
 HD void m3_mul(const float* a, const float* b, float* c) {          // c = a b

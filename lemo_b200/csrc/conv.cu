@@ -484,6 +484,7 @@ int lemo_convnet_get_weights(LemoConvNet* h, float* w, void* stream) {
     return 0;
 }
 int lemo_enc_forward(LemoConvNet* h, const float* x, int32_t N, float* z, void* stream) {
+    LEMO_NVTX("lemo_enc_forward");
     LEMO_CHECK(h && h->n->kind == 0 && x && z, "bad arguments");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;
@@ -531,6 +532,7 @@ int lemo_convnet_profile_layer(LemoConvNet* h, int32_t layer, int32_t N, int32_t
     return 0;
 }
 int lemo_enc_backward_input(LemoConvNet* h, const float* dz, int32_t N, float* dx, void* stream) {
+    LEMO_NVTX("lemo_enc_backward_input");
     LEMO_CHECK(h && h->n->kind == 0 && dz && dx && h->dx_planes, "bad arguments / handle created without backward");
     ConvNet* n = h->n;
     cudaStream_t st = (cudaStream_t)stream;

@@ -15,6 +15,7 @@
 #include "fit_common.cuh"
 #include "perframe_mega.cuh"
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include "../../include/lemo_b200.h"
 #include <vector>
@@ -451,6 +452,7 @@ static int fit_begin_run(Fit* f, float lr0, float lr1, float lr2, int sw1, int s
 }
 
 int lemo_fit_run(LemoFit* h, int32_t n_iters, float lr0, float lr1, int32_t lr_switch, void* stream) {
+    LEMO_NVTX("lemo_fit_run");
     LEMO_CHECK(h && h->f.mode == 0 && n_iters >= 0, "lemo_fit_run is the temporal-mode driver");
     Fit* f = &h->f;
     cudaStream_t st = (cudaStream_t)stream;
@@ -477,18 +479,35 @@ static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
     a.W1 = v->W1; a.b1 = v->b1; a.W2 = v->W2; a.b2 = v->b2; a.W3 = v->W3; a.b3 = v->b3;
     a.h1 = v->h1; a.h2 = v->h2; a.o = v->o; a.dh2 = v->dh2;
     a.dh1p = f->pf_ws; a.dXp = a.dh1p + (size_t)S * PM_CL * 512; a.dAp = a.dXp + (size_t)S * PM_CL * 512;
-    BodyCtx* c = f->ctx;
-    a.full_pose = c->full_pose; a.R = c->R; a.X = c->X; a.G = c->G; a.A = c->A; a.Jrest = c->Jrest; a.Jposed = c->Jposed;
-    a.dA = c->dA; a.dX = c->dX; a.dR = c->dR;
-    a.Rg = f->Rg; a.Rb = f->Rb; a.dRg = f->dRg; a.dRb = f->dRb;
     a.P = f->P; a.Gp = f->Gp; a.betas = f->betas; a.mrec = f->mrec; a.p72 = f->p72; a.acc = f->acc;
     a.acc_n = ACC_N; a.acc_rec = ACC_REC; a.acc_vp = ACC_VP; a.acc_shape = ACC_SHAPE; a.acc_hand = ACC_HAND;
     a.S = S; a.T = f->T; a.n_iters = n_iters;
     a.w_rec = f->cfg.w_rec; a.w_vp = f->cfg.w_vposer; a.w_shape = f->cfg.w_shape; a.w_hand = f->cfg.w_hand;
     LEMO_CUDA(cudaMemsetAsync(f->acc, 0, (size_t)S * ACC_N * sizeof(float), st));
+    static unsigned long long* d_tl = nullptr;           // LEMO_PERFRAME_TL=1: phase timeline of one step (debug; printed after a sync)
+    static int want_tl = -1;
+    if (want_tl < 0) { const char* e = getenv("LEMO_PERFRAME_TL"); want_tl = (e && e[0] == '1') ? 1 : 0; }
+    if (want_tl && !d_tl) { LEMO_CUDA(cudaMalloc((void**)&d_tl, 32 * sizeof(unsigned long long))); LEMO_CUDA(cudaMemset(d_tl, 0, 32 * 8)); }
+    a.tl = want_tl ? d_tl : nullptr;
     const int nclusters = std::min(S, 16);           // 8-CTA clusters: two per GPC; more sequences than that are walked in turn
-    k_perframe_mega<<<PM_CL * nclusters, PM_NT, 0, st>>>(a);
+    static bool configured = false;
+    if (!configured) {
+        LEMO_CUDA(cudaFuncSetAttribute(k_perframe_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PM_DYN_BYTES));
+        configured = true;
+    }
+    k_perframe_mega<<<PM_CL * nclusters, PM_NT, PM_DYN_BYTES, st>>>(a);
     LEMO_CUDA(cudaGetLastError());
+    if (want_tl && n_iters > 5) {
+        unsigned long long h[32];
+        LEMO_CUDA(cudaStreamSynchronize(st));
+        LEMO_CUDA(cudaMemcpy(h, d_tl, sizeof(h), cudaMemcpyDeviceToHost));
+        const char* names[19] = {"P1 fc1", "sync1", "P2 load h1 + fc2", "sync2", "P3 out", "sync3", "P4 gs + pose/chain fwd", "P5 blend/skin/loss",
+                                 "P6 adjoint partials", "sync4", "P7 combine", "chain_bwd", "pose_to_rot_bwd + gs_bwd", "P8 dh2", "sync5", "P9 dh1 partial",
+                                 "sync6", "P10 dh1/dz/priors", "adam"};
+        printf("[perframe timeline] step 5 of frame 0, cluster 0 rank 0 (ns):");
+        for (int i = 0; i < 18; ++i) printf(" %s %llu |", names[i], h[i + 1] - h[i]);
+        printf(" total to adam %llu\n", h[18] - h[0]);
+    }
     f->launches += 1;
     return 0;
 }
@@ -496,6 +515,7 @@ static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
 int lemo_debug_set_perframe(int32_t mode) { g_perframe_mode = mode; return 0; }
 
 int lemo_fit_run_perframe(LemoFit* h, int32_t n_iters, void* stream) {
+    LEMO_NVTX("lemo_fit_run_perframe");
     LEMO_CHECK(h && h->f.mode == 1 && n_iters >= 0, "lemo_fit_run_perframe is the per-frame-mode driver");
     Fit* f = &h->f;
     cudaStream_t st = (cudaStream_t)stream;

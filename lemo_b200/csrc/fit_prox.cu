@@ -576,6 +576,7 @@ static int copy_block(float* dst, const float* src, size_t n, cudaStream_t st) {
 }
 
 int lemo_fit_prox_set_window(LemoProxFit* h, const LemoProxWindowC* w, void* stream) {
+    LEMO_NVTX("lemo_fit_prox_set_window");
     LEMO_CHECK(h && w, "null argument");
     LEMO_CHECK(w->gt_joints && w->joint_weights, "gt_joints and joint_weights are required");
     ProxFit* f = &h->f;
@@ -609,6 +610,7 @@ static int prox_begin(ProxFit* f, float lr, bool reset_moments, cudaStream_t st)
 }
 
 int lemo_fit_prox_run(LemoProxFit* h, int32_t n_iters, float lr, int32_t resume, void* stream) {
+    LEMO_NVTX("lemo_fit_prox_run");
     LEMO_CHECK(h && n_iters >= 0, "bad arguments");
     ProxFit* f = &h->f;
     cudaStream_t st = (cudaStream_t)stream;
@@ -643,6 +645,7 @@ int lemo_fit_prox_run(LemoProxFit* h, int32_t n_iters, float lr, int32_t resume,
 }
 
 int lemo_fit_prox_eval(LemoProxFit* h, void* stream) {
+    LEMO_NVTX("lemo_fit_prox_eval");
     LEMO_CHECK(h, "null handle");
     ProxFit* f = &h->f;
     cudaStream_t st = (cudaStream_t)stream;

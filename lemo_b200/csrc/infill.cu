@@ -262,6 +262,7 @@ extern "C" {
 
 int lemo_repr_local_markers_4chan(const float* body, const float* contact, int32_t T, const double* d_stats, float* repr,
                                   double* rot_0_pivot, double* workspace, void* stream) {
+    LEMO_NVTX("lemo_repr_local_markers_4chan");
     LEMO_CHECK(body && contact && repr && rot_0_pivot && workspace && T >= 2, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     double* fwd = workspace;                 // [T][3]
@@ -297,6 +298,7 @@ int lemo_infill_prepare_input(const float* clip, int32_t d, int32_t T, float* x_
 
 int lemo_infill_finalize(const float* rec_pad, const float* clip, const double* d_stats, const double* rot_0_pivot, int32_t d, int32_t T,
                          float* markers_rec, float* contact_lbl, float* markers_input, double* workspace, void* stream) {
+    LEMO_NVTX("lemo_infill_finalize");
     LEMO_CHECK(rec_pad && clip && d_stats && rot_0_pivot && markers_rec && contact_lbl && workspace && d == IF_D && T >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     k_infill_scan<<<1, 32, 0, st>>>(clip, d_stats, rot_0_pivot, T, workspace);

@@ -8,7 +8,9 @@
 //     per-sequence global (L2-resident) buffers between cluster barriers; the adjoint W^T products are computed as per-CTA partial
 //     vectors that every CTA adds in rank order (deterministic);
 //   * pose -> rotations -> kinematic chain and its adjoint are the SAME device bodies the stand-alone kernels run (body_dev.cuh),
-//     executed redundantly by each CTA (55 joints: latency, not work), so no barrier is spent on them;
+//     executed redundantly by each CTA (55 joints: latency, not work) on SHARED-MEMORY copies of the model constants (joint
+//     regressor directions, hand PCA bases, pose mean, tree) and shared-memory scratch, so no barrier and no L2 round trip is
+//     spent on them (with global scratch these three bodies were 18 of the 41 us of a step);
 //   * the 81 marker rows of the body model are dealt 11 per CTA: fp32 blend (243 of the 512 x 31425 blend-shape columns), skinning,
 //     L1 marker loss and their adjoints; dA / dX / dtransl partials are combined like the MLP partials;
 //   * parameters and Adam moments (65 per frame) are replicated in every CTA's shared memory: all CTAs apply the identical update,
@@ -25,6 +27,7 @@ constexpr int PM_CL = 8;          // CTAs per cluster = per sequence
 constexpr int PM_NT = 256;        // threads per CTA
 constexpr int PM_VPC = 11;        // marker rows per CTA (8 x 11 >= 81)
 constexpr int PM_PART = 664;      // dA[660] + dtransl[3] + loss partial
+constexpr size_t PM_DYN_BYTES = 4 * (size_t)(NJ * 3 * NBETA + 165 + 2 * 540 + 168 + 112 + 168 + 496 + 512 + 660 + 660 + 168 + 168 + 660 + 512 + 496 + 12 + 192 + 12 + 192 + 128 + 16 + XK * 33 + NJ * PM_VPC + 16);
 
 struct MegaArgs {
     // loss-row sub-model (V = 81 marker rows)
@@ -35,9 +38,6 @@ struct MegaArgs {
     const float *W1, *b1, *W2, *b2, *W3, *b3;
     float *h1, *h2, *o, *dh2;                    // [S,512] [S,512] [S,126] [S,512]
     float *dh1p, *dXp, *dAp;                     // per-CTA partials: [S][8][512], [S][8][512], [S][8][PM_PART]
-    // body scratch, one row per sequence (the fitter's BodyCtx)
-    float *full_pose, *R, *X, *G, *A, *Jrest, *Jposed, *dA, *dX, *dR;
-    float *Rg, *Rb, *dRg, *dRb;
     // fit state
     float *P, *Gp;
     const float *betas, *mrec;
@@ -45,6 +45,7 @@ struct MegaArgs {
     int acc_n, acc_rec, acc_vp, acc_shape, acc_hand;
     int S, T, n_iters;
     float w_rec, w_vp, w_shape, w_hand;
+    unsigned long long* tl;                      // debug timeline (nullable): globaltimer stamps of cluster 0 / rank 0 at the phase boundaries of step 5
 };
 
 __device__ __forceinline__ size_t pm_poff(int i, int S, int s) {      // flat parameter vector P = [tr S*3 | r6 S*6 | z S*32 | lh S*12 | rh S*12]
@@ -55,7 +56,14 @@ __device__ __forceinline__ size_t pm_poff(int i, int S, int s) {      // flat pa
     return (size_t)S * 53 + (size_t)s * 12 + (i - 53);
 }
 
-__global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perframe_mega(MegaArgs a) {
+__device__ __forceinline__ unsigned long long pm_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PM_STAMP(i) do { if (a.tl && blockIdx.x == 0 && tid == 0 && t == 0 && it == 5) a.tl[i] = pm_now(); } while (0)
+
+__global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perframe_mega(MegaArgs a) {
     cgx::cluster_group cluster = cgx::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,24 +73,59 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
     __shared__ __align__(16) float s_vec[512];          // staging: X / dh2 / dh1
     __shared__ __align__(16) float s_h1[512];
     __shared__ __align__(16) float s_h2[512];
-    __shared__ float s_A[NJ * 12];
     __shared__ float s_red[8][64];
     __shared__ float s_T[PM_VPC][12], s_dT[PM_VPC][12], s_vp[PM_VPC][3], s_gv[PM_VPC][3], s_dvp[3 * PM_VPC];
     __shared__ float s_tgt[201], s_do[128], s_sc[8];
 
+    const int v0 = PM_VPC * rank, nv = max(0, min(PM_VPC, V - v0)), c0 = 3 * v0, ncol = 3 * nv;
+    // dynamic shared memory: model constants (loaded once per launch) + the body scratch of "frame 0" of this CTA
+    extern __shared__ __align__(16) float dyn[];
+    float* c_Jd = dyn;                       // [55*3*20]
+    float* c_Jt = c_Jd + NJ * 3 * NBETA;     // [165]
+    float* c_hl = c_Jt + NJ * 3;             // [npc*45]
+    float* c_hr = c_hl + 12 * 45;
+    float* c_pm = c_hr + 12 * 45;            // [165]
+    int* c_par = reinterpret_cast<int*>(c_pm + 168);
+    int* c_dep = c_par + 56;
+    float* b_fp = reinterpret_cast<float*>(c_dep + 56);   // full_pose [165]
+    float* b_R = b_fp + 168;                 // [55*9]
+    float* b_X = b_R + 496;                  // [512]
+    float* b_G = b_X + 512;                  // [660]
+    float* s_A = b_G + 660;                  // [660]
+    float* b_Jr = s_A + 660;                 // [165]
+    float* b_Jp = b_Jr + 168;                // [165]
+    float* b_dA = b_Jp + 168;                // [660]
+    float* b_dX = b_dA + 660;                // [512]
+    float* b_dR = b_dX + 512;                // [495]
+    float* b_Rg = b_dR + 496;                // [9]
+    float* b_Rb = b_Rg + 12;                 // [189]
+    float* b_dRg = b_Rb + 192;               // [9]
+    float* b_dRb = b_dRg + 12;               // [189]
+    float* b_o = b_dRb + 192;                // [126]
+    float* b_beta = b_o + 128;               // [10]
+    float* c_Wt = b_beta + 16;               // [512][33]: this CTA's 33 blend-shape columns, resident for the whole launch (67.6 KB)
+    float* c_wj = c_Wt + XK * 33;            // [55][11]: skinning weights of this CTA's marker rows
+    for (int i = tid; i < NJ * 3 * NBETA; i += PM_NT) c_Jd[i] = a.Jd[i];
+    for (int i = tid; i < NJ * 3; i += PM_NT) { c_Jt[i] = a.Jt[i]; c_pm[i] = a.pose_mean[i]; }
+    for (int i = tid; i < a.npc * 45; i += PM_NT) { c_hl[i] = a.hand_l[i]; c_hr[i] = a.hand_r[i]; }
+    if (tid < NJ) { c_par[tid] = a.parents[tid]; c_dep[tid] = a.depth[tid]; }
+    for (int i = tid; i < XK * 33; i += PM_NT) { const int k = i / 33, cc = i - k * 33; c_Wt[i] = cc < ncol ? a.Wt[(size_t)k * NC + c0 + cc] : 0.f; }
+    for (int i = tid; i < NJ * PM_VPC; i += PM_NT) { const int j = i / PM_VPC, v = i - j * PM_VPC; c_wj[i] = v < nv ? a.wjm[(size_t)j * V + v0 + v] : 0.f; }
+    __syncthreads();
+
     PoseK pk;
     pk.in = PoseIn();
-    pk.in.transl = a.P; pk.in.R_global = a.Rg; pk.in.R_body = a.Rb;
-    pk.in.lhand = a.P + (size_t)S * 41; pk.in.rhand = a.P + (size_t)S * 53;
-    pk.in.betas = a.betas; pk.in.betas_stride = 10; pk.in.hand_is_pca = 1;
-    pk.hand_l = a.hand_l; pk.hand_r = a.hand_r; pk.pose_mean = a.pose_mean; pk.npc = a.npc;
+    pk.in.transl = s_p; pk.in.R_global = b_Rg; pk.in.R_body = b_Rb;
+    pk.in.lhand = s_p + 41; pk.in.rhand = s_p + 53;
+    pk.in.betas = b_beta; pk.in.betas_stride = 10; pk.in.hand_is_pca = 1;
+    pk.hand_l = c_hl; pk.hand_r = c_hr; pk.pose_mean = c_pm; pk.npc = a.npc;
     PoseGrad pg;
-    pg.R_global = a.dRg; pg.R_body = a.dRb; pg.lhand = a.Gp + (size_t)S * 41; pg.rhand = a.Gp + (size_t)S * 53;
+    pg.R_global = b_dRg; pg.R_body = b_dRb; pg.lhand = s_g + 41; pg.rhand = s_g + 53;
 
-    const int v0 = PM_VPC * rank, nv = max(0, min(PM_VPC, V - v0)), c0 = 3 * v0, ncol = 3 * nv;
 
     for (int s = cid; s < S; s += ncl) {
         if (tid < 65) s_p[tid] = a.P[pm_poff(tid, S, s)];
+        if (tid < 10) b_beta[tid] = a.betas[(size_t)s * 10 + tid];
         __syncthreads();
         for (int t = 0; t < a.T; ++t) {
             if (tid < 65) { s_m[tid] = 0.f; s_v[tid] = 0.f; }                      // fresh optim.Adam per frame (:319)
@@ -96,12 +139,9 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     s_sc[1] = (float)(1.0 - pow(0.9, tt));
                     s_sc[2] = (float)sqrt(1.0 - pow(0.999, tt));
                 }
+                PM_STAMP(0);
                 // ------------------------------------------------ P1: global 6D -> R ; fc1 rows [64 rank, +64)
-                if (tid == 0) {
-                    float r[9];
-                    gs6d_fwd(s_p + 3, r);
-                    for (int k = 0; k < 9; ++k) a.Rg[(size_t)s * 9 + k] = r[k];
-                }
+                if (tid == 0) gs6d_fwd(s_p + 3, b_Rg);
                 {
                     const int r = tid >> 2, q = tid & 3, n = 64 * rank + r;
                     float acc = 0.f;
@@ -111,78 +151,100 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                     if (q == 0) a.h1[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b1 + n));
                 }
+                PM_STAMP(1);
                 cluster.sync();
+                PM_STAMP(2);
                 // ------------------------------------------------ P2: fc2 rows [64 rank, +64), one warp per row
                 s_h1[tid] = a.h1[(size_t)s * 512 + tid]; s_h1[tid + 256] = a.h1[(size_t)s * 512 + tid + 256];
                 __syncthreads();
-                for (int rr = 0; rr < 8; ++rr) {
-                    const int n = 64 * rank + warp * 8 + rr;
-                    const float4* w = reinterpret_cast<const float4*>(a.W2 + (size_t)n * 512);
-                    float acc = 0.f;
+                // every phase below is a stream of L2 reads with ~1 us of latency each: the loops are unrolled so that 16-32 independent
+                // loads are in flight per thread (the first version issued them 1-4 at a time and spent 47 us per step waiting)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 wv = __ldg(w + i * 32 + lane);
-                        const float4 x = *reinterpret_cast<const float4*>(&s_h1[(i * 32 + lane) * 4]);
-                        acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+                for (int half = 0; half < 2; ++half) {
+                    float4 wv[4][4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const float4* w = reinterpret_cast<const float4*>(a.W2 + (size_t)(64 * rank + warp * 8 + half * 4 + rr) * 512);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) wv[rr][i] = __ldg(w + i * 32 + lane);
                     }
-                    acc = warp_sum(acc);
-                    if (lane == 0) a.h2[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b2 + n));
-                }
-                cluster.sync();
-                // ------------------------------------------------ P3: output rows [16 rank, +16)
-                s_h2[tid] = a.h2[(size_t)s * 512 + tid]; s_h2[tid + 256] = a.h2[(size_t)s * 512 + tid + 256];
-                __syncthreads();
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int n = 16 * rank + warp * 2 + rr;
-                    if (n < 126) {
-                        const float4* w = reinterpret_cast<const float4*>(a.W3 + (size_t)n * 512);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int n = 64 * rank + warp * 8 + half * 4 + rr;
                         float acc = 0.f;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float4 wv = __ldg(w + i * 32 + lane);
-                            const float4 x = *reinterpret_cast<const float4*>(&s_h2[(i * 32 + lane) * 4]);
-                            acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+                            const float4 x = *reinterpret_cast<const float4*>(&s_h1[(i * 32 + lane) * 4]);
+                            acc = fmaf(wv[rr][i].x, x.x, acc); acc = fmaf(wv[rr][i].y, x.y, acc);
+                            acc = fmaf(wv[rr][i].z, x.z, acc); acc = fmaf(wv[rr][i].w, x.w, acc);
                         }
                         acc = warp_sum(acc);
-                        if (lane == 0) a.o[(size_t)s * 126 + n] = acc + __ldg(a.b3 + n);
+                        if (lane == 0) a.h2[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b2 + n));
                     }
                 }
+                PM_STAMP(3);
                 cluster.sync();
-                // ------------------------------------------------ P4 (every CTA): Gram-Schmidt, pose -> R -> chain (shared device body)
-                if (tid < NBODY) {
-                    float x6[6], r[9];
-                    for (int k = 0; k < 6; ++k) x6[k] = a.o[(size_t)s * 126 + tid * 6 + k];
-                    gs6d_fwd(x6, r);
-                    for (int k = 0; k < 9; ++k) a.Rb[((size_t)s * NBODY + tid) * 9 + k] = r[k];
-                }
-                if (tid < 65) a.P[pm_poff(tid, S, s)] = s_p[tid];                   // every CTA stores the same values
+                PM_STAMP(4);
+                // ------------------------------------------------ P3: output rows [16 rank, +16)
+                s_h2[tid] = a.h2[(size_t)s * 512 + tid]; s_h2[tid + 256] = a.h2[(size_t)s * 512 + tid + 256];
                 __syncthreads();
-                pose_chain_fwd_body(pk, a.Jt, a.Jd, a.parents, a.depth, a.max_depth, a.full_pose, a.R, a.X, nullptr, a.G, a.A, a.Jrest,
-                                    a.Jposed, nullptr, s);
+                {
+                    float4 wv[2][4];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int n = min(125, 16 * rank + warp * 2 + rr);
+                        const float4* w = reinterpret_cast<const float4*>(a.W3 + (size_t)n * 512);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) wv[rr][i] = __ldg(w + i * 32 + lane);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int n = 16 * rank + warp * 2 + rr;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 x = *reinterpret_cast<const float4*>(&s_h2[(i * 32 + lane) * 4]);
+                            acc = fmaf(wv[rr][i].x, x.x, acc); acc = fmaf(wv[rr][i].y, x.y, acc);
+                            acc = fmaf(wv[rr][i].z, x.z, acc); acc = fmaf(wv[rr][i].w, x.w, acc);
+                        }
+                        acc = warp_sum(acc);
+                        if (lane == 0 && n < 126) a.o[(size_t)s * 126 + n] = acc + __ldg(a.b3 + n);
+                    }
+                }
+                PM_STAMP(5);
+                cluster.sync();
+                PM_STAMP(6);
+                // ------------------------------------------------ P4 (every CTA): Gram-Schmidt, pose -> R -> chain (shared device body)
+                if (tid < 126) b_o[tid] = a.o[(size_t)s * 126 + tid];
+                __syncthreads();
+                if (tid < NBODY) gs6d_fwd(b_o + tid * 6, b_Rb + tid * 9);
+                __syncthreads();
+                pose_chain_fwd_body(pk, c_Jt, c_Jd, c_par, c_dep, a.max_depth, b_fp, b_R, b_X, nullptr, b_G, s_A, b_Jr, b_Jp, nullptr, 0);
                 __syncthreads();
                 if (last && rank == 0 && tid < 72) {                               // the [T,72] row the script saves: parameters of the LAST forward
                     float v;
                     if (tid < 3) v = s_p[tid];
-                    else if (tid < 6) v = a.full_pose[(size_t)s * 165 + (tid - 3)];
-                    else if (tid < 16) v = a.betas[(size_t)s * 10 + (tid - 6)];
+                    else if (tid < 6) v = b_fp[tid - 3];
+                    else if (tid < 16) v = b_beta[tid - 6];
                     else v = s_p[9 + (tid - 16)];
                     a.p72[((size_t)s * a.T + t) * 72 + tid] = v;
                 }
+                PM_STAMP(7);
                 // ------------------------------------------------ P5: blend + skinning + L1 loss on this CTA's marker rows
-                for (int i = tid; i < NJ * 12; i += PM_NT) s_A[i] = a.A[(size_t)s * NJ * 12 + i];
-                s_vec[tid] = a.X[(size_t)s * XK + tid]; s_vec[tid + 256] = a.X[(size_t)s * XK + tid + 256];
-                __syncthreads();
                 {
                     const int grp = tid >> 6, cc = tid & 63;
                     float acc = 0.f;
-                    if (cc < ncol)
-                        for (int k = grp; k < XK; k += 4) acc = fmaf(s_vec[k], __ldg(a.Wt + (size_t)k * NC + c0 + cc), acc);
+                    if (cc < ncol) {
+#pragma unroll 8
+                        for (int k = grp; k < XK; k += 4) acc = fmaf(b_X[k], c_Wt[k * 33 + cc], acc);
+                    }
                     s_red[grp][cc] = acc;
                 }
                 if (tid < nv * 12) {
                     const int i = tid / 12, k = tid - i * 12;
                     float acc = 0.f;
-                    for (int j = 0; j < NJ; ++j) acc = fmaf(__ldg(a.wjm + (size_t)j * V + v0 + i), s_A[j * 12 + k], acc);
+#pragma unroll 11
+                    for (int j = 0; j < NJ; ++j) acc = fmaf(c_wj[j * PM_VPC + i], s_A[j * 12 + k], acc);
                     s_T[i][k] = acc;
                 }
                 __syncthreads();
@@ -205,6 +267,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     if (lane == 0) s_sc[4 + warp] = lpart;
                 }
                 __syncthreads();
+                PM_STAMP(8);
                 // ------------------------------------------------ P6: adjoint on this CTA's rows -> partials of dA, dtransl, dX
                 if (tid < ncol) {
                     const int i = tid / 3, c = tid - i * 3;
@@ -220,7 +283,9 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     for (int e = tid; e < NJ * 12; e += PM_NT) {
                         const int j = e / 12, k = e - j * 12;
                         float acc = 0.f;
-                        for (int i = 0; i < nv; ++i) acc = fmaf(__ldg(a.wjm + (size_t)j * V + v0 + i), s_dT[i][k], acc);
+#pragma unroll
+                        for (int i = 0; i < PM_VPC; ++i)
+                            if (i < nv) acc = fmaf(c_wj[j * PM_VPC + i], s_dT[i][k], acc);
                         pz[e] = acc;
                     }
                     if (tid < 3) {
@@ -231,47 +296,50 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     if (tid == 3) pz[NJ * 12 + 3] = s_sc[4] + s_sc[5];
                     float* px = a.dXp + ((size_t)s * PM_CL + rank) * XK;
                     for (int k = tid; k < XK; k += PM_NT) {
-                        const float* w = a.Wt + (size_t)k * NC + c0;
+                        const float* w = c_Wt + k * 33;
                         float acc = 0.f;
-                        for (int cc = 0; cc < ncol; ++cc) acc = fmaf(__ldg(w + cc), s_dvp[cc], acc);
+#pragma unroll
+                        for (int cc = 0; cc < 3 * PM_VPC; ++cc)
+                            if (cc < ncol) acc = fmaf(w[cc], s_dvp[cc], acc);
                         px[k] = acc;
                     }
                 }
+                PM_STAMP(9);
                 cluster.sync();
+                PM_STAMP(10);
                 // ------------------------------------------------ P7 (every CTA): combine partials in rank order, chain adjoint
                 for (int e = tid; e < PM_PART; e += PM_NT) {
                     float acc = 0.f;
                     for (int r = 0; r < PM_CL; ++r) acc += a.dAp[((size_t)s * PM_CL + r) * PM_PART + e];
-                    if (e < NJ * 12) { const int j = e / 12, k = e - j * 12; a.dA[((size_t)j * S + s) * 12 + k] = acc; }
+                    if (e < NJ * 12) b_dA[e] = acc;                                  // joint-major [55][B*12] with B = 1
                     else if (e < NJ * 12 + 3) s_g[e - NJ * 12] = acc;               // d loss / d transl
                     else s_sc[3] = acc;                                             // marker loss value
                 }
                 for (int k = tid; k < XK; k += PM_NT) {
                     float acc = 0.f;
                     for (int r = 0; r < PM_CL; ++r) acc += a.dXp[((size_t)s * PM_CL + r) * XK + k];
-                    a.dX[(size_t)s * XK + k] = acc;
+                    b_dX[k] = acc;
                 }
                 __syncthreads();
-                chain_bwd_body(a.R, a.G, a.Jrest, a.dA, nullptr, a.dX, a.Jd, a.parents, a.depth, a.max_depth, S, 10, a.dR, nullptr, nullptr, s);
+                PM_STAMP(11);
+                chain_bwd_body(b_R, b_G, b_Jr, b_dA, nullptr, b_dX, c_Jd, c_par, c_dep, a.max_depth, 1, 10, b_dR, nullptr, nullptr, 0);
                 __syncthreads();
-                pose_to_rot_bwd_body(pk, pg, S, a.full_pose, a.dR, s);
+                PM_STAMP(12);
+                pose_to_rot_bwd_body(pk, pg, 1, b_fp, b_dR, 0);
                 __syncthreads();
-                if (tid == 0) gs6d_bwd(s_p + 3, a.dRg + (size_t)s * 9, s_g + 3);
-                if (tid < NBODY) {
-                    float x6[6];
-                    for (int k = 0; k < 6; ++k) x6[k] = a.o[(size_t)s * 126 + tid * 6 + k];
-                    gs6d_bwd(x6, a.dRb + ((size_t)s * NBODY + tid) * 9, s_do + tid * 6);
-                }
-                if (tid >= 32 && tid < 32 + 24) {
-                    const int c = tid - 32;
-                    s_g[41 + c] = c < 12 ? pg.lhand[(size_t)s * 12 + c] : pg.rhand[(size_t)s * 12 + (c - 12)];
-                }
-                __syncthreads();
+                if (tid == 0) gs6d_bwd(s_p + 3, b_dRg, s_g + 3);
+                if (tid < NBODY) gs6d_bwd(b_o + tid * 6, b_dRb + tid * 9, s_do + tid * 6);
+                __syncthreads();                                                    // (the hand PCA gradients were written straight into s_g)
+                PM_STAMP(13);
                 // ------------------------------------------------ P8: dh2 columns [64 rank, +64) = (W3^T d_o) * lrelu'(h2)
                 {
                     const int nn = tid & 63, og = tid >> 6, n = 64 * rank + nn;
                     float acc = 0.f;
-                    for (int o = og; o < 126; o += 4) acc = fmaf(__ldg(a.W3 + (size_t)o * 512 + n), s_do[o], acc);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int o = og + 4 * i;
+                        if (o < 126) acc = fmaf(__ldg(a.W3 + (size_t)o * 512 + n), s_do[o], acc);
+                    }
                     s_red[og][nn] = acc;
                 }
                 __syncthreads();
@@ -280,12 +348,15 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     const float v = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
                     a.dh2[(size_t)s * 512 + n] = v * (s_h2[n] > 0.f ? 1.f : 0.2f);
                 }
+                PM_STAMP(14);
                 cluster.sync();
+                PM_STAMP(15);
                 // ------------------------------------------------ P9: partial of dh1 = W2^T dh2 over this CTA's rows of W2
                 s_vec[tid] = a.dh2[(size_t)s * 512 + tid]; s_vec[tid + 256] = a.dh2[(size_t)s * 512 + tid + 256];
                 __syncthreads();
                 {
                     float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
                     for (int r = 0; r < 64; ++r) {
                         const int n = 64 * rank + r;
                         const float d = s_vec[n];
@@ -295,7 +366,9 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     float* ph = a.dh1p + ((size_t)s * PM_CL + rank) * 512;
                     ph[tid] = acc0; ph[tid + 256] = acc1;
                 }
+                PM_STAMP(16);
                 cluster.sync();
+                PM_STAMP(17);
                 // ------------------------------------------------ P10 (every CTA): dh1, dz = W1^T dh1, priors, Adam
                 __syncthreads();
                 for (int c = tid; c < 512; c += PM_NT) {
@@ -307,6 +380,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                 {
                     const int c = tid & 31, kg = tid >> 5;
                     float acc = 0.f;
+#pragma unroll 16
                     for (int k = kg; k < 512; k += 8) acc = fmaf(__ldg(a.W1 + (size_t)k * 32 + c), s_vec[k], acc);
                     s_red[kg][c] = acc;
                 }
@@ -324,10 +398,11 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT) k_perfram
                     float pv = 0.f, ph = 0.f, ps = 0.f;
                     for (int k = 0; k < 32; ++k) pv += s_p[9 + k] * s_p[9 + k];
                     for (int k = 0; k < 24; ++k) ph += s_p[41 + k] * s_p[41 + k];
-                    for (int k = 0; k < 10; ++k) { const float b = a.betas[(size_t)s * 10 + k]; ps += b * b; }
+                    for (int k = 0; k < 10; ++k) ps += b_beta[k] * b_beta[k];
                     float* ac = a.acc + (size_t)s * a.acc_n;
                     ac[a.acc_rec] = s_sc[3]; ac[a.acc_vp] = pv / 32.f; ac[a.acc_hand] = ph / 24.f; ac[a.acc_shape] = ps / 10.f;
                 }
+                PM_STAMP(18);
                 if (tid < 65) {                                                     // torch.optim.Adam.step, identical in every CTA
                     const float gi = s_g[tid];
                     const float mi = 0.9f * s_m[tid] + (1.f - 0.9f) * gi;

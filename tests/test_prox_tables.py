@@ -30,6 +30,20 @@ def test_priors_match_reference_outputs(gold):
         pr.create_prior('laplace')
 
 
+def test_gmm_prior_matches_reference_outputs():
+    """MaxMixturePrior (prior.py:100-231) on a synthetic 8-component mixture: merged and per-component likelihoods equal the
+    outputs of the reference class (tests/golden/reference_golden_gmm.npz, tools/make_gmm_golden.py), and create_prior('gmm') builds it."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'reference_golden_gmm.npz'))
+    gmm = dict(means=g['means'], covars=g['covars'], weights=g['weights'])
+    pose = torch.from_numpy(g['pose'])
+    for merged, key in ((True, 'nll_merged'), (False, 'nll_full')):
+        m = pr.create_prior('gmm', gmm=gmm, use_merged=merged)
+        assert isinstance(m, pr.MaxMixturePrior) and m.num_gaussians == 8 and m.random_var_dim == 69
+        out = m(pose, torch.zeros(12, 10)).numpy()
+        assert np.allclose(out, g[key], rtol=1e-5, atol=1e-4), np.abs(out - g[key]).max()
+    assert np.allclose(m.get_mean().numpy(), g['mean_pose'], atol=1e-6)
+
+
 def test_oracle_angle_term_matches_reference(gold):
     """The restatement inside oracle/ref_prox.py (and lemo_b200's SMPLifyLoss) uses `full_pose[:, 3:66][:, idx - 3] * sgn`."""
     pose = torch.from_numpy(gold['pose'])

@@ -37,7 +37,7 @@ if 'perframe' in stages:
     clean, _, _ = synth.make_sequence(0, T=T)
     for i in range(S):
         pf.set_sequence(i, clean[0, 6:16], np.zeros((T, 67, 3), np.float32))
-    pf.run(n_iters=3)
+    pf.run(n_iters=10)
     torch.cuda.synchronize()
     print('PERFRAME done', flush=True)
 
