@@ -342,152 +342,10 @@ __global__ void __launch_bounds__(192, 1) k_blend_v2(const __grid_constant__ CUt
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ K-chunked TF32 GEMM (experimental)
-// C[M,N] = epi( A[M,K] . B[N,K]^T ) for the small-M GEMMs of the fit (VPoser MLP and its adjoint: M = S*T <= 960, N, K <= 512), on
-// tcgen05 with fp32-grade results.  Two things kept the first tensor-core attempt (k_blend_tf32 with `three`) off the default path
-// (vposer.cu): 128 x 224 tiles give 24 CTAs at these shapes, and the tensor core's fp32 accumulator truncates -- a bias that grows
-// with the number of accumulated K steps (4e-5 of max|R| over K = 512 even with the exact 3-term operand split).  Here
-//   * tiles are 128 x 64 (64 CTAs at M = 960, N = 512) with a 4-stage TMA ring of [A_hi | A_lo | B_hi | B_lo] blocks,
-//   * K is cut into <= 8 chunks, each accumulated in ITS OWN 64 TMEM columns (8 x 64 = the 512 columns of an SM), so no accumulator
-//     sees more than K/8 steps; the epilogue adds the chunks in fp32 on the CUDA cores in a fixed order, then applies the usual
-//     bias / LeakyReLU / LeakyReLU' mask / (hi|lo) split of the result.
-// STATUS: compiled and desk-checked only (written after this round's GPU budget was spent); selected by LEMO_VPOSER=tc64, never by
-// default, and listed in DESIGN.md section 7 as the first thing to measure next round.
-constexpr int G_BN = 64, G_STAGES = 4;
-constexpr int G_B_BYTES = G_BN * TC_BK * 4;                              // 8 KB
-constexpr int G_STAGE_BYTES = 2 * TC_A_BYTES + 2 * G_B_BYTES;            // 48 KB
-constexpr int G_OUT_PITCH = G_BN + 1;
-constexpr size_t G_SMEM = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256;
-static_assert((size_t)TC_BM * G_OUT_PITCH * 4 <= (size_t)G_STAGES * G_STAGE_BYTES, "epilogue staging reuses the pipeline buffers");
-
-__global__ void __launch_bounds__(192, 1) k_gemm_tc64(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                      const __grid_constant__ CUtensorMap map_blo, float* __restrict__ C, int M, int N, int K,
-                                                      int lo_col, TcEpi ep) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = (uint64_t*)(smem + (size_t)G_STAGES * G_STAGE_BYTES);           // [0,4) full, [4,8) empty, [8] accumulators complete
-    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * G_BN, m0 = blockIdx.y * TC_BM;
-    const int nkb = K / TC_BK;
-    const int chunk_kb = (nkb + 7) / 8;                                              // k-blocks per accumulator chunk
-    const int nchunk = (nkb + chunk_kb - 1) / chunk_kb;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < G_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[G_STAGES + s]), 1); }
-        mbar_init(smem_u32(&bars[2 * G_STAGES]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % G_STAGES;
-                mbar_wait(smem_u32(&bars[G_STAGES + s]), ((kb / G_STAGES) & 1) ^ 1);
-                const uint32_t full = smem_u32(&bars[s]);
-                mbar_expect_tx(full, G_STAGE_BYTES);
-                const uint32_t dst = smem_u32(smem + (size_t)s * G_STAGE_BYTES);
-                tma_load_2d(dst, &map_a, full, kb * TC_BK, m0);                                  // A_hi block
-                tma_load_2d(dst + TC_A_BYTES, &map_a, full, lo_col + kb * TC_BK, m0);            // A_lo block
-                tma_load_2d(dst + 2 * TC_A_BYTES, &map_b, full, kb * TC_BK, n0);                 // B_hi block (64 rows)
-                tma_load_2d(dst + 2 * TC_A_BYTES + G_B_BYTES, &map_blo, full, kb * TC_BK, n0);   // B_lo block
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, G_BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % G_STAGES;
-                mbar_wait(smem_u32(&bars[s]), (kb / G_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * G_STAGE_BYTES);
-                const uint64_t ahi = umma_desc_sw128(a_addr), alo = umma_desc_sw128(a_addr + TC_A_BYTES);
-                const uint64_t bhi = umma_desc_sw128(a_addr + 2 * TC_A_BYTES), blo = umma_desc_sw128(a_addr + 2 * TC_A_BYTES + G_B_BYTES);
-                const uint32_t acc = tmem_base + (uint32_t)((kb / chunk_kb) * G_BN);
-                const bool first = (kb % chunk_kb) == 0;
-#pragma unroll
-                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                    const uint64_t off = (uint64_t)(k * TC_UMMA_K * 4 >> 4);
-                    umma_tf32(acc, ahi + off, bhi + off, idesc, (first && k == 0) ? 0u : 1u);
-                    umma_tf32(acc, alo + off, bhi + off, idesc, 1u);
-                    umma_tf32(acc, ahi + off, blo + off, idesc, 1u);
-                }
-                umma_commit(smem_u32(&bars[G_STAGES + s]));
-            }
-            umma_commit(smem_u32(&bars[2 * G_STAGES]));
-        }
-    } else {
-        const int lq = warp & 3;
-        mbar_wait(smem_u32(&bars[2 * G_STAGES]), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* s_out = reinterpret_cast<float*>(smem);
-        const int row = lq * 32 + lane;
-#pragma unroll 1
-        for (int c0 = 0; c0 < G_BN; c0 += 32) {
-            float sum[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-            for (int ch = 0; ch < nchunk; ++ch) {                                     // fixed order: chunk 0 first
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * G_BN + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-                    "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                      "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s_out[row * G_OUT_PITCH + c0 + j] = sum[j];
-        }
-        __syncwarp();
-        const long long ldc = ep.ldc ? ep.ldc : N;
-        float bias_r[G_BN / 32];
-#pragma unroll
-        for (int k = 0; k < G_BN / 32; ++k) {
-            const int gc = n0 + lane + 32 * k;
-            bias_r[k] = (ep.bias && gc < N) ? __ldg(ep.bias + gc) : 0.f;
-        }
-        const int nrows = min(32, M - (m0 + lq * 32));
-        for (int rr = 0; rr < nrows; ++rr) {
-            const int gr = m0 + lq * 32 + rr;
-            const float* src = s_out + (lq * 32 + rr) * G_OUT_PITCH + lane;
-#pragma unroll
-            for (int k = 0; k < G_BN / 32; ++k) {
-                const int gc = n0 + lane + 32 * k;
-                if (gc >= N) continue;
-                float v = src[32 * k] + bias_r[k];
-                if (ep.act == 1) v = v > 0.f ? v : 0.2f * v;
-                else if (ep.act == 2) v *= __ldg(ep.mask_src + (size_t)gr * ldc + gc) > 0.f ? 1.f : 0.2f;
-                if (C) C[(size_t)gr * ldc + gc] = v;
-                if (ep.split_out) {
-                    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                    ep.split_out[(size_t)gr * ep.split_ld + gc] = hi;
-                    ep.split_out[(size_t)gr * ep.split_ld + ep.split_lo + gc] = v - hi;
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
+// (A K-chunked variant of this GEMM -- 128 x 64 tiles, one TMEM accumulator per K/8 chunk summed on the CUDA cores, for the VPoser MLP --
+// was written in round 1 and MEASURED in round 2 (tools/diag_vposer_modes.py on B200): R_body error vs an fp64 oracle 5.3e-5 at B = 960
+// against 2.8e-5 for the fp32 CUDA-core GEMMs and 3.6e-4 for the plain TF32 kernel, decode + adjoint time within 6 % of the fp32 path.
+// Twice the error for no gain: removed, the VPoser GEMMs stay on gemm.cu's cluster split-K SGEMM.)
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -571,21 +429,6 @@ int blend_tc_launch_bias(const void* map_x, const void* map_w, float* VP, int B,
 }
 int tc_map_a(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BM); }
 int tc_map_b(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, TC_BN); }
-int tc_map_b64(void* map, const float* base, long long rows, int cols) { return make_kmajor_map(map, base, rows, cols, G_BN); }
-// K-chunked variant (k_gemm_tc64): map_b / map_b_lo must come from tc_map_b64; always the 3-term product
-int tc_gemm64_launch(const void* map_a, const void* map_b, const void* map_b_lo, float* C, int M, int N, int K, int lo_col, const TcEpi& ep,
-                     cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        LEMO_CUDA(cudaFuncSetAttribute(k_gemm_tc64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-        configured = true;
-    }
-    LEMO_CHECK(K % TC_BK == 0 && K > 0 && map_b_lo, "tc_gemm64: K must be a positive multiple of 32 and the B_lo operand is required");
-    k_gemm_tc64<<<dim3(cdiv(N, G_BN), cdiv(M, TC_BM)), 192, G_SMEM, st>>>(*(const CUtensorMap*)map_a, *(const CUtensorMap*)map_b,
-                                                                          *(const CUtensorMap*)map_b_lo, C, M, N, K, lo_col, ep);
-    LEMO_CUDA(cudaGetLastError());
-    return 0;
-}
 
 // dst[n][kpad] = rn_tf32(src) with optional transpose: src is [rows_src][cols_src] row-major; transpose=0: dst[n=r][k=c]; 1: dst[n=c][k=r]
 __global__ void k_tc_prep_b(const float* __restrict__ src, int rows_src, int cols_src, int transpose, int kpad, float* __restrict__ dst,

@@ -26,10 +26,12 @@ constexpr int SKB_TV = 256;                 // vertices per tile of k_skin_bwd
 constexpr int SKB_PART = NJ * 12 + 3;       // per-CTA partial: dA[55][12] + dtransl[3]
 static inline int skin_bwd_tiles(int V, int B) {
     const int ntile = cdiv(V, SKB_TV);
-    return ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 720)));
+    // full meshes: aim at ~16 CTAs per SM in total (the per-CTA partials are combined in CTA order, so the count does not affect the result's
+    // reproducibility, only the summation grouping)
+    return ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 2368)));
 }
 static inline int skin_bwd_ctas(int V, int B) { return cdiv(cdiv(V, SKB_TV), skin_bwd_tiles(V, B)); }
-static inline int dx_slices(int V) { return std::max(1, std::min(64, (3 * V) / 2048)); }
+static inline int dx_slices(int V) { return std::max(1, std::min(64, (3 * V) / 832)); }     // full mesh: 37 K-slices x 32 tiles = 1184 CTAs
 
 
 // =============================================================================================

@@ -137,9 +137,6 @@ int tc_gemm_launch(const void* map_a, const void* map_b, float* C, int M, int N,
                    const void* map_b_lo = nullptr);   // map_b_lo: B - rn_tf32(B) => fp32-grade 3-term product
 int tc_map_a(void* map, const float* base, long long rows, int cols);     // A operand [rows, cols], 128-row boxes
 int tc_map_b(void* map, const float* base, long long rows, int cols);     // B operand [rows = N, cols = K], 224-row boxes
-int tc_map_b64(void* map, const float* base, long long rows, int cols);   // same with 64-row boxes (k_gemm_tc64)
-int tc_gemm64_launch(const void* map_a, const void* map_b, const void* map_b_lo, float* C, int M, int N, int K, int lo_col, const TcEpi& ep,
-                     cudaStream_t st);      // K-chunked TMEM accumulation, 128 x 64 tiles (experimental)
 int tc_prep_b(const float* src, int rows_src, int cols_src, int transpose, int kpad, float* dst, cudaStream_t st, float* dst_lo = nullptr);
 // tcgen05 blend GEMM (blend_tc.cu)
 int blend_tc_map_x(const float* X2, int maxB, void* map_x);

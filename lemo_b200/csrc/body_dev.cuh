@@ -12,7 +12,7 @@ namespace lemo {
 template <bool SUB64>
 __device__ __forceinline__ void body_sync() {
     if (SUB64) asm volatile("bar.sync 1, 64;" ::: "memory");
-    else body_sync<SUB64>();
+    else __syncthreads();
 }
 
 // =============================================================================================

@@ -92,12 +92,6 @@ int vposer_create(const float* w1, const float* b1, const float* w2, const float
     LEMO_TRY(tc_map_b(v->m_w1t, v->W1t, 32, 512)); LEMO_TRY(tc_map_b(v->m_w2t, v->W2t, 512, 512)); LEMO_TRY(tc_map_b(v->m_w3t, v->W3t, 512, 128));
     LEMO_TRY(tc_map_a(v->m_zs, v->zs, maxB, 64)); LEMO_TRY(tc_map_a(v->m_h1s, v->h1s, maxB, 1024)); LEMO_TRY(tc_map_a(v->m_h2s, v->h2s, maxB, 1024));
     LEMO_TRY(tc_map_a(v->m_dos, v->dos, maxB, 256)); LEMO_TRY(tc_map_a(v->m_dh2s, v->dh2s, maxB, 1024)); LEMO_TRY(tc_map_a(v->m_dh1s, v->dh1s, maxB, 1024));
-    if (vposer_tc_mode() == 2) {            // 64-row-box maps only when the experimental K-chunked GEMM is selected
-        LEMO_TRY(tc_map_b64(v->n_w1, v->W1r, 512, 32)); LEMO_TRY(tc_map_b64(v->n_w2, v->W2r, 512, 512)); LEMO_TRY(tc_map_b64(v->n_w3, v->W3r, 126, 512));
-        LEMO_TRY(tc_map_b64(v->n_w1t, v->W1t, 32, 512)); LEMO_TRY(tc_map_b64(v->n_w2t, v->W2t, 512, 512)); LEMO_TRY(tc_map_b64(v->n_w3t, v->W3t, 512, 128));
-        LEMO_TRY(tc_map_b64(v->o_w1, v->L1r, 512, 32)); LEMO_TRY(tc_map_b64(v->o_w2, v->L2r, 512, 512)); LEMO_TRY(tc_map_b64(v->o_w3, v->L3r, 126, 512));
-        LEMO_TRY(tc_map_b64(v->o_w1t, v->L1t, 32, 512)); LEMO_TRY(tc_map_b64(v->o_w2t, v->L2t, 512, 512)); LEMO_TRY(tc_map_b64(v->o_w3t, v->L3t, 512, 128));
-    }
     LEMO_CUDA(cudaDeviceSynchronize());
     v->has_tc = true;
     *out = v;
@@ -116,17 +110,17 @@ void vposer_free(VPoser* v) {
 // (M = 960, N = 512 gives 24 CTAs of 128x224 against 120 CTAs for the CUDA-core GEMM: 2.24 vs 2.03 ms per fitting step) and less
 // accurate (R_body 4e-5 vs 1e-6 of max even with the exact 3-term split -- the tensor core's fp32 accumulation itself is only good to
 // ~1e-5 over K = 512), and the rotations it produces are NOT diluted by a larger term the way blend-shape offsets are.
-// LEMO_VPOSER=tc64 selects the K-chunked variant (blend_tc.cu: k_gemm_tc64), written to remove both objections -- 128 x 64 tiles and
-// one TMEM accumulator per K/8 chunk, summed in fp32 on the CUDA cores -- but not yet measured.
+// A K-chunked variant (128 x 64 tiles, one TMEM accumulator per K/8 chunk summed on the CUDA cores) was measured in round 2: 5.3e-5 vs
+// 2.8e-5 (fp32 CUDA cores) on R_body at B = 960, time within 6 % -- removed (see the note in blend_tc.cu).
 static int vposer_tc_mode() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("LEMO_VPOSER"); on = !e ? 0 : strcmp(e, "tc") == 0 ? 1 : strcmp(e, "tc64") == 0 ? 2 : 0; }
+    if (on < 0) { const char* e = getenv("LEMO_VPOSER"); on = (e && strcmp(e, "tc") == 0) ? 1 : 0; }
     return on;
 }
 static bool vposer_tc_enabled() { return vposer_tc_mode() != 0; }
-static int vp_gemm(int mode, const void* map_a, const void* m224, const void* l224, const void* m64, const void* l64, float* C, int M, int N,
-                   int K, int lo_col, const TcEpi& ep, cudaStream_t st) {
-    if (mode == 2) return tc_gemm64_launch(map_a, m64, l64, C, M, N, K, lo_col, ep, st);
+static int vp_gemm(int mode, const void* map_a, const void* m224, const void* l224, float* C, int M, int N, int K, int lo_col, const TcEpi& ep,
+                   cudaStream_t st) {
+    (void)mode;
     return tc_gemm_launch(map_a, m224, C, M, N, K, lo_col, ep, st, l224);
 }
 
@@ -137,11 +131,11 @@ int vposer_decode(VPoser* v, const float* z, int B, float* R_body, float* aa, cu
         k_vp_split<<<cdiv(B * 32, 256), 256, 0, st>>>(z, B, 32, 32, v->zs);
         TcEpi e1; e1.bias = v->b1; e1.act = 1; e1.split_out = v->h1s; e1.split_ld = 1024; e1.split_lo = 512;
         const int md = vposer_tc_mode();
-        LEMO_TRY(vp_gemm(md, v->m_zs, v->m_w1, v->l_w1, v->n_w1, v->o_w1, v->h1, B, 512, 32, 32, e1, st));
+        LEMO_TRY(vp_gemm(md, v->m_zs, v->m_w1, v->l_w1, v->h1, B, 512, 32, 32, e1, st));
         TcEpi e2; e2.bias = v->b2; e2.act = 1; e2.split_out = v->h2s; e2.split_ld = 1024; e2.split_lo = 512;
-        LEMO_TRY(vp_gemm(md, v->m_h1s, v->m_w2, v->l_w2, v->n_w2, v->o_w2, v->h2, B, 512, 512, 512, e2, st));
+        LEMO_TRY(vp_gemm(md, v->m_h1s, v->m_w2, v->l_w2, v->h2, B, 512, 512, 512, e2, st));
         TcEpi e3; e3.bias = v->b3;
-        LEMO_TRY(vp_gemm(md, v->m_h2s, v->m_w3, v->l_w3, v->n_w3, v->o_w3, v->o, B, 126, 512, 512, e3, st));
+        LEMO_TRY(vp_gemm(md, v->m_h2s, v->m_w3, v->l_w3, v->o, B, 126, 512, 512, e3, st));
         k_vp_gs<<<cdiv(B * NBODY, 128), 128, 0, st>>>(v->o, B * NBODY, R_body, aa);
         LEMO_CUDA(cudaGetLastError());
         return 0;
@@ -163,10 +157,10 @@ int vposer_decode_backward(VPoser* v, const float* z, int B, const float* dR_bod
     if (tc) {
         TcEpi e1; e1.act = 2; e1.mask_src = v->h2; e1.split_out = v->dh2s; e1.split_ld = 1024; e1.split_lo = 512;
         const int md = vposer_tc_mode();
-        LEMO_TRY(vp_gemm(md, v->m_dos, v->m_w3t, v->l_w3t, v->n_w3t, v->o_w3t, v->dh2, B, 512, 128, 128, e1, st));
+        LEMO_TRY(vp_gemm(md, v->m_dos, v->m_w3t, v->l_w3t, v->dh2, B, 512, 128, 128, e1, st));
         TcEpi e2; e2.act = 2; e2.mask_src = v->h1; e2.split_out = v->dh1s; e2.split_ld = 1024; e2.split_lo = 512;
-        LEMO_TRY(vp_gemm(md, v->m_dh2s, v->m_w2t, v->l_w2t, v->n_w2t, v->o_w2t, v->dh1, B, 512, 512, 512, e2, st));
-        LEMO_TRY(vp_gemm(md, v->m_dh1s, v->m_w1t, v->l_w1t, v->n_w1t, v->o_w1t, dz, B, 32, 512, 512, TcEpi{}, st));
+        LEMO_TRY(vp_gemm(md, v->m_dh2s, v->m_w2t, v->l_w2t, v->dh1, B, 512, 512, 512, e2, st));
+        LEMO_TRY(vp_gemm(md, v->m_dh1s, v->m_w1t, v->l_w1t, dz, B, 32, 512, 512, TcEpi{}, st));
         return 0;
     }
     // dh2 = (d_o . W3) * lrelu'(h2) ;  W3 is [126,512] row-major = B operand [K=126, N=512]

@@ -15,9 +15,6 @@ struct VPoser {
     alignas(64) unsigned char m_w1[128], m_w2[128], m_w3[128], m_w1t[128], m_w2t[128], m_w3t[128];
     alignas(64) unsigned char l_w1[128], l_w2[128], l_w3[128], l_w1t[128], l_w2t[128], l_w3t[128];
     alignas(64) unsigned char m_zs[128], m_h1s[128], m_h2s[128], m_dos[128], m_dh2s[128], m_dh1s[128];
-    // the same weight operands with 64-row TMA boxes for the K-chunked GEMM (k_gemm_tc64, LEMO_VPOSER=tc64, experimental)
-    alignas(64) unsigned char n_w1[128], n_w2[128], n_w3[128], n_w1t[128], n_w2t[128], n_w3t[128];
-    alignas(64) unsigned char o_w1[128], o_w2[128], o_w3[128], o_w1t[128], o_w2t[128], o_w3t[128];
 };
 int vposer_create(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
                   int maxB, int device, VPoser** out);
