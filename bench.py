@@ -473,7 +473,22 @@ def main():
                             'SMPL-X evaluated once', 'ms_per_iteration': pms, 'iterations_per_sec': 1e3 / pms,
                 'gpu_launches_per_iteration': (pfit.kernel_launches() - l0p) / n_p,
                 'window_900_iterations_s': 0.9 * pms, 'final_loss': float(pfit.losses()['total_loss'])}
-        # Chamfer nearest-neighbour kernels alone (8 B n m flop against the fp32 FMA roof): brute force vs the static-scene query
+        # the same window on a model whose skinning weights have 4 influences per vertex, like the real SMPL-X (the default synthetic
+        # model is dense over all 55 joints): the full-mesh skinning adjoint then runs over the non-zeros (k_skin_bwd_sp_*)
+        del pfit
+        body_sp = smplx.create(synth.make_smplx_model(0, weights_nnz=4), model_type='smplx', gender='male', ext='npz', num_pca_comps=12,
+                               batch_size=100).to(dev)
+        pfit, _, _ = make_window(body_sp, vp, enc, B=100, D=256, m_scene=100000, seed=3, device=dev, use_cuda_graph=not a.no_graph)
+        pfit.run(5)
+        torch.cuda.synchronize(dev)
+        c0.record()
+        pfit.run(n_p)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        prox['ms_per_iteration_sparse_skinning_weights'] = c0.elapsed_time(c1) / n_p
+        prox['sparse_note'] = ('same window, synthetic model with 4 skinning influences per vertex (real SMPL-X sparsity) instead of dense '
+                               'random weights: skinning adjoint over the non-zeros')
+        del pfit, body_sp
         import ctypes as C
         xs = torch.randn(100000, 3, device=dev) * torch.tensor([3.0, 3.0, 0.05], device=dev)
         xq = torch.randn(100, 1121, 3, device=dev) * torch.tensor([1.0, 1.0, 0.5], device=dev)

@@ -104,6 +104,9 @@ int lemo_debug_set_blend_tc(int32_t on);
 /* A/B switch for full-mesh skinning (lbs.py:106-117): 1 = tcgen05 TF32 3-term GEMM with the 3x4 apply as its epilogue (default),
    0 = CUDA-core kernel.  Debug/measurement only. */
 int lemo_debug_set_skin_tc(int32_t on);
+/* 1 (default): full models whose skinning weights are sparse (< 25 % non-zero, like the real SMPL-X) run the adjoint over the non-zeros;
+   0: always the dense 55-wide adjoint.  Both are deterministic; they differ by summation order only. */
+int lemo_debug_set_skin_sparse(int32_t on);
 
 /* replaces verts[:, ids, :] gathers     (opt_amass_temp.py:359,366,416-425; bit-exact integer indexing) */
 int lemo_gather_rows(const float* src, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* out, void* stream);

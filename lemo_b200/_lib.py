@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get('LEMO_NVCC_EXTRA', '').split() + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
@@ -115,6 +115,7 @@ SIGNATURES = {
     'lemo_smplx_backward': (C.c_int, [_P, C.POINTER(LemoPoseC), _I, _P, _P, C.POINTER(LemoPoseGradC), _P]),
     'lemo_debug_set_blend_tc': (C.c_int, [_I]),
     'lemo_debug_set_skin_tc': (C.c_int, [_I]),
+    'lemo_debug_set_skin_sparse': (C.c_int, [_I]),
     'lemo_gather_rows': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_scatter_rows_add': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_rot6d_to_rotmat': (C.c_int, [_P, _I, _P, _P]),

@@ -73,6 +73,10 @@ bool skin_tc_enabled() {
     return g_skin_tc == 1;
 }
 void skin_tc_set(int on) { g_skin_tc = on ? 1 : 0; }
+// sparse full-mesh skinning adjoint (Model::sk_*): on whenever the model's weights are sparse; LEMO_SKIN_ADJ=dense / lemo_debug_set_skin_sparse(0)
+// force the dense kernel (parity tests compare the two)
+static int g_skin_sparse = []() { const char* e = getenv("LEMO_SKIN_ADJ"); return (e && strcmp(e, "dense") == 0) ? 0 : 1; }();
+void skin_sparse_set(int on) { g_skin_sparse = on ? 1 : 0; }
 
 // K-major transposed copy of Wt + its TMA descriptor for the tensor-core blend GEMM
 static int model_setup_tc(Model* m) {
@@ -124,6 +128,38 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
         for (int v = 0; v < V; ++v)
             for (int j = 0; j < NJ; ++j) wjm[(size_t)j * V + v] = d->h_lbs_weights[(size_t)v * NJ + j];
         LEMO_TRY(dev_upload(&m->w_jm, wjm.data(), wjm.size()));
+        const int ntile = cdiv(V, SKB_TV);
+        if (ntile > 2) {                                              // compact adjoint tables (see Model::sk_*)
+            std::vector<int> aoff(ntile + 1), aj;
+            for (int t = 0; t < ntile; ++t) {
+                aoff[t] = (int)aj.size();
+                for (int j = 0; j < NJ; ++j) {
+                    bool any = false;
+                    for (int v = t * SKB_TV; v < std::min(V, (t + 1) * SKB_TV) && !any; ++v) any = wjm[(size_t)j * V + v] != 0.f;
+                    if (any) aj.push_back(j);
+                }
+            }
+            aoff[ntile] = (int)aj.size();
+            if (aj.size() * 5 < (size_t)ntile * NJ * 2) {
+                const int ns = (int)aj.size();
+                std::vector<float> w((size_t)ns * SKB_TV, 0.f);
+                std::vector<int> joff(NJ + 1), jslot;
+                for (int t = 0; t < ntile; ++t)
+                    for (int sl = aoff[t]; sl < aoff[t + 1]; ++sl)
+                        for (int u = 0; u < SKB_TV && t * SKB_TV + u < V; ++u) w[(size_t)sl * SKB_TV + u] = wjm[(size_t)aj[sl] * V + t * SKB_TV + u];
+                for (int j = 0; j < NJ; ++j) {
+                    joff[j] = (int)jslot.size();
+                    for (int sl = 0; sl < ns; ++sl) if (aj[sl] == j) jslot.push_back(sl);
+                }
+                joff[NJ] = (int)jslot.size();
+                m->sk_ntile = ntile; m->sk_nslot = ns;
+                LEMO_TRY(dev_upload(&m->sk_aoff, aoff.data(), aoff.size()));
+                LEMO_TRY(dev_upload(&m->sk_aj, aj.data(), aj.size()));
+                LEMO_TRY(dev_upload(&m->sk_w, w.data(), w.size()));
+                LEMO_TRY(dev_upload(&m->sk_joff, joff.data(), joff.size()));
+                LEMO_TRY(dev_upload(&m->sk_jslot, jslot.data(), jslot.size()));
+            }
+        }
     }
     {   // fold the joint regressor: J = Jreg.(v_template + shapedirs.beta) = J_template + J_dirs.beta   (double accum)
         std::vector<float> jt(NJ * 3), jd(NJ * 3 * NBETA);
@@ -151,6 +187,34 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
     LEMO_TRY(model_setup_tc(m));
     LEMO_TRY(dev_upload(&m->parents, m->h_parents, NJ));
     LEMO_TRY(dev_upload(&m->depth, m->h_depth, NJ));
+    {
+        LEMO_CHECK(m->max_depth <= TREE_MAX_DEPTH, "kinematic tree deeper than the level table");
+        int t[TREE_N];
+        memset(t, 0, sizeof(t));
+        int pos = 0, k = 0;
+        for (int lev = 0; lev <= m->max_depth + 1; ++lev) {
+            t[TREE_OFF + lev] = pos;
+            for (int j = 0; j < NJ; ++j)
+                if (m->h_depth[j] == lev) t[TREE_ORDER + pos++] = j;
+        }
+        for (int j = 0; j < NJ; ++j) {
+            t[TREE_PAR + j] = m->h_parents[j];
+            t[TREE_KOFF + j] = k;
+            for (int c = j + 1; c < NJ; ++c)
+                if (m->h_parents[c] == j) t[TREE_KLIST + k++] = c;
+        }
+        t[TREE_KOFF + NJ] = k;
+        for (int i = 0; i < (TREE_MAX_DEPTH + 1) * 32; ++i) t[TREE_LANE + i] = -1;
+        for (int lev = 0; lev <= m->max_depth; ++lev) {
+            const int o0 = t[TREE_OFF + lev], o1 = t[TREE_OFF + lev + 1];
+            LEMO_CHECK(o1 - o0 <= 32, "more than 32 joints on one level of the kinematic tree");
+            for (int i = o0; i < o1; ++i) {
+                const int j = t[TREE_ORDER + i];
+                t[TREE_LANE + lev * 32 + (i - o0)] = j | ((m->h_parents[j] + 1) << 8) | (t[TREE_KOFF + j] << 16) | ((t[TREE_KOFF + j + 1] - t[TREE_KOFF + j]) << 24);
+            }
+        }
+        LEMO_TRY(dev_upload(&m->tree, t, TREE_N));
+    }
     LEMO_TRY(dev_upload(&m->hand_l, d->h_hand_comp_l, (size_t)m->npc * 45));
     LEMO_TRY(dev_upload(&m->hand_r, d->h_hand_comp_r, (size_t)m->npc * 45));
     LEMO_TRY(dev_upload(&m->pose_mean, d->h_pose_mean, 165));
@@ -210,6 +274,7 @@ int model_select_rows(const Model* m, const int* rows_host, int n, Model** out) 
     s->V = n;
     s->n_extra = 0; s->n_lmk = 0; s->extra_vids = nullptr; s->lmk_tri = nullptr; s->lmk_bary = nullptr;
     s->n_jv = 0; s->jv_vid = nullptr; s->jv_off = nullptr; s->jv_q = nullptr; s->jv_w = nullptr;
+    s->sk_ntile = 0; s->sk_nslot = 0; s->sk_aoff = nullptr; s->sk_aj = nullptr; s->sk_w = nullptr; s->sk_joff = nullptr; s->sk_jslot = nullptr;
     int* rows_dev = nullptr;
     LEMO_TRY(dev_upload(&rows_dev, rows_host, n));
     LEMO_TRY(dev_alloc(&s->v_template, (size_t)n * 3));
@@ -232,10 +297,11 @@ void model_free(Model* m) {
     cudaSetDevice(m->device);
     cudaFree(m->v_template); cudaFree(m->Wt); cudaFree(m->WtT); cudaFree(m->W2); cudaFree(m->w_jm);
     if (!m->is_sub) {
-        cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth);
+        cudaFree(m->J_template); cudaFree(m->J_dirs); cudaFree(m->parents); cudaFree(m->depth); cudaFree(m->tree);
         cudaFree(m->hand_l); cudaFree(m->hand_r); cudaFree(m->pose_mean);
         cudaFree(m->extra_vids); cudaFree(m->lmk_tri); cudaFree(m->lmk_bary);
         cudaFree(m->jv_vid); cudaFree(m->jv_off); cudaFree(m->jv_q); cudaFree(m->jv_w);
+        cudaFree(m->sk_aoff); cudaFree(m->sk_aj); cudaFree(m->sk_w); cudaFree(m->sk_joff); cudaFree(m->sk_jslot);
     }
     delete m;
 }
@@ -296,18 +362,18 @@ __global__ void __launch_bounds__(64) k_pose_to_rot_bwd(PoseK p, PoseGrad g, int
     pose_to_rot_bwd_body(p, g, B, full_pose, dR, blockIdx.x);
 }
 __global__ void __launch_bounds__(64) k_pose_chain_fwd(PoseK p, const float* __restrict__ J_template, const float* __restrict__ J_dirs,
-                                                       const int* __restrict__ parents, const int* __restrict__ depth, int max_depth,
+                                                       const int* __restrict__ tree, int max_depth,
                                                        float* __restrict__ full_pose, float* __restrict__ R, float* __restrict__ X,
                                                        float* __restrict__ X2, float* __restrict__ G, float* __restrict__ A,
                                                        float* __restrict__ Jrest, float* __restrict__ Jposed, float* __restrict__ A2) {
-    pose_chain_fwd_body(p, J_template, J_dirs, parents, depth, max_depth, full_pose, R, X, X2, G, A, Jrest, Jposed, A2, blockIdx.x);
+    pose_chain_fwd_body(p, J_template, J_dirs, tree, max_depth, full_pose, R, X, X2, G, A, Jrest, Jposed, A2, blockIdx.x);
 }
 __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
                                                   const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
-                                                  const float* __restrict__ J_dirs, const int* __restrict__ parents,
-                                                  const int* __restrict__ depth, int max_depth, int B, int betas_stride,
+                                                  const float* __restrict__ J_dirs, const int* __restrict__ tree, int max_depth, int B,
+                                                  int betas_stride,
                                                   float* __restrict__ dR, float* __restrict__ dbetas, float* __restrict__ dexpr) {
-    chain_bwd_body(R, G, Jrest, dA, dJp, dX, J_dirs, parents, depth, max_depth, B, betas_stride, dR, dbetas, dexpr, blockIdx.x);
+    chain_bwd_body(R, G, Jrest, dA, dJp, dX, J_dirs, tree, max_depth, B, betas_stride, dR, dbetas, dexpr, blockIdx.x);
 }
 
 
@@ -449,6 +515,113 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
     s = block_sum(gs1, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 1] = s; else atomicAdd(&dtr[b * 3 + 1], s); }
     s = block_sum(gs2, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 2] = s; else atomicAdd(&dtr[b * 3 + 2], s); }
 }
+// ---- compact skinning adjoint (full meshes with sparse weights; same result as k_skin_bwd up to summation order, fixed order throughout).
+// One CTA per (tile of 256 vertices, frame).  Phase A, thread = vertex: T = sum over the tile's ACTIVE joints of w A_j.R, d v_posed = T^T g,
+// dT = g (x) [v_posed, 1] parked in shared memory.  Phase B, thread = (active-joint slot a, vertex residue r of 16): the 12 entries of
+// dA[joint(a)] over the vertices u = r mod 16, then the 16 residues are added in order and the slot's 12 sums are written to
+// partc[frame][slot]; k_skin_bwd_act_reduce adds the slots of a joint in tile order.
+__global__ void __launch_bounds__(256) k_skin_bwd_act(const float* __restrict__ A, const int* __restrict__ aoff, const int* __restrict__ aj,
+                                                      const float* __restrict__ wact, const float* __restrict__ VP, const float* __restrict__ Gv,
+                                                      int V, int B, int nslot, float* __restrict__ DVP, float* __restrict__ partc,
+                                                      float* __restrict__ part_tr) {
+    __shared__ float sA[NJ * 12];
+    __shared__ __align__(16) float s_dt[SKB_TV * 12];
+    __shared__ float s_part[16][16][12];
+    __shared__ float sred[32];
+    __shared__ int s_j[NJ];
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int s0 = aoff[tile], na = aoff[tile + 1] - s0;
+    for (int i = threadIdx.x; i < NJ * 12; i += 256) sA[i] = A[(size_t)b * NJ * 12 + i];
+    if (threadIdx.x < na) s_j[threadIdx.x] = aj[s0 + threadIdx.x];
+    __syncthreads();
+    const int u = threadIdx.x, v = tile * SKB_TV + u;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    float dt[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) dt[k] = 0.f;
+    if (v < V) {
+        float T[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) T[k] = 0.f;
+        for (int a = 0; a < na; ++a) {
+            const float w = __ldg(wact + (size_t)(s0 + a) * SKB_TV + u);
+            const float* aa = sA + s_j[a] * 12;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[i * 3 + c] = fmaf(w, aa[i * 4 + c], T[i * 3 + c]);
+        }
+        const float* g = Gv + ((size_t)b * V + v) * 3;
+        g0 = g[0]; g1 = g[1]; g2 = g[2];
+        const float* vp = VP + ((size_t)b * V + v) * 3;
+        const float p[4] = {vp[0], vp[1], vp[2], 1.f};
+        float* dvp = DVP + ((size_t)b * V + v) * 3;
+        dvp[0] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+        dvp[1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+        dvp[2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+        const float gg[3] = {g0, g1, g2};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dt[i * 4 + c] = gg[i] * p[c];
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < 3; ++k4)
+        *reinterpret_cast<float4*>(&s_dt[u * 12 + k4 * 4]) = make_float4(dt[k4 * 4], dt[k4 * 4 + 1], dt[k4 * 4 + 2], dt[k4 * 4 + 3]);
+    __syncthreads();
+    const int a = threadIdx.x >> 4, r = threadIdx.x & 15;
+    for (int a0 = 0; a0 < na; a0 += 16) {
+        float acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+        if (a0 + a < na) {
+            const float* wrow = wact + (size_t)(s0 + a0 + a) * SKB_TV;
+#pragma unroll 4
+            for (int uu = r; uu < SKB_TV; uu += 16) {
+                const float w = __ldg(wrow + uu);
+                const float4* d = reinterpret_cast<const float4*>(&s_dt[uu * 12]);
+                const float4 d0 = d[0], d1 = d[1], d2 = d[2];
+                acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]); acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]); acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                acc[8] = fmaf(w, d2.x, acc[8]); acc[9] = fmaf(w, d2.y, acc[9]); acc[10] = fmaf(w, d2.z, acc[10]); acc[11] = fmaf(w, d2.w, acc[11]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_part[a][r][k] = acc[k];
+        __syncthreads();
+        if (threadIdx.x < 16 * 12) {
+            const int aa = threadIdx.x / 12, k = threadIdx.x - aa * 12;
+            if (a0 + aa < na) {
+                float sum = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) sum += s_part[aa][rr][k];
+                partc[((size_t)b * nslot + s0 + a0 + aa) * 12 + k] = sum;
+            }
+        }
+        __syncthreads();
+    }
+    float* pt = part_tr + ((size_t)tile * B + b) * 3;
+    float s;
+    s = block_sum(g0, sred); if (threadIdx.x == 0) pt[0] = s;
+    s = block_sum(g1, sred); if (threadIdx.x == 0) pt[1] = s;
+    s = block_sum(g2, sred); if (threadIdx.x == 0) pt[2] = s;
+}
+__global__ void k_skin_bwd_act_reduce(const float* __restrict__ partc, const int* __restrict__ joff, const int* __restrict__ jslot, int nslot,
+                                      const float* __restrict__ part_tr, int ntile, int B, float* __restrict__ dA, float* __restrict__ dtr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * SKB_PART) return;
+    const int b = i / SKB_PART, t = i - b * SKB_PART;
+    float a = 0.f;
+    if (t < NJ * 12) {
+        const int j = t / 12, k = t - j * 12;
+        for (int q = joff[j]; q < joff[j + 1]; ++q) a += partc[((size_t)b * nslot + jslot[q]) * 12 + k];
+        dA[(size_t)j * B * 12 + (size_t)b * 12 + k] += a;
+    } else {
+        for (int p = 0; p < ntile; ++p) a += part_tr[((size_t)p * B + b) * 3 + (t - NJ * 12)];
+        dtr[b * 3 + (t - NJ * 12)] += a;
+    }
+}
+
 __global__ void k_skin_bwd_reduce(const float* __restrict__ part, int nparts, int B, float* __restrict__ dA, float* __restrict__ dtr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * SKB_PART) return;
@@ -549,7 +722,7 @@ static PoseK make_posek(const Model* m, const PoseIn& in) {
 int body_pose_forward(BodyCtx* c, const PoseIn& in, int B, cudaStream_t st) {
     LEMO_CHECK(c && B > 0 && B <= c->maxB, "batch exceeds the size this body handle was created for");
     const Model* m = c->m;
-    k_pose_chain_fwd<<<B, 64, 0, st>>>(make_posek(m, in), m->J_template, m->J_dirs, m->parents, m->depth, m->max_depth, c->full_pose,
+    k_pose_chain_fwd<<<B, 64, 0, st>>>(make_posek(m, in), m->J_template, m->J_dirs, m->tree, m->max_depth, c->full_pose,
                                         c->R, c->X, c->X2, c->G, c->A, c->Jrest, c->Jposed, c->A2);
     LEMO_CUDA(cudaGetLastError());
     return 0;
@@ -620,8 +793,19 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
         const int ntile = cdiv(V, SKB_TV);
         const int tiles = skin_bwd_tiles(V, B), ctas = cdiv(ntile, tiles);
         float* part = (ctas > 1 && c->part && (size_t)ctas * B * SKB_PART <= c->part_floats) ? c->part : nullptr;
-        k_skin_bwd<<<dim3(ctas, B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr, part);
-        if (part) k_skin_bwd_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(part, ctas, B, ps->dA, ps->dtr);
+        const bool sparse = g_skin_sparse && m->sk_nslot > 0 && c->part &&
+                            (size_t)B * m->sk_nslot * 12 + (size_t)m->sk_ntile * B * 3 <= c->part_floats;
+        if (sparse) {
+            float* partc = c->part;
+            float* part_tr = c->part + (size_t)B * m->sk_nslot * 12;
+            k_skin_bwd_act<<<dim3(m->sk_ntile, B), 256, 0, st>>>(ps->A, m->sk_aoff, m->sk_aj, m->sk_w, c->VP, c->Gv, V, B, m->sk_nslot, c->DVP,
+                                                                 partc, part_tr);
+            k_skin_bwd_act_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(partc, m->sk_joff, m->sk_jslot, m->sk_nslot, part_tr, m->sk_ntile, B,
+                                                                           ps->dA, ps->dtr);
+        } else {
+            k_skin_bwd<<<dim3(ctas, B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr, part);
+            if (part) k_skin_bwd_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(part, ctas, B, ps->dA, ps->dtr);
+        }
     }
     LEMO_CUDA(cudaGetLastError());
     // dX[B,512] += DVP[B,3V] . Wt^T        (contraction over 3V: split-K with atomics)
@@ -651,7 +835,7 @@ int body_pose_backward(BodyCtx* c, const PoseIn& in, int B, const PoseGrad& g, c
     LEMO_CHECK(c && c->dA, "body handle was created without backward buffers");
     const Model* m = c->m;
     if (g.betas && in.betas_stride == 0) LEMO_CUDA(cudaMemsetAsync(g.betas, 0, 10 * sizeof(float), st));
-    k_chain_bwd<<<B, 64, 0, st>>>(c->R, c->G, c->Jrest, c->dA, c->dJp, c->dX, m->J_dirs, m->parents, m->depth, m->max_depth, B,
+    k_chain_bwd<<<B, 64, 0, st>>>(c->R, c->G, c->Jrest, c->dA, c->dJp, c->dX, m->J_dirs, m->tree, m->max_depth, B,
                                    in.betas_stride, c->dR, g.betas, g.expression);
     k_pose_to_rot_bwd<<<B, 64, 0, st>>>(make_posek(m, in), g, B, c->full_pose, c->dR);
     if (g.transl) k_copy<<<cdiv(B * 3, 128), 128, 0, st>>>(c->dtr, g.transl, B * 3);

@@ -5,6 +5,17 @@
 
 namespace lemo {
 
+// Kinematic-tree tables (ints, built once per model on the host): the chain walks are done by ONE warp, level by level, lane i taking the
+// i-th joint of the level, with __syncwarp() between levels instead of CTA barriers.
+constexpr int TREE_PAR = 0;        // [55] parent of joint j (-1 for the root)
+constexpr int TREE_ORDER = 56;     // [55] joints sorted by (depth, index)
+constexpr int TREE_OFF = 112;      // [max_depth + 2] first position of each level in ORDER
+constexpr int TREE_KOFF = 128;     // [56] children of joint j = KLIST[KOFF[j] .. KOFF[j+1]) in ascending index
+constexpr int TREE_KLIST = 184;    // [54]
+constexpr int TREE_LANE = 240;     // [TREE_MAX_DEPTH + 1][32] one word per (level, lane): joint | (parent + 1) << 8 | KOFF << 16 | n_children << 24, or -1
+constexpr int TREE_N = 240 + 15 * 32;
+constexpr int TREE_MAX_DEPTH = 14;
+
 constexpr int SKIN_TC_FR = 8;      // frames per unit of the tensor-core skinning kernel (layout of BodyCtx::A2)
 
 // Immutable device-resident model (created once per gender per device).
@@ -28,6 +39,7 @@ struct Model {
     float* J_dirs = nullptr;       // [55,3,20]  J_regressor . shapedirs
     int* parents = nullptr;        // [55] device
     int* depth = nullptr;          // [55] device
+    int* tree = nullptr;           // [TREE_N] device: level-ordered tree tables (see TREE_*)
     float* hand_l = nullptr;       // [npc,45]
     float* hand_r = nullptr;
     float* pose_mean = nullptr;    // [165]
@@ -39,9 +51,18 @@ struct Model {
     int n_jv = 0;
     int *jv_vid = nullptr, *jv_off = nullptr, *jv_q = nullptr;
     float* jv_w = nullptr;
+    // compact view of the skinning weights for the full-mesh adjoint (real SMPL-X weights have a handful of influences per vertex, so a
+    // tile of 256 consecutive vertices touches ~10 of the 55 joints: the dense 55-wide adjoint spends most of its FMAs on zeros).
+    // Built for full models when the tiles' active-joint lists add up to < 40 % of ntile x 55:
+    //   tile t owns slots [sk_aoff[t], sk_aoff[t+1]); slot s = (joint sk_aj[s], weights sk_w[s][256] of the tile's vertices, zero-filled);
+    //   joint j is finished from the slots sk_jslot[sk_joff[j] .. sk_joff[j+1]) in tile order (fixed order: deterministic)
+    int sk_ntile = 0, sk_nslot = 0;
+    int *sk_aoff = nullptr, *sk_aj = nullptr, *sk_joff = nullptr, *sk_jslot = nullptr;
+    float* sk_w = nullptr;
     int h_parents[NJ];
     int h_depth[NJ];
 };
+
 
 // Pointers describing one batch of pose inputs (device, fp32, contiguous rows).
 struct PoseIn {
@@ -155,6 +176,7 @@ size_t skin_tc_a2_floats(int maxB);
 int skin_tc_launch(const void* map_w2, const void* map_a2, const float* VP, const float* transl, int V, int B, float* verts, cudaStream_t st);
 bool skin_tc_enabled();
 void skin_tc_set(int on);
+void skin_sparse_set(int on);
 
 int gather_rows(const float* src, const int* idx_dev, int B, int V, int n, float* out, cudaStream_t st);
 int scatter_rows_add(const float* g_rows, const int* idx_dev, int B, int V, int n, float* g_dense, cudaStream_t st);

@@ -6,6 +6,14 @@
 
 namespace lemo {
 
+// -DLEMO_BODY_TL: globaltimer stamps inside the bodies (CTA 0, thread 0), read back by the per-frame driver's timeline print (debug builds only)
+#ifdef LEMO_BODY_TL
+static __device__ unsigned long long g_body_tl[32];
+#define BODY_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_body_tl[i] = t_; } } while (0)
+#else
+#define BODY_STAMP(i) do { } while (0)
+#endif
+
 // Barrier of the pose / chain bodies.  SUB64 = false: the whole CTA (stand-alone kernels, 64 threads).  SUB64 = true: named barrier 1
 // over the first 64 threads only -- the persistent per-frame kernel calls the bodies from its warps 0-1 while warps 2-7 wait at the
 // next CTA-wide barrier, so the ~20 level barriers of a chain walk are two-warp barriers instead of eight-warp ones.
@@ -56,6 +64,7 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
                                                      const float* __restrict__ dR, int b) {
     __shared__ float s_daa[NJ * 3];
     const int j = threadIdx.x;
+    BODY_STAMP(14);
     if (j < NJ) {
         const float* dr = dR + (b * NJ + j) * 9;
         const bool ov = (j == 0 && p.in.R_global) || (j >= 1 && j <= NBODY && p.in.R_body);
@@ -84,7 +93,9 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
             if (o) for (int k = 0; k < 3; ++k) o[k] = daa[k];
         }
     }
+    BODY_STAMP(15);
     body_sync<SUB64>();
+    BODY_STAMP(16);
     if (p.in.hand_is_pca && j < 2 * p.npc) {
         const bool left = j < p.npc;
         const int c = left ? j : j - p.npc;
@@ -97,6 +108,7 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
             base[b * p.npc + c] = acc;
         }
     }
+    BODY_STAMP(17);
 }
 
 // =============================================================================================
@@ -109,19 +121,24 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
 // (Two kernels -- one thread per (frame, joint), then this block shape -- cost 5.5 + 8 us per forward at B=120; forking the chain
 // onto a side stream beside the blend GEMM was measured too: the fork/join edges cost what the overlap saves.)
 // =============================================================================================
+// want_aa = false skips the axis-angle of rotation-matrix overrides (only the saved [T,72] rows need it).
 template <bool SUB64 = false>
 __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float* __restrict__ J_template,
-                                                    const float* __restrict__ J_dirs, const int* __restrict__ parents,
-                                                    const int* __restrict__ depth, int max_depth, float* __restrict__ full_pose,
+                                                    const float* __restrict__ J_dirs, const int* __restrict__ tree, int max_depth,
+                                                    float* __restrict__ full_pose,
                                                     float* __restrict__ R, float* __restrict__ X, float* __restrict__ X2,
                                                     float* __restrict__ G,
                                                     float* __restrict__ A, float* __restrict__ Jrest, float* __restrict__ Jposed,
-                                                    float* __restrict__ A2, int b) {
-    __shared__ float sG[NJ][12];
+                                                    float* __restrict__ A2, int b, bool want_aa = true) {
+    __shared__ __align__(16) float sG[NJ][12];
     __shared__ float sJ[NJ][3];
-    __shared__ float sbeta[NBETA];
-    __shared__ float sX[XK];
+    __shared__ float sR[NJ][9];
+    __shared__ __align__(16) float sbeta[NBETA];   // 16-byte aligned: the compiler reads it with LDS.128, which otherwise straddles a neighbour array (racecheck)
+    __shared__ __align__(16) float sX[XK];
     const int j = threadIdx.x;
+    const int nthr = SUB64 ? 64 : blockDim.x;
+    int e = tree[TREE_LANE + (threadIdx.x & 31)];          // level-0 word of the tree walk below, requested early
+    BODY_STAMP(0);
     if (j < NBETA) {
         float v = 0.f;
         if (j < 10) v = p.in.betas ? p.in.betas[(size_t)b * p.in.betas_stride + j] : 0.f;
@@ -130,27 +147,28 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
         sX[NPF + j] = v;
     }
     if (j >= NBETA && j < XK - NPF) sX[NPF + j] = 0.f;
-    float r[9];
-    int par = -1, dep = 0;
     if (j < NJ) {
-        float aa[3];
+        float aa[3], r[9];
         const float* Rov = nullptr;
         if (j == 0 && p.in.R_global) Rov = p.in.R_global + b * 9;
         if (j >= 1 && j <= NBODY && p.in.R_body) Rov = p.in.R_body + (b * NBODY + (j - 1)) * 9;
         if (Rov) {
             for (int k = 0; k < 9; ++k) r[k] = Rov[k];
-            rotmat_to_aa_tgm(r, aa);                 // what the reference scripts store in the [T,72] result
+            if (want_aa) rotmat_to_aa_tgm(r, aa);    // what the reference scripts store in the [T,72] result
+            else aa[0] = aa[1] = aa[2] = 0.f;
         } else {
             joint_aa(p, b, j, aa);
             rodrigues_fwd(aa, r);
         }
         for (int k = 0; k < 3; ++k) full_pose[b * 165 + j * 3 + k] = aa[k];
-        for (int k = 0; k < 9; ++k) R[((size_t)b * NJ + j) * 9 + k] = r[k];
+        for (int k = 0; k < 9; ++k) { R[((size_t)b * NJ + j) * 9 + k] = r[k]; sR[j][k] = r[k]; }
         if (j >= 1)
             for (int k = 0; k < 9; ++k) sX[(j - 1) * 9 + k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
     }
+    BODY_STAMP(1);
     body_sync<SUB64>();
-    for (int k = threadIdx.x; k < XK; k += (SUB64 ? 64 : blockDim.x)) {
+    BODY_STAMP(2);
+    for (int k = threadIdx.x; k < XK; k += nthr) {
         const float x = sX[k];
         uint32_t t;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));       // round to nearest: k_blend_v2 multiplies most columns by Xhi alone
@@ -169,27 +187,54 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
             sJ[j][k] = acc;
             Jrest[((size_t)b * NJ + j) * 3 + k] = acc;
         }
-        par = parents[j]; dep = depth[j];
     }
+    BODY_STAMP(3);
     body_sync<SUB64>();
-    for (int lev = 0; lev <= max_depth; ++lev) {
-        if (j < NJ && dep == lev) {
-            float g[12];
-            if (lev == 0) {
-                for (int i = 0; i < 3; ++i) { g[i * 4] = r[i * 3]; g[i * 4 + 1] = r[i * 3 + 1]; g[i * 4 + 2] = r[i * 3 + 2]; g[i * 4 + 3] = sJ[j][i]; }
-            } else {
-                const float* gp = sG[par];
-                const float t[3] = {sJ[j][0] - sJ[par][0], sJ[j][1] - sJ[par][1], sJ[j][2] - sJ[par][2]};
-                for (int i = 0; i < 3; ++i) {
-                    for (int c = 0; c < 3; ++c)
-                        g[i * 4 + c] = gp[i * 4] * r[c] + gp[i * 4 + 1] * r[3 + c] + gp[i * 4 + 2] * r[6 + c];
-                    g[i * 4 + 3] = gp[i * 4] * t[0] + gp[i * 4 + 1] * t[1] + gp[i * 4 + 2] * t[2] + gp[i * 4 + 3];
-                }
+    BODY_STAMP(4);
+    // the chain (lbs.py:196-263): warp 0 walks the tree level by level, lane i = i-th joint of the level (one packed table word per level
+    // and lane); only __syncwarp between levels.  Everything a level needs except its parents' transforms -- the table word, the joint's
+    // rotation and its offset from the parent -- is fetched one level ahead, so a level costs one shared-memory round trip plus the 3x4 product.
+    if (threadIdx.x < 32) {
+        float r[9], t[3];
+        auto fetch = [&](int w) {
+            if (w >= 0) {
+                const int jj = w & 255, par = ((w >> 8) & 255) - 1;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) r[k] = sR[jj][k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) t[k] = par < 0 ? sJ[jj][k] : sJ[jj][k] - sJ[par][k];
             }
-            for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
+        };
+        fetch(e);
+        for (int lev = 0; lev <= max_depth; ++lev) {
+            const int e_next = lev < max_depth ? tree[TREE_LANE + (lev + 1) * 32 + threadIdx.x] : -1;
+            if (e >= 0) {
+                const int jj = e & 255, par = ((e >> 8) & 255) - 1;
+                float g[12];
+                if (par < 0) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { g[q * 4] = r[q * 3]; g[q * 4 + 1] = r[q * 3 + 1]; g[q * 4 + 2] = r[q * 3 + 2]; g[q * 4 + 3] = t[q]; }
+                } else {
+                    const float* gp = sG[par];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            g[q * 4 + c] = gp[q * 4] * r[c] + gp[q * 4 + 1] * r[3 + c] + gp[q * 4 + 2] * r[6 + c];
+                        g[q * 4 + 3] = gp[q * 4] * t[0] + gp[q * 4 + 1] * t[1] + gp[q * 4 + 2] * t[2] + gp[q * 4 + 3];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) sG[jj][k] = g[k];
+            }
+            fetch(e_next);
+            __syncwarp();
+            e = e_next;
         }
-        body_sync<SUB64>();
     }
+    BODY_STAMP(5);
+    body_sync<SUB64>();
+    BODY_STAMP(6);
     if (j < NJ) {
         const float* g = sG[j];
         float* go = G + ((size_t)b * NJ + j) * 12;
@@ -211,30 +256,33 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
             }
         }
     }
+    BODY_STAMP(7);
 }
 
 // adjoint of k_chain_fwd.  dA is joint-major [55][B*12]; dJp [B,55,3]; dX [B,512].
 // Writes dR [B,55,9]; betas/expression grads (per frame, or atomically into one row when betas_stride==0).
-template <bool SUB64 = false>
+// NEED_J = false drops the rest-joint adjoint (it only feeds the betas / expression gradients).
+template <bool SUB64 = false, bool NEED_J = true>
 __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
                                                const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
-                                               const float* __restrict__ J_dirs, const int* __restrict__ parents,
-                                               const int* __restrict__ depth, int max_depth, int B, int betas_stride,
+                                               const float* __restrict__ J_dirs, const int* __restrict__ tree, int max_depth, int B,
+                                               int betas_stride,
                                                float* __restrict__ dR, float* __restrict__ dbetas, float* __restrict__ dexpr, int b) {
     __shared__ float sdG[NJ][12];     // dL/dG  (3x4)
     __shared__ float sdJ[NJ][3];      // dL/dJrest
     __shared__ float sC[NJ][15];      // per-joint contribution to its parent: dG (12) + dJrest[parent] (3)
-    __shared__ int spar[NJ];
-    __shared__ float sG[NJ][12];      // global transforms of this frame (parents are read from here, not from HBM, inside the level loop)
+    __shared__ float sG[NJ][12];      // global transforms of this frame
     __shared__ float sJr[NJ][3];
+    __shared__ float sR[NJ][9];
+    __shared__ float sdR[NJ][9];      // chain part of dR; the blend-shape part dX is added by all threads after the walk
     const int j = threadIdx.x;
-    float r[9], gl[12], Jr[3];
-    int par = -1, dep = 0;
+    int e = tree[TREE_LANE + max_depth * 32 + (threadIdx.x & 31)];      // deepest level's word of the walk below, requested early
+    BODY_STAMP(8);
     if (j < NJ) {
-        for (int k = 0; k < 9; ++k) r[k] = R[((size_t)b * NJ + j) * 9 + k];
+        float gl[12], Jr[3];
+        for (int k = 0; k < 9; ++k) sR[j][k] = R[((size_t)b * NJ + j) * 9 + k];
         for (int k = 0; k < 12; ++k) sG[j][k] = gl[k] = G[((size_t)b * NJ + j) * 12 + k];
         for (int k = 0; k < 3; ++k) sJr[j][k] = Jr[k] = Jrest[((size_t)b * NJ + j) * 3 + k];
-        par = parents[j]; dep = depth[j];
         const float* da = dA + (size_t)j * B * 12 + (size_t)b * 12;
         float dAt[3] = {da[3], da[7], da[11]};
         // A.R = G.R ; A.t = G.t - G.R J
@@ -243,58 +291,100 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
             sdG[j][i * 4 + 3] = dAt[i] + (dJp ? dJp[((size_t)b * NJ + j) * 3 + i] : 0.f);
         }
         // dJ += -G.R^T dAt
-        for (int c = 0; c < 3; ++c) sdJ[j][c] = -(gl[c] * dAt[0] + gl[4 + c] * dAt[1] + gl[8 + c] * dAt[2]);
+        if (NEED_J)
+            for (int c = 0; c < 3; ++c) sdJ[j][c] = -(gl[c] * dAt[0] + gl[4 + c] * dAt[1] + gl[8 + c] * dAt[2]);
     }
-    if (j < NJ) spar[j] = par;
+    BODY_STAMP(9);
     body_sync<SUB64>();
-    unsigned long long kids = 0ull;   // children of joint j as a bit mask, walked in ascending order below
-    if (j < NJ)
-        for (int c = j + 1; c < NJ; ++c)
-            if (spar[c] == j) kids |= 1ull << c;
-    // children -> parent accumulation in a FIXED order (no shared-memory atomics): results are bitwise reproducible,
-    // which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same parameters).
-    for (int lev = max_depth; lev >= 1; --lev) {
-        if (j < NJ && dep == lev) {
-            const float* gp = sG[par];                                // parent's global transform
-            float gpR[9] = {gp[0], gp[1], gp[2], gp[4], gp[5], gp[6], gp[8], gp[9], gp[10]};
-            float dGr[9] = {sdG[j][0], sdG[j][1], sdG[j][2], sdG[j][4], sdG[j][5], sdG[j][6], sdG[j][8], sdG[j][9], sdG[j][10]};
-            float dGt[3] = {sdG[j][3], sdG[j][7], sdG[j][11]};
-            const float* Jp = sJr[par];
-            const float t[3] = {Jr[0] - Jp[0], Jr[1] - Jp[1], Jr[2] - Jp[2]};
-            float dr[9], dpr[9], dt[3];
-            m3_mul_at(gpR, dGr, dr);               // dR_j = Gp.R^T dG_j.R
-            m3_mul_bt(dGr, r, dpr);                // dGp.R += dG_j.R R_j^T
-            m3t_vec(gpR, dGt, dt);                 // dt = Gp.R^T dG_j.t
-            float* o = dR + ((size_t)b * NJ + j) * 9;
+    BODY_STAMP(10);
+    // children -> parent accumulation, deepest level first, by warp 0 alone (lane i = i-th joint of the level, one __syncwarp per level).
+    // When a joint's turn comes it first adds what its children left for it, in ascending child index: FIXED order, no shared-memory
+    // atomics -- results are bitwise reproducible, which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same
+    // parameters).  The static operands of a level (parent rotation, own rotation, offset, child list) are fetched one level ahead.
+    if (threadIdx.x < 32) {
+        float gpR[9], rr[9], t[3];
+        int kid[6];
+        auto fetch = [&](int w) {
+            if (w >= 0) {
+                const int jj = w & 255, par = ((w >> 8) & 255) - 1, k0 = (w >> 16) & 255, nk = (w >> 24) & 255;
+                if (par >= 0) {
+                    const float* gp = sG[par];
+                    gpR[0] = gp[0]; gpR[1] = gp[1]; gpR[2] = gp[2]; gpR[3] = gp[4]; gpR[4] = gp[5]; gpR[5] = gp[6]; gpR[6] = gp[8]; gpR[7] = gp[9]; gpR[8] = gp[10];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) rr[k] = sR[jj][k];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) t[k] = sJr[jj][k] - sJr[par][k];
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) kid[q] = q < nk ? tree[TREE_KLIST + k0 + q] : 0;
+            }
+        };
+        fetch(e);
+        for (int lev = max_depth; lev >= 0; --lev) {
+            const int e_next = lev > 0 ? tree[TREE_LANE + (lev - 1) * 32 + threadIdx.x] : -1;
+            if (e >= 0) {
+                const int jj = e & 255, par = ((e >> 8) & 255) - 1, k0 = (e >> 16) & 255, nk = (e >> 24) & 255;
+                float dG[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) dG[k] = sdG[jj][k];
+                for (int q = 0; q < nk; ++q) {
+                    const int c = q < 6 ? kid[q] : tree[TREE_KLIST + k0 + q];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) dG[k] += sC[c][k];
+                }
+                if (par >= 0) {
+                    const float dGr[9] = {dG[0], dG[1], dG[2], dG[4], dG[5], dG[6], dG[8], dG[9], dG[10]};
+                    const float dGt[3] = {dG[3], dG[7], dG[11]};
+                    float dr[9], dpr[9], dt[3];
+                    m3_mul_at(gpR, dGr, dr);               // dR_j = Gp.R^T dG_j.R
+                    m3_mul_bt(dGr, rr, dpr);               // dGp.R += dG_j.R R_j^T
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) sdR[jj][k] = dr[k];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) sC[jj][q * 4 + c] = dpr[q * 3 + c] + dGt[q] * t[c];
+                        sC[jj][q * 4 + 3] = dGt[q];
+                    }
+                    if (NEED_J) {
+                        m3t_vec(gpR, dGt, dt);             // dt = Gp.R^T dG_j.t
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { sC[jj][12 + q] = -dt[q]; sdJ[jj][q] += dt[q]; }
+                    }
+                } else {                                   // root: its rotation gradient is dG.R itself; the translation feeds its rest joint
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) sdR[jj][q * 3 + c] = dG[q * 4 + c];
+                        if (NEED_J) sdJ[jj][q] += dG[q * 4 + 3];
+                    }
+                }
+            }
+            fetch(e_next);
+            __syncwarp();
+            e = e_next;
+        }
+    }
+    BODY_STAMP(11);
+    body_sync<SUB64>();
+    BODY_STAMP(12);
+    if (NEED_J && j < NJ) {                  // children's share of the rest-joint adjoint (ascending child index)
+        for (int q = tree[TREE_KOFF + j]; q < tree[TREE_KOFF + j + 1]; ++q) {
+            const int c = tree[TREE_KLIST + q];
+            for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
+        }
+    }
+    if (j < NJ) {
+        float* o = dR + ((size_t)b * NJ + j) * 9;
+        if (j == 0) for (int k = 0; k < 9; ++k) o[k] = sdR[0][k];
+        else {
             const float* dx = dX + (size_t)b * XK + (j - 1) * 9;
-            for (int k = 0; k < 9; ++k) o[k] = dr[k] + dx[k];
-            for (int i = 0; i < 3; ++i) {
-                for (int c = 0; c < 3; ++c) sC[j][i * 4 + c] = dpr[i * 3 + c] + dGt[i] * t[c];
-                sC[j][i * 4 + 3] = dGt[i];
-                sC[j][12 + i] = -dt[i];
-                sdJ[j][i] += dt[i];
-            }
-        }
-        body_sync<SUB64>();
-        if (j < NJ && dep == lev - 1) {
-            for (unsigned long long m = kids; m; m &= m - 1) {
-                const int c = __ffsll((long long)m) - 1;
-                for (int k = 0; k < 12; ++k) sdG[j][k] += sC[c][k];
-                for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
-            }
-        }
-        body_sync<SUB64>();
-    }
-    if (j == 0) {
-        float* o = dR + ((size_t)b * NJ) * 9;
-        for (int i = 0; i < 3; ++i) {
-            for (int c = 0; c < 3; ++c) o[i * 3 + c] = sdG[0][i * 4 + c];
-            sdJ[0][i] += sdG[0][i * 4 + 3];
+            for (int k = 0; k < 9; ++k) o[k] = sdR[j][k] + dx[k];
         }
     }
-    body_sync<SUB64>();
+    if (NEED_J) body_sync<SUB64>();
     // betas / expression: direct (X columns) + through Jrest (skipped when neither gradient is requested: 165 loads per thread)
-    if (j < NBETA && (dbetas || dexpr)) {
+    if (NEED_J && j < NBETA && (dbetas || dexpr)) {
         float acc = dX[(size_t)b * XK + NPF + j];
         for (int q = 0; q < NJ; ++q)
             for (int k = 0; k < 3; ++k) acc = fmaf(J_dirs[(q * 3 + k) * NBETA + j], sdJ[q][k], acc);
@@ -305,7 +395,7 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
             }
         } else if (dexpr) dexpr[(size_t)b * 10 + (j - 10)] = acc;
     }
+    BODY_STAMP(13);
 }
-
 
 }  // namespace lemo

@@ -332,10 +332,52 @@ __global__ void k_prep_weights(const float* __restrict__ w, int Cin, int Cout, i
     }
 }
 
+// all layers in ONE launch (the AE fine-tune refreshes 20 layers after every Adam step: 20 launches of ~4 us each were 5 % of a step)
+constexpr int PREP_MAX_LAYERS = 24;
+struct PrepTab {
+    int n;
+    long long start[PREP_MAX_LAYERS + 1];        // prefix sums of Cin*Cout*9
+    long long w_off[PREP_MAX_LAYERS];
+    int Cin[PREP_MAX_LAYERS], Cout[PREP_MAX_LAYERS], transposed[PREP_MAX_LAYERS];
+    float *wk_f[PREP_MAX_LAYERS], *wk_b[PREP_MAX_LAYERS];
+};
+__global__ void k_prep_weights_all(const __grid_constant__ PrepTab t, const float* __restrict__ w_flat) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= t.start[t.n]) return;
+    int l = 0;
+    while (g >= t.start[l + 1]) ++l;
+    const int i = (int)(g - t.start[l]), Cin = t.Cin[l], Cout = t.Cout[l];
+    const float v = w_flat[t.w_off[l] + i];
+    const int k = i % 9, r = i / 9;
+    if (!t.transposed[l]) {
+        const int ic = r % Cin, oc = r / Cin;
+        t.wk_f[l][((size_t)ic * 9 + k) * Cout + oc] = v;
+        t.wk_b[l][((size_t)oc * 9 + (8 - k)) * Cin + ic] = v;
+    } else {
+        const int oc = r % Cout, ic = r / Cout;
+        t.wk_f[l][((size_t)ic * 9 + (8 - k)) * Cout + oc] = v;
+        t.wk_b[l][((size_t)oc * 9 + k) * Cin + ic] = v;
+    }
+}
+
 int convnet_refresh_weights(ConvNet* n, cudaStream_t st) {
-    for (auto& L : n->layers) {
-        const int tot = L.Cin * L.Cout * 9;
-        k_prep_weights<<<cdiv(tot, 256), 256, 0, st>>>(n->w_flat + L.w_off, L.Cin, L.Cout, L.transposed ? 1 : 0, L.wk_f, L.wk_b);
+    if ((int)n->layers.size() <= PREP_MAX_LAYERS) {
+        PrepTab t{};
+        t.n = (int)n->layers.size();
+        long long pos = 0;
+        for (int l = 0; l < t.n; ++l) {
+            const ConvLayer& L = n->layers[l];
+            t.start[l] = pos; pos += (long long)L.Cin * L.Cout * 9;
+            t.w_off[l] = L.w_off; t.Cin[l] = L.Cin; t.Cout[l] = L.Cout; t.transposed[l] = L.transposed ? 1 : 0;
+            t.wk_f[l] = L.wk_f; t.wk_b[l] = L.wk_b;
+        }
+        t.start[t.n] = pos;
+        k_prep_weights_all<<<(unsigned)cdiv(pos, 256), 256, 0, st>>>(t, n->w_flat);
+    } else {
+        for (auto& L : n->layers) {
+            const int tot = L.Cin * L.Cout * 9;
+            k_prep_weights<<<cdiv(tot, 256), 256, 0, st>>>(n->w_flat + L.w_off, L.Cin, L.Cout, L.transposed ? 1 : 0, L.wk_f, L.wk_b);
+        }
     }
     LEMO_CUDA(cudaGetLastError());
     if (n->tc) LEMO_TRY(enc_tc_refresh_weights(n, st));
@@ -397,6 +439,10 @@ void convnet_free(ConvNet* n) {
     cudaFree(n->w_flat); cudaFree(n->d_wflat); cudaFree(n->sk_scratch); cudaFree(n->wg_scratch); cudaFree(n->ft_sched);
     if (n->ft_gexec) cudaGraphExecDestroy((cudaGraphExec_t)n->ft_gexec);
     if (n->ft_graph) cudaGraphDestroy((cudaGraph_t)n->ft_graph);
+    cudaFree(n->wg_scratch2);
+    for (int i = 0; i < 2; ++i) if (n->bw_side[i]) cudaStreamDestroy((cudaStream_t)n->bw_side[i]);
+    if (n->bw_ready) cudaEventDestroy((cudaEvent_t)n->bw_ready);
+    for (int i = 0; i < 3; ++i) if (n->bw_done[i]) cudaEventDestroy((cudaEvent_t)n->bw_done[i]);
     if (n->ft_stream) { cudaStreamDestroy((cudaStream_t)n->ft_stream); cudaEventDestroy((cudaEvent_t)n->ft_ev_in); cudaEventDestroy((cudaEvent_t)n->ft_ev_out); }
     for (auto& L : n->layers) { cudaFree(L.wk_f); cudaFree(L.wk_b); }
     for (auto p : n->act) cudaFree(p);

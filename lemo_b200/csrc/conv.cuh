@@ -67,6 +67,12 @@ struct ConvNet {
     size_t sk_floats = 0;
     float* wg_scratch = nullptr;       // weight-gradient partials (fixed-order reduction instead of float atomics)
     size_t wg_floats = 0;
+    // AE backward: the weight gradients of a layer run on two side streams beside the input-gradient chain (fork/join with events; captured
+    // into the fine-tune graph as parallel branches); three rotating gradient buffers give every weight gradient two layers of slack
+    float* wg_scratch2 = nullptr;
+    void* bw_side[2] = {nullptr, nullptr};
+    void* bw_ready = nullptr;
+    void* bw_done[3] = {nullptr, nullptr, nullptr};
     // fine-tune driver (lemo_ae_finetune_run): device-side step schedule + one captured step
     void *ft_sched = nullptr, *ft_graph = nullptr, *ft_gexec = nullptr, *ft_stream = nullptr, *ft_ev_in = nullptr, *ft_ev_out = nullptr;
     const void *ft_x = nullptr, *ft_mask = nullptr;

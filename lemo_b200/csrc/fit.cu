@@ -474,10 +474,10 @@ static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
     MegaArgs a{};
     const Model* m = f->sub;
     a.vt = m->v_template; a.Wt = m->Wt; a.wjm = m->w_jm; a.Jt = m->J_template; a.Jd = m->J_dirs; a.hand_l = m->hand_l; a.hand_r = m->hand_r;
-    a.pose_mean = m->pose_mean; a.parents = m->parents; a.depth = m->depth; a.max_depth = m->max_depth; a.V = m->V; a.npc = m->npc;
+    a.pose_mean = m->pose_mean; a.tree = m->tree; a.max_depth = m->max_depth; a.V = m->V; a.npc = m->npc;
     VPoser* v = f->vp;
     a.W1 = v->W1; a.b1 = v->b1; a.W2 = v->W2; a.b2 = v->b2; a.W3 = v->W3; a.b3 = v->b3;
-    a.h1 = v->h1; a.h2 = v->h2; a.o = v->o; a.dh2 = v->dh2;
+    a.h2 = v->h2; a.o = v->o;
     a.dh1p = f->pf_ws; a.dXp = a.dh1p + (size_t)S * PM_CL * 512; a.dAp = a.dXp + (size_t)S * PM_CL * 512;
     a.P = f->P; a.Gp = f->Gp; a.betas = f->betas; a.mrec = f->mrec; a.p72 = f->p72; a.acc = f->acc;
     a.acc_n = ACC_N; a.acc_rec = ACC_REC; a.acc_vp = ACC_VP; a.acc_shape = ACC_SHAPE; a.acc_hand = ACC_HAND;
@@ -501,12 +501,21 @@ static int perframe_mega_run(Fit* f, int n_iters, cudaStream_t st) {
         unsigned long long h[32];
         LEMO_CUDA(cudaStreamSynchronize(st));
         LEMO_CUDA(cudaMemcpy(h, d_tl, sizeof(h), cudaMemcpyDeviceToHost));
-        const char* names[19] = {"P1 fc1", "sync1", "P2 load h1 + fc2", "sync2", "P3 out", "sync3", "P4 gs + pose/chain fwd", "P5 blend/skin/loss",
-                                 "P6 adjoint partials", "sync4", "P7 combine", "chain_bwd", "pose_to_rot_bwd + gs_bwd", "P8 dh2", "sync5", "P9 dh1 partial",
+        const char* names[19] = {"P1 fc1 (all rows)", "cta barrier", "P2 fc2", "sync2", "P3 out", "sync3", "P4 gs + pose/chain fwd", "P5 blend/skin/loss",
+                                 "P6 adjoint partials", "sync4", "P7 combine", "chain_bwd", "pose_to_rot_bwd + gs_bwd", "P8 dh2", "cta barrier", "P9 dh1 partial",
                                  "sync6", "P10 dh1/dz/priors", "adam"};
         printf("[perframe timeline] step 5 of frame 0, cluster 0 rank 0 (ns):");
         for (int i = 0; i < 18; ++i) printf(" %s %llu |", names[i], h[i + 1] - h[i]);
         printf(" total to adam %llu\n", h[18] - h[0]);
+#ifdef LEMO_BODY_TL
+        unsigned long long bt[32];
+        LEMO_CUDA(cudaMemcpyFromSymbol(bt, g_body_tl, sizeof(bt)));
+        const char* bn[17] = {"fwd: betas/rodrigues", "sync", "X + rest joints", "sync", "tree walk", "sync", "G/A/Jposed out", "(gap)", "bwd: load + dG init",
+                              "sync", "tree walk", "sync", "dR out", "(gap)", "p2r: rodrigues adjoint", "sync", "hand PCA"};
+        printf("[body timeline, last step] (ns):");
+        for (int i = 0; i < 17; ++i) if (i != 7 && i != 13) printf(" %s %lld |", bn[i], (long long)(bt[i + 1] - bt[i]));
+        printf("\n");
+#endif
     }
     f->launches += 1;
     return 0;

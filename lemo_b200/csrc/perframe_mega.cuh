@@ -15,7 +15,7 @@
 //     L1 marker loss and their adjoints; dA / dX / dtransl partials are combined like the MLP partials;
 //   * parameters and Adam moments (65 per frame) are replicated in every CTA's shared memory: all CTAs apply the identical update,
 //     nothing is broadcast; the learning-rate schedule (.1/.01 -> .01 @>60 -> .003 @>80) and bias corrections are computed in-kernel.
-// Six cluster barriers per step, no host involvement until the last frame is done.
+// Four cluster barriers per step, no host involvement until the last frame is done.
 #pragma once
 #include "body_dev.cuh"
 #include <cooperative_groups.h>
@@ -27,16 +27,16 @@ constexpr int PM_CL = 8;          // CTAs per cluster = per sequence
 constexpr int PM_NT = 256;        // threads per CTA
 constexpr int PM_VPC = 11;        // marker rows per CTA (8 x 11 >= 81)
 constexpr int PM_PART = 664;      // dA[660] + dtransl[3] + loss partial
-constexpr size_t PM_DYN_BYTES = 4 * (size_t)(NJ * 3 * NBETA + 165 + 2 * 540 + 168 + 112 + 168 + 496 + 512 + 660 + 660 + 168 + 168 + 660 + 512 + 496 + 12 + 192 + 12 + 192 + 128 + 16 + XK * 33 + NJ * PM_VPC + 16);
+constexpr size_t PM_DYN_BYTES = 4 * (size_t)(NJ * 3 * NBETA + 165 + 2 * 540 + 168 + TREE_N + 168 + 496 + 512 + 660 + 660 + 168 + 168 + 660 + 512 + 496 + 12 + 192 + 12 + 192 + 128 + 16 + XK * 33 + NJ * PM_VPC + 16 + 32 * 512 + 512);
 
 struct MegaArgs {
     // loss-row sub-model (V = 81 marker rows)
     const float *vt, *Wt, *wjm, *Jt, *Jd, *hand_l, *hand_r, *pose_mean;
-    const int *parents, *depth;
+    const int* tree;
     int max_depth, V, npc;
     // VPoser decoder, nn.Linear layout [out][in]
     const float *W1, *b1, *W2, *b2, *W3, *b3;
-    float *h1, *h2, *o, *dh2;                    // [S,512] [S,512] [S,126] [S,512]
+    float *h2, *o;                               // [S,512] [S,126]
     float *dh1p, *dXp, *dAp;                     // per-CTA partials: [S][8][512], [S][8][512], [S][8][PM_PART]
     // fit state
     float *P, *Gp;
@@ -75,7 +75,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
     __shared__ __align__(16) float s_h2[512];
     __shared__ float s_red[8][64];
     __shared__ float s_T[PM_VPC][12], s_dT[PM_VPC][12], s_vp[PM_VPC][3], s_gv[PM_VPC][3], s_dvp[3 * PM_VPC];
-    __shared__ float s_tgt[201], s_do[128], s_sc[8];
+    __shared__ float s_tgt[201], s_do[128], s_sc[8], s_vt[3 * PM_VPC], s_dh2[64];
 
     const int v0 = PM_VPC * rank, nv = max(0, min(PM_VPC, V - v0)), c0 = 3 * v0, ncol = 3 * nv;
     // dynamic shared memory: model constants (loaded once per launch) + the body scratch of "frame 0" of this CTA
@@ -85,9 +85,8 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
     float* c_hl = c_Jt + NJ * 3;             // [npc*45]
     float* c_hr = c_hl + 12 * 45;
     float* c_pm = c_hr + 12 * 45;            // [165]
-    int* c_par = reinterpret_cast<int*>(c_pm + 168);
-    int* c_dep = c_par + 56;
-    float* b_fp = reinterpret_cast<float*>(c_dep + 56);   // full_pose [165]
+    int* c_tree = reinterpret_cast<int*>(c_pm + 168);   // [TREE_N] level-ordered tree tables
+    float* b_fp = reinterpret_cast<float*>(c_tree + TREE_N);   // full_pose [165]
     float* b_R = b_fp + 168;                 // [55*9]
     float* b_X = b_R + 496;                  // [512]
     float* b_G = b_X + 512;                  // [660]
@@ -105,10 +104,15 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
     float* b_beta = b_o + 128;               // [10]
     float* c_Wt = b_beta + 16;               // [512][33]: this CTA's 33 blend-shape columns, resident for the whole launch (67.6 KB)
     float* c_wj = c_Wt + XK * 33;            // [55][11]: skinning weights of this CTA's marker rows
+    float* c_W1T = c_wj + NJ * PM_VPC + 16;  // [32][512]: first VPoser layer, transposed (fc1 and its adjoint are done by every CTA: no exchange)
+    float* c_b1 = c_W1T + 32 * 512;          // [512]
     for (int i = tid; i < NJ * 3 * NBETA; i += PM_NT) c_Jd[i] = a.Jd[i];
     for (int i = tid; i < NJ * 3; i += PM_NT) { c_Jt[i] = a.Jt[i]; c_pm[i] = a.pose_mean[i]; }
     for (int i = tid; i < a.npc * 45; i += PM_NT) { c_hl[i] = a.hand_l[i]; c_hr[i] = a.hand_r[i]; }
-    if (tid < NJ) { c_par[tid] = a.parents[tid]; c_dep[tid] = a.depth[tid]; }
+    for (int i = tid; i < TREE_N; i += PM_NT) c_tree[i] = a.tree[i];
+    for (int i = tid; i < 512 * 32; i += PM_NT) c_W1T[(i & 31) * 512 + (i >> 5)] = a.W1[i];
+    for (int i = tid; i < 512; i += PM_NT) c_b1[i] = a.b1[i];
+    if (tid < 3 * PM_VPC) s_vt[tid] = tid < ncol ? a.vt[c0 + tid] : 0.f;
     for (int i = tid; i < XK * 33; i += PM_NT) { const int k = i / 33, cc = i - k * 33; c_Wt[i] = cc < ncol ? a.Wt[(size_t)k * NC + c0 + cc] : 0.f; }
     for (int i = tid; i < NJ * PM_VPC; i += PM_NT) { const int j = i / PM_VPC, v = i - j * PM_VPC; c_wj[i] = v < nv ? a.wjm[(size_t)j * V + v0 + v] : 0.f; }
     __syncthreads();
@@ -140,23 +144,25 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                     s_sc[2] = (float)sqrt(1.0 - pow(0.999, tt));
                 }
                 PM_STAMP(0);
-                // ------------------------------------------------ P1: global 6D -> R ; fc1 rows [64 rank, +64)
+                // ------------------------------------------------ P1 (every CTA): global 6D -> R ; fc1, all 512 rows from shared memory
                 if (tid == 0) gs6d_fwd(s_p + 3, b_Rg);
                 {
-                    const int r = tid >> 2, q = tid & 3, n = 64 * rank + r;
-                    float acc = 0.f;
+                    float z[32];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(a.W1 + (size_t)n * 32 + q * 8 + k), s_p[9 + q * 8 + k], acc);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                    if (q == 0) a.h1[(size_t)s * 512 + n] = lrelu(acc + __ldg(a.b1 + n));
+                    for (int k = 0; k < 32; ++k) z[k] = s_p[9 + k];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int n = tid + rr * PM_NT;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) acc = fmaf(c_W1T[k * 512 + n], z[k], acc);
+                        s_h1[n] = lrelu(acc + c_b1[n]);
+                    }
                 }
                 PM_STAMP(1);
-                cluster.sync();
+                __syncthreads();
                 PM_STAMP(2);
                 // ------------------------------------------------ P2: fc2 rows [64 rank, +64), one warp per row
-                s_h1[tid] = a.h1[(size_t)s * 512 + tid]; s_h1[tid + 256] = a.h1[(size_t)s * 512 + tid + 256];
-                __syncthreads();
                 // every phase below is a stream of L2 reads with ~1 us of latency each: the loops are unrolled so that 16-32 independent
                 // loads are in flight per thread (the first version issued them 1-4 at a time and spent 47 us per step waiting)
 #pragma unroll
@@ -219,7 +225,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 __syncthreads();
                 if (tid < NBODY) gs6d_fwd(b_o + tid * 6, b_Rb + tid * 9);
                 __syncthreads();
-                pose_chain_fwd_body(pk, c_Jt, c_Jd, c_par, c_dep, a.max_depth, b_fp, b_R, b_X, nullptr, b_G, s_A, b_Jr, b_Jp, nullptr, 0);
+                pose_chain_fwd_body(pk, c_Jt, c_Jd, c_tree, a.max_depth, b_fp, b_R, b_X, nullptr, b_G, s_A, b_Jr, b_Jp, nullptr, 0, last);
                 __syncthreads();
                 if (last && rank == 0 && tid < 72) {                               // the [T,72] row the script saves: parameters of the LAST forward
                     float v;
@@ -231,13 +237,11 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 }
                 PM_STAMP(7);
                 // ------------------------------------------------ P5: blend + skinning + L1 loss on this CTA's marker rows
-                {
-                    const int grp = tid >> 6, cc = tid & 63;
+                if (tid < 7 * 33) {                                                 // 7 k-groups x 33 columns: consecutive threads, consecutive words
+                    const int grp = tid / 33, cc = tid - grp * 33;
                     float acc = 0.f;
-                    if (cc < ncol) {
 #pragma unroll 8
-                        for (int k = grp; k < XK; k += 4) acc = fmaf(b_X[k], c_Wt[k * 33 + cc], acc);
-                    }
+                    for (int k = grp; k < XK; k += 7) acc = fmaf(b_X[k], c_Wt[k * 33 + cc], acc);
                     s_red[grp][cc] = acc;
                 }
                 if (tid < nv * 12) {
@@ -248,7 +252,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                     s_T[i][k] = acc;
                 }
                 __syncthreads();
-                if (tid < ncol) s_vp[tid / 3][tid % 3] = __ldg(a.vt + c0 + tid) + ((s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]));
+                if (tid < ncol) s_vp[tid / 3][tid % 3] = s_vt[tid] + (((s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid])) + ((s_red[4][tid] + s_red[5][tid]) + s_red[6][tid]));
                 __syncthreads();
                 float lpart = 0.f;
                 if (tid < ncol) {
@@ -269,13 +273,13 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 __syncthreads();
                 PM_STAMP(8);
                 // ------------------------------------------------ P6: adjoint on this CTA's rows -> partials of dA, dtransl, dX
-                if (tid < ncol) {
+                if (tid < 3 * PM_VPC) {                                             // (rows past nv: zeros, so the loops below need no predicate)
                     const int i = tid / 3, c = tid - i * 3;
-                    s_dvp[tid] = s_T[i][c] * s_gv[i][0] + s_T[i][4 + c] * s_gv[i][1] + s_T[i][8 + c] * s_gv[i][2];
+                    s_dvp[tid] = tid < ncol ? s_T[i][c] * s_gv[i][0] + s_T[i][4 + c] * s_gv[i][1] + s_T[i][8 + c] * s_gv[i][2] : 0.f;
                 }
-                if (tid < nv * 12) {
+                if (tid < PM_VPC * 12) {
                     const int i = tid / 12, k = tid - i * 12, row = k >> 2, col = k & 3;
-                    s_dT[i][k] = s_gv[i][row] * (col < 3 ? s_vp[i][col] : 1.f);
+                    s_dT[i][k] = i < nv ? s_gv[i][row] * (col < 3 ? s_vp[i][col] : 1.f) : 0.f;
                 }
                 __syncthreads();
                 {
@@ -284,8 +288,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                         const int j = e / 12, k = e - j * 12;
                         float acc = 0.f;
 #pragma unroll
-                        for (int i = 0; i < PM_VPC; ++i)
-                            if (i < nv) acc = fmaf(c_wj[j * PM_VPC + i], s_dT[i][k], acc);
+                        for (int i = 0; i < PM_VPC; ++i) acc = fmaf(c_wj[j * PM_VPC + i], s_dT[i][k], acc);
                         pz[e] = acc;
                     }
                     if (tid < 3) {
@@ -295,12 +298,16 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                     }
                     if (tid == 3) pz[NJ * 12 + 3] = s_sc[4] + s_sc[5];
                     float* px = a.dXp + ((size_t)s * PM_CL + rank) * XK;
-                    for (int k = tid; k < XK; k += PM_NT) {
+                    float dv[3 * PM_VPC];
+#pragma unroll
+                    for (int cc = 0; cc < 3 * PM_VPC; ++cc) dv[cc] = s_dvp[cc];
+#pragma unroll
+                    for (int kk = 0; kk < XK / PM_NT; ++kk) {
+                        const int k = tid + kk * PM_NT;
                         const float* w = c_Wt + k * 33;
                         float acc = 0.f;
 #pragma unroll
-                        for (int cc = 0; cc < 3 * PM_VPC; ++cc)
-                            if (cc < ncol) acc = fmaf(w[cc], s_dvp[cc], acc);
+                        for (int cc = 0; cc < 3 * PM_VPC; ++cc) acc = fmaf(w[cc], dv[cc], acc);
                         px[k] = acc;
                     }
                 }
@@ -308,27 +315,41 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 cluster.sync();
                 PM_STAMP(10);
                 // ------------------------------------------------ P7 (every CTA): combine partials in rank order, chain adjoint
-                for (int e = tid; e < PM_PART; e += PM_NT) {
+                // (all partial loads of a thread are independent: issued together, one L2 latency for the lot)
+#pragma unroll
+                for (int ee = 0; ee < (PM_PART + PM_NT - 1) / PM_NT; ++ee) {
+                    const int e = tid + ee * PM_NT;
+                    if (e >= PM_PART) break;
+                    float pv[PM_CL];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) pv[r] = __ldcg(a.dAp + ((size_t)s * PM_CL + r) * PM_PART + e);
                     float acc = 0.f;
-                    for (int r = 0; r < PM_CL; ++r) acc += a.dAp[((size_t)s * PM_CL + r) * PM_PART + e];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) acc += pv[r];
                     if (e < NJ * 12) b_dA[e] = acc;                                  // joint-major [55][B*12] with B = 1
                     else if (e < NJ * 12 + 3) s_g[e - NJ * 12] = acc;               // d loss / d transl
                     else s_sc[3] = acc;                                             // marker loss value
                 }
-                for (int k = tid; k < XK; k += PM_NT) {
+#pragma unroll
+                for (int kk = 0; kk < XK / PM_NT; ++kk) {
+                    const int k = tid + kk * PM_NT;
+                    float pv[PM_CL];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) pv[r] = __ldcg(a.dXp + ((size_t)s * PM_CL + r) * XK + k);
                     float acc = 0.f;
-                    for (int r = 0; r < PM_CL; ++r) acc += a.dXp[((size_t)s * PM_CL + r) * XK + k];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) acc += pv[r];
                     b_dX[k] = acc;
                 }
                 __syncthreads();
                 PM_STAMP(11);
-                chain_bwd_body(b_R, b_G, b_Jr, b_dA, nullptr, b_dX, c_Jd, c_par, c_dep, a.max_depth, 1, 10, b_dR, nullptr, nullptr, 0);
+                chain_bwd_body<false, false>(b_R, b_G, b_Jr, b_dA, nullptr, b_dX, c_Jd, c_tree, a.max_depth, 1, 10, b_dR, nullptr, nullptr, 0);
                 __syncthreads();
                 PM_STAMP(12);
+                // Gram-Schmidt adjoints on warps 2-3, straight from dR, while warps 0-1 run the axis-angle adjoint of the hands
+                if (tid == 64) gs6d_bwd(s_p + 3, b_dR, s_g + 3);
+                if (tid >= 96 && tid < 96 + NBODY) gs6d_bwd(b_o + (tid - 96) * 6, b_dR + (1 + tid - 96) * 9, s_do + (tid - 96) * 6);
                 pose_to_rot_bwd_body(pk, pg, 1, b_fp, b_dR, 0);
-                __syncthreads();
-                if (tid == 0) gs6d_bwd(s_p + 3, b_dRg, s_g + 3);
-                if (tid < NBODY) gs6d_bwd(b_o + tid * 6, b_dRb + tid * 9, s_do + tid * 6);
                 __syncthreads();                                                    // (the hand PCA gradients were written straight into s_g)
                 PM_STAMP(13);
                 // ------------------------------------------------ P8: dh2 columns [64 rank, +64) = (W3^T d_o) * lrelu'(h2)
@@ -346,20 +367,18 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 if (tid < 64) {
                     const int n = 64 * rank + tid;
                     const float v = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
-                    a.dh2[(size_t)s * 512 + n] = v * (s_h2[n] > 0.f ? 1.f : 0.2f);
+                    s_dh2[tid] = v * (s_h2[n] > 0.f ? 1.f : 0.2f);
                 }
                 PM_STAMP(14);
-                cluster.sync();
+                __syncthreads();                                                    // (no cluster barrier: P9 needs only THIS CTA's 64 columns of dh2)
                 PM_STAMP(15);
                 // ------------------------------------------------ P9: partial of dh1 = W2^T dh2 over this CTA's rows of W2
-                s_vec[tid] = a.dh2[(size_t)s * 512 + tid]; s_vec[tid + 256] = a.dh2[(size_t)s * 512 + tid + 256];
-                __syncthreads();
                 {
                     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 16
                     for (int r = 0; r < 64; ++r) {
                         const int n = 64 * rank + r;
-                        const float d = s_vec[n];
+                        const float d = s_dh2[r];
                         acc0 = fmaf(__ldg(a.W2 + (size_t)n * 512 + tid), d, acc0);
                         acc1 = fmaf(__ldg(a.W2 + (size_t)n * 512 + tid + 256), d, acc1);
                     }
@@ -371,25 +390,28 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 PM_STAMP(17);
                 // ------------------------------------------------ P10 (every CTA): dh1, dz = W1^T dh1, priors, Adam
                 __syncthreads();
-                for (int c = tid; c < 512; c += PM_NT) {
+#pragma unroll
+                for (int kk = 0; kk < 512 / PM_NT; ++kk) {
+                    const int c = tid + kk * PM_NT;
+                    float pv[PM_CL];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) pv[r] = __ldcg(a.dh1p + ((size_t)s * PM_CL + r) * 512 + c);
                     float acc = 0.f;
-                    for (int r = 0; r < PM_CL; ++r) acc += a.dh1p[((size_t)s * PM_CL + r) * 512 + c];
+#pragma unroll
+                    for (int r = 0; r < PM_CL; ++r) acc += pv[r];
                     s_vec[c] = acc * (s_h1[c] > 0.f ? 1.f : 0.2f);
                 }
                 __syncthreads();
-                {
-                    const int c = tid & 31, kg = tid >> 5;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                                       // dz[c] = W1^T dh1: one warp per latent, lanes over the 512 rows
+                    const int c = warp + 8 * q;
                     float acc = 0.f;
-#pragma unroll 16
-                    for (int k = kg; k < 512; k += 8) acc = fmaf(__ldg(a.W1 + (size_t)k * 32 + c), s_vec[k], acc);
-                    s_red[kg][c] = acc;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc = fmaf(c_W1T[c * 512 + lane + 32 * i], s_vec[lane + 32 * i], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) s_g[9 + c] = acc + a.w_vp * 2.f * s_p[9 + c] * (1.f / 32.f);       // + d/dz of w_vposer * mean(z^2)  (:343-346)
                 }
-                __syncthreads();
-                if (tid < 32) {
-                    float acc = 0.f;
-                    for (int kg = 0; kg < 8; ++kg) acc += s_red[kg][tid];
-                    s_g[9 + tid] = acc + a.w_vp * 2.f * s_p[9 + tid] * (1.f / 32.f);      // + d/dz of w_vposer * mean(z^2)  (:343-346)
-                } else if (tid < 32 + 24) {
+                if (tid >= 32 && tid < 32 + 24) {
                     const int c = tid - 32;
                     s_g[41 + c] += a.w_hand * 2.f * s_p[41 + c] * (1.f / 24.f);           // + d of w_hand * mean(hand^2)
                 }
@@ -402,6 +424,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                     float* ac = a.acc + (size_t)s * a.acc_n;
                     ac[a.acc_rec] = s_sc[3]; ac[a.acc_vp] = pv / 32.f; ac[a.acc_hand] = ph / 24.f; ac[a.acc_shape] = ps / 10.f;
                 }
+                if (last) __syncthreads();                                          // the reported terms read s_p before Adam moves it (racecheck)
                 PM_STAMP(18);
                 if (tid < 65) {                                                     // torch.optim.Adam.step, identical in every CTA
                     const float gi = s_g[tid];

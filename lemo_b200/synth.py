@@ -27,7 +27,7 @@ ASSETS = os.path.join(_HERE, 'assets')
 
 def make_smplx_model(seed=0, n_verts=V, weights_nnz=0):
     """Random SMPL-X-shaped model.  seed 0 = 'neutral/male', seed 1 = 'female'.
-    weights_nnz>0 keeps only that many skinning weights per vertex (realistic sparsity variant)."""
+    weights_nnz>0 keeps at most that many skinning weights per vertex, on tree-adjacent joints (realistic sparsity variant)."""
     g = np.random.default_rng(seed)
     f32 = np.float32
     m = {}
@@ -39,8 +39,15 @@ def make_smplx_model(seed=0, n_verts=V, weights_nnz=0):
     m['J_regressor'] = (jr / jr.sum(1, keepdims=True)).astype(f32)
     w = g.random((n_verts, J))
     if weights_nnz:
-        kth = np.partition(w, J - weights_nnz, axis=1)[:, J - weights_nnz][:, None]
-        w = np.where(w >= kth, w, 0.0)
+        # like the real model: every vertex is bound to a few joints that are neighbours in the kinematic tree, and the vertex numbering
+        # is spatially coherent (consecutive vertices belong to the same body part): home joint by vertex index, then its ancestors
+        home = np.minimum((np.arange(n_verts) * J) // max(n_verts, 1), J - 1)
+        keep = np.zeros((n_verts, J), bool)
+        cur = home.copy()
+        for _ in range(weights_nnz):
+            keep[np.arange(n_verts), cur] = True
+            cur = np.where(PARENTS[cur] >= 0, PARENTS[cur], cur)
+        w = np.where(keep, w, 0.0)
     m['lbs_weights'] = (w / w.sum(1, keepdims=True)).astype(f32)
     m['parents'] = PARENTS.copy()
     m['hands_componentsl'] = (0.1 * g.standard_normal((45, 45))).astype(f32)

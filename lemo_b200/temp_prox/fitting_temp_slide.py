@@ -313,7 +313,11 @@ class SMPLifyLoss(nn.Module):
 
     def _scan_terms(self, out, body_model_faces, scan_tensor, scan_point_num, vis):
         """s2m / m2s (:638-670): per frame, Chamfer between the valid scan points and the camera-visible vertices (m2s: visible AND
-        body_mask), GMoF-robustified, averaged over frames.  `vis` [B,V] (0/1) replaces psbody's visibility_compute when given."""
+        body_mask), GMoF-robustified, averaged over frames.  `vis` [B,V] (0/1) replaces psbody's visibility_compute when given.
+        Reference behaviour kept: the reference passes `vertices[:, visible_i, :]` ([bs, n_vis, 3]) beside a [1, N, 3] scan slice, and
+        its Chamfer wrapper takes the batch size from the FIRST argument (dist_chamfer.py:13) -- so for every frame i the scan of frame i
+        is matched against the vertices of frame 0 selected by frame i's visibility.  At bs = 1 (the single-frame PROX fit the term was
+        written for) this is the expected pairing; both shipped temporal configurations switch the terms off."""
         dev = out.vertices.device
         bs = out.vertices.shape[0]
         if vis is None:
@@ -332,10 +336,10 @@ class SMPLifyLoss(nn.Module):
         for i in range(bs):
             cur = scan_tensor[i:i + 1][:, 0:int(scan_point_num[i])].contiguous()
             if self.s2m and self.s2m_weight > 0 and bool(vis[i].any()):
-                d, _, _, _ = distChamfer(cur, out.vertices[i:i + 1][:, vis[i], :].contiguous())
+                d, _, _, _ = distChamfer(cur, out.vertices[0:1][:, vis[i], :].contiguous())
                 s2m_list.append(self.s2m_robustifier(torch.sqrt(d + 1e-30)).mean())
             if self.m2s and self.m2s_weight > 0 and bool(vis[i].any()):
-                _, d, _, _ = distChamfer(cur, out.vertices[i:i + 1][:, vis[i] & body_mask, :].contiguous())
+                _, d, _, _ = distChamfer(cur, out.vertices[0:1][:, vis[i] & body_mask, :].contiguous())
                 m2s_list.append(self.m2s_robustifier(torch.sqrt(d + 1e-30)).mean())
         zero = torch.zeros((), device=dev)
         s2m = sum(s2m_list) / len(s2m_list) * self.s2m_weight if s2m_list else zero

@@ -117,3 +117,24 @@ def fit_window(P_np, ctx, cfg, n_iters, lr=0.005, first_batch_flag=False, trace=
             return tot
         last = float(opt.step(closure))
     return {k: v.detach().numpy() for k, v in P.items()}, last
+
+
+def scan_terms(vertices, scan, scan_num, vis, body_mask, rho_s2m, rho_m2s, w_s2m, w_m2s, s2m=True, m2s=True):
+    """TEST ORACLE for the scan-to-mesh / mesh-to-scan terms (reference temp_prox/fitting_temp_slide.py:638-670), brute-force distances.
+    vertices [bs,V,3] (may require grad), scan [bs,N,3], scan_num [bs], vis [bs,V] bool, body_mask [V] bool.  Follows the reference's
+    batch behaviour: its Chamfer wrapper sizes the batch from the scan slice (dist_chamfer.py:13, batch 1), so the visible vertices are
+    always read from frame 0 of `vertices[:, visible_i, :]`."""
+    gm = lambda r, rho: rho ** 2 * r ** 2 / (r ** 2 + rho ** 2)
+    l1, l2 = [], []
+    for i in range(vertices.shape[0]):
+        cur = scan[i, :int(scan_num[i])]
+        if not bool(vis[i].any()):
+            continue
+        if s2m and w_s2m > 0:
+            d = ((cur[:, None, :] - vertices[0][vis[i]][None]) ** 2).sum(-1).min(dim=1)[0]
+            l1.append(gm(torch.sqrt(d), rho_s2m).mean())
+        if m2s and w_m2s > 0:
+            d = ((vertices[0][vis[i] & body_mask][:, None, :] - cur[None]) ** 2).sum(-1).min(dim=1)[0]
+            l2.append(gm(torch.sqrt(d), rho_m2s).mean())
+    z = torch.zeros((), dtype=vertices.dtype)
+    return (sum(l1) / len(l1) * w_s2m if l1 else z), (sum(l2) / len(l2) * w_m2s if l2 else z)

@@ -206,3 +206,45 @@ def test_unsupported_terms_fall_back_to_the_eager_closure():
     s['monitor'].run_fitting(lbfgs_like, s['closure'], s['final_params'], s['body_model'], pose_embedding=s['pose_embedding'],
                              vposer=s['vposer'], use_vposer=True)
     assert s['monitor'].last_path.startswith('eager'), s['monitor'].last_path
+
+
+def test_scan_terms_match_oracle():
+    """s2m / m2s (reference fitting_temp_slide.py:638-670) on the lemo Chamfer kernels vs the brute-force oracle: values
+    and the gradient on the vertices.  bs = 3 exercises the reference's batch behaviour (frame-0 vertices, see ref_prox.scan_terms)."""
+    import types
+    from lemo_b200.temp_prox import fitting_temp_slide as fitting
+    g = torch.Generator().manual_seed(11)
+    bs, V, N = 3, 700, 400
+    verts = torch.randn(bs, V, 3, generator=g) * 0.4
+    scan = verts[:, torch.randperm(V, generator=g)[:N]] + 0.05 * torch.randn(bs, N, 3, generator=g)
+    scan_num = torch.tensor([400, 333, 250])
+    vis = torch.rand(bs, V, generator=g) > 0.4
+    body_mask = torch.rand(V, generator=g) > 0.2
+    loss = fitting.create_loss(loss_type='smplify', s2m=True, m2s=True, rho_s2m=0.2, rho_m2s=0.5, s2m_weight=1.7, m2s_weight=0.6,
+                               body_mask=body_mask.numpy(), interpenetration=False, sdf_penetration=False, contact=False,
+                               use_motion_smooth_prior=False, use_friction=False, use_motion_infill_prior=False, device=DEV).to(DEV)
+    v_dev = verts.to(DEV).requires_grad_(True)
+    s2m, m2s = loss._scan_terms(types.SimpleNamespace(vertices=v_dev), None, scan.to(DEV), scan_num, vis.to(DEV))
+    (s2m + m2s).backward()
+    v_ref = verts.double().requires_grad_(True)
+    r1, r2 = ref_prox.scan_terms(v_ref, scan.double(), scan_num, vis, body_mask, 0.2, 0.5, 1.7, 0.6)
+    (r1 + r2).backward()
+    assert abs(float(s2m) - float(r1)) < 1e-5 * max(1.0, abs(float(r1))), (float(s2m), float(r1))
+    assert abs(float(m2s) - float(r2)) < 1e-5 * max(1.0, abs(float(r2))), (float(m2s), float(r2))
+    assert rel(v_dev.grad.cpu().double(), v_ref.grad) < 1e-4
+    assert float(v_dev.grad[1:].abs().max()) == 0.0          # the reference's pairing: only frame 0 receives gradient
+
+
+def test_lbfgs_line_search_drives_the_eager_closure():
+    """optim_type 'lbfgsls' (reference optimizers/optim_factory.py:50): the closure protocol -- zero_grad, forward, backward, return the
+    loss -- under an optimizer that re-evaluates it several times per step; the loss must go down and the fused driver must stay out."""
+    from lemo_b200.temp_prox.optimizers import create_optimizer
+    B = 12
+    P, cfg = synth.make_prox_problem(B, D=16, m_scene=500, seed=9)
+    s = _reference_call_surface(B, P, cfg, maxiters=3, first_batch_flag=True)
+    opt, _ = create_optimizer(s['final_params'], optim_type='lbfgsls', lr=1.0, maxiters=4)
+    l0 = float(s['closure'](backward=False))
+    final = s['monitor'].run_fitting(opt, s['closure'], s['final_params'], s['body_model'], pose_embedding=s['pose_embedding'],
+                                     vposer=s['vposer'], use_vposer=True)
+    assert s['monitor'].last_path.startswith('eager'), s['monitor'].last_path
+    assert np.isfinite(final) and final < l0, (final, l0)

@@ -165,3 +165,20 @@ def test_smplify_loss_reference_signature():
         create_loss(loss_type='camera_init')
 
 
+
+
+def test_create_optimizer_kinds():
+    """optimizers/optim_factory.py:26-65: (optimizer, False) for every type the reference accepts, ValueError otherwise."""
+    import torch
+    from lemo_b200.temp_prox.optimizers import create_optimizer
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    kinds = {'adam': torch.optim.Adam, 'lbfgs': torch.optim.LBFGS, 'lbfgsls': torch.optim.LBFGS, 'rmsprop': torch.optim.RMSprop,
+             'sgd': torch.optim.SGD}
+    for k, cls in kinds.items():
+        opt, flag = create_optimizer(p, optim_type=k, lr=0.005, maxiters=30)
+        assert isinstance(opt, cls) and flag is False
+    assert create_optimizer(p, optim_type='lbfgsls', lr=1.0, maxiters=30)[0].param_groups[0]['line_search_fn'] == 'strong_wolfe'
+    a = create_optimizer(p, optim_type='adam', lr=0.005, beta1=0.9, beta2=0.999)[0].param_groups[0]
+    assert a['lr'] == 0.005 and tuple(a['betas']) == (0.9, 0.999)
+    with pytest.raises(ValueError):
+        create_optimizer(p, optim_type='adagrad')
