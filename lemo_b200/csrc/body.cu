@@ -77,6 +77,8 @@ void skin_tc_set(int on) { g_skin_tc = on ? 1 : 0; }
 // force the dense kernel (parity tests compare the two)
 static int g_skin_sparse = []() { const char* e = getenv("LEMO_SKIN_ADJ"); return (e && strcmp(e, "dense") == 0) ? 0 : 1; }();
 void skin_sparse_set(int on) { g_skin_sparse = on ? 1 : 0; }
+// LEMO_DX=gemm routes the full-mesh dX product through the generic SGEMM instead of k_dx_tallk (A/B measurements)
+static int g_dx_tallk = []() { const char* e = getenv("LEMO_DX"); return (e && strcmp(e, "gemm") == 0) ? 0 : 1; }();
 
 // K-major transposed copy of Wt + its TMA descriptor for the tensor-core blend GEMM
 static int model_setup_tc(Model* m) {
@@ -632,6 +634,69 @@ __global__ void k_skin_bwd_reduce(const float* __restrict__ part, int nparts, in
     else dtr[b * 3 + (t - NJ * 12)] += a;
 }
 // C[M,N] += sum over slices of the partial products parked by a splitk == 2 GEMM, in slice order
+// dX partials of the full mesh: part[z][M][512] = DVP[M][Kz] . Wt[512][Kz]^T for K slice z (M = frames <= 128, K = 3V = 31425).
+// Both operands are K-fast in memory (a dot-product GEMM), M is small and K huge, so the tile is the whole M x 128 columns and the grid is
+// (4 column blocks, K slices).  8 x 8 outputs per thread, as two 4-wide halves 64 apart so that the shared-memory fragments are read
+// with conflict-free 128-bit loads: 4 LDS.128 per 64 FMAs (the generic 4 x 4 kernel needs 2 per 16 and is bound by shared-memory
+// bandwidth: 161 us for this product at B = 100).  Global loads are register-prefetched one K block ahead.
+constexpr int DXK = 16, DXP = 132;
+__global__ void __launch_bounds__(256) k_dx_tallk(const float* __restrict__ A, const float* __restrict__ Bm, int M, int K, int kslice,
+                                                  float* __restrict__ part) {
+    __shared__ __align__(16) float As[DXK][DXP];
+    __shared__ __align__(16) float Bs[DXK][DXP];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * 128, z = blockIdx.y;
+    const int k_begin = z * kslice, k_end = min(K, k_begin + kslice);
+    const int lk = tid & 15, lr = tid >> 4;            // loader role: column lk of the K block, rows lr + 16 i
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float ra[8], rb[8];
+    auto load = [&](int k0) {
+        const int gk = k0 + lk;
+        const bool kin = gk < k_end;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = lr + 16 * i;
+            ra[i] = (kin && r < M) ? A[(size_t)r * K + gk] : 0.f;
+            rb[i] = kin ? __ldg(Bm + (size_t)(n0 + r) * K + gk) : 0.f;
+        }
+    };
+    load(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += DXK) {
+        __syncthreads();                                // previous block consumed
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { As[lk][lr + 16 * i] = ra[i]; Bs[lk][lr + 16 * i] = rb[i]; }
+        __syncthreads();
+        if (k0 + DXK < k_end) load(k0 + DXK);
+#pragma unroll
+        for (int k = 0; k < DXK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float* out = part + (size_t)z * M * XK;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = (i < 4 ? 0 : 64) + ty * 4 + (i & 3);
+        if (m >= M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh)
+            *reinterpret_cast<float4*>(out + (size_t)m * XK + n0 + jh * 64 + tx * 4) =
+                make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+    }
+}
+
 __global__ void k_slices_reduce(const float* __restrict__ part, int nz, long long mn, float* __restrict__ C) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= mn) return;
@@ -818,7 +883,10 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
         if (g.nz > 1 && c->part && (size_t)g.nz * B * XK <= c->part_floats) {
             // full mesh: every K slice parks its partial product, the slices are added in order (no float atomics)
             g.splitk = 2; g.C = c->part;
-            LEMO_TRY(gemm_launch(g, st));
+            if (B <= 128 && g_dx_tallk) {
+                const int kslice = cdiv(cdiv(3 * V, g.nz), DXK) * DXK;
+                k_dx_tallk<<<dim3(XK / 128, g.nz), 256, 0, st>>>(c->DVP, m->Wt, B, 3 * V, kslice, c->part);
+            } else LEMO_TRY(gemm_launch(g, st));
             k_slices_reduce<<<cdiv((long long)B * XK, 256), 256, 0, st>>>(c->part, g.nz, (long long)B * XK, ps->dX);
             LEMO_CUDA(cudaGetLastError());
         } else LEMO_TRY(gemm_launch(g, st));

@@ -192,42 +192,29 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
     body_sync<SUB64>();
     BODY_STAMP(4);
     // the chain (lbs.py:196-263): warp 0 walks the tree level by level, lane i = i-th joint of the level (one packed table word per level
-    // and lane); only __syncwarp between levels.  Everything a level needs except its parents' transforms -- the table word, the joint's
-    // rotation and its offset from the parent -- is fetched one level ahead, so a level costs one shared-memory round trip plus the 3x4 product.
+    // and lane, the next level's word requested a level ahead); only __syncwarp between levels.  (Fetching the next level's rotation and
+    // offset ahead of the barrier as well was measured: slower -- the loads must complete before the barrier, so a level then pays two
+    // shared-memory latencies instead of one.)
     if (threadIdx.x < 32) {
-        float r[9], t[3];
-        auto fetch = [&](int w) {
-            if (w >= 0) {
-                const int jj = w & 255, par = ((w >> 8) & 255) - 1;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) r[k] = sR[jj][k];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) t[k] = par < 0 ? sJ[jj][k] : sJ[jj][k] - sJ[par][k];
-            }
-        };
-        fetch(e);
         for (int lev = 0; lev <= max_depth; ++lev) {
             const int e_next = lev < max_depth ? tree[TREE_LANE + (lev + 1) * 32 + threadIdx.x] : -1;
             if (e >= 0) {
                 const int jj = e & 255, par = ((e >> 8) & 255) - 1;
+                const float* r = sR[jj];
                 float g[12];
                 if (par < 0) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) { g[q * 4] = r[q * 3]; g[q * 4 + 1] = r[q * 3 + 1]; g[q * 4 + 2] = r[q * 3 + 2]; g[q * 4 + 3] = t[q]; }
+                    for (int q = 0; q < 3; ++q) { g[q * 4] = r[q * 3]; g[q * 4 + 1] = r[q * 3 + 1]; g[q * 4 + 2] = r[q * 3 + 2]; g[q * 4 + 3] = sJ[jj][q]; }
                 } else {
                     const float* gp = sG[par];
-#pragma unroll
+                    const float t[3] = {sJ[jj][0] - sJ[par][0], sJ[jj][1] - sJ[par][1], sJ[jj][2] - sJ[par][2]};
                     for (int q = 0; q < 3; ++q) {
-#pragma unroll
                         for (int c = 0; c < 3; ++c)
                             g[q * 4 + c] = gp[q * 4] * r[c] + gp[q * 4 + 1] * r[3 + c] + gp[q * 4 + 2] * r[6 + c];
                         g[q * 4 + 3] = gp[q * 4] * t[0] + gp[q * 4 + 1] * t[1] + gp[q * 4 + 2] * t[2] + gp[q * 4 + 3];
                     }
                 }
-#pragma unroll
                 for (int k = 0; k < 12; ++k) sG[jj][k] = g[k];
             }
-            fetch(e_next);
             __syncwarp();
             e = e_next;
         }
@@ -297,70 +284,48 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
     BODY_STAMP(9);
     body_sync<SUB64>();
     BODY_STAMP(10);
-    // children -> parent accumulation, deepest level first, by warp 0 alone (lane i = i-th joint of the level, one __syncwarp per level).
-    // When a joint's turn comes it first adds what its children left for it, in ascending child index: FIXED order, no shared-memory
-    // atomics -- results are bitwise reproducible, which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same
-    // parameters).  The static operands of a level (parent rotation, own rotation, offset, child list) are fetched one level ahead.
+    // children -> parent accumulation, deepest level first, by warp 0 alone (lane i = i-th joint of the level).  When a joint's turn comes
+    // it first adds what its children left for it, in ascending child index: FIXED order, no shared-memory atomics -- results are bitwise
+    // reproducible, which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same parameters).  One __syncwarp
+    // per level.
     if (threadIdx.x < 32) {
-        float gpR[9], rr[9], t[3];
-        int kid[6];
-        auto fetch = [&](int w) {
-            if (w >= 0) {
-                const int jj = w & 255, par = ((w >> 8) & 255) - 1, k0 = (w >> 16) & 255, nk = (w >> 24) & 255;
-                if (par >= 0) {
-                    const float* gp = sG[par];
-                    gpR[0] = gp[0]; gpR[1] = gp[1]; gpR[2] = gp[2]; gpR[3] = gp[4]; gpR[4] = gp[5]; gpR[5] = gp[6]; gpR[6] = gp[8]; gpR[7] = gp[9]; gpR[8] = gp[10];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) rr[k] = sR[jj][k];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) t[k] = sJr[jj][k] - sJr[par][k];
-                }
-#pragma unroll
-                for (int q = 0; q < 6; ++q) kid[q] = q < nk ? tree[TREE_KLIST + k0 + q] : 0;
-            }
-        };
-        fetch(e);
         for (int lev = max_depth; lev >= 0; --lev) {
             const int e_next = lev > 0 ? tree[TREE_LANE + (lev - 1) * 32 + threadIdx.x] : -1;
             if (e >= 0) {
                 const int jj = e & 255, par = ((e >> 8) & 255) - 1, k0 = (e >> 16) & 255, nk = (e >> 24) & 255;
                 float dG[12];
-#pragma unroll
                 for (int k = 0; k < 12; ++k) dG[k] = sdG[jj][k];
                 for (int q = 0; q < nk; ++q) {
-                    const int c = q < 6 ? kid[q] : tree[TREE_KLIST + k0 + q];
-#pragma unroll
+                    const int c = tree[TREE_KLIST + k0 + q];
                     for (int k = 0; k < 12; ++k) dG[k] += sC[c][k];
                 }
                 if (par >= 0) {
+                    const float* gp = sG[par];                            // parent's global transform
+                    const float gpR[9] = {gp[0], gp[1], gp[2], gp[4], gp[5], gp[6], gp[8], gp[9], gp[10]};
                     const float dGr[9] = {dG[0], dG[1], dG[2], dG[4], dG[5], dG[6], dG[8], dG[9], dG[10]};
                     const float dGt[3] = {dG[3], dG[7], dG[11]};
+                    float rr[9];
+                    for (int k = 0; k < 9; ++k) rr[k] = sR[jj][k];
+                    const float t[3] = {sJr[jj][0] - sJr[par][0], sJr[jj][1] - sJr[par][1], sJr[jj][2] - sJr[par][2]};
                     float dr[9], dpr[9], dt[3];
                     m3_mul_at(gpR, dGr, dr);               // dR_j = Gp.R^T dG_j.R
                     m3_mul_bt(dGr, rr, dpr);               // dGp.R += dG_j.R R_j^T
-#pragma unroll
                     for (int k = 0; k < 9; ++k) sdR[jj][k] = dr[k];
-#pragma unroll
                     for (int q = 0; q < 3; ++q) {
-#pragma unroll
                         for (int c = 0; c < 3; ++c) sC[jj][q * 4 + c] = dpr[q * 3 + c] + dGt[q] * t[c];
                         sC[jj][q * 4 + 3] = dGt[q];
                     }
                     if (NEED_J) {
                         m3t_vec(gpR, dGt, dt);             // dt = Gp.R^T dG_j.t
-#pragma unroll
                         for (int q = 0; q < 3; ++q) { sC[jj][12 + q] = -dt[q]; sdJ[jj][q] += dt[q]; }
                     }
                 } else {                                   // root: its rotation gradient is dG.R itself; the translation feeds its rest joint
-#pragma unroll
                     for (int q = 0; q < 3; ++q) {
-#pragma unroll
                         for (int c = 0; c < 3; ++c) sdR[jj][q * 3 + c] = dG[q * 4 + c];
                         if (NEED_J) sdJ[jj][q] += dG[q * 4 + 3];
                     }
                 }
             }
-            fetch(e_next);
             __syncwarp();
             e = e_next;
         }
