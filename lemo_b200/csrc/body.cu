@@ -31,7 +31,7 @@ static inline int skin_bwd_tiles(int V, int B) {
     return ntile <= 2 ? ntile : std::max(1, std::min(ntile, (int)((long long)ntile * B / 2368)));
 }
 static inline int skin_bwd_ctas(int V, int B) { return cdiv(cdiv(V, SKB_TV), skin_bwd_tiles(V, B)); }
-static inline int dx_slices(int V) { return std::max(1, std::min(64, (3 * V) / 832)); }     // full mesh: 37 K-slices x 32 tiles = 1184 CTAs
+static inline int dx_slices(int V) { return std::max(1, std::min(80, (3 * V) / 416)); }     // full mesh: 75 K-slices x 4 column blocks = 300 CTAs, two per SM
 
 
 // =============================================================================================
@@ -639,44 +639,57 @@ __global__ void k_skin_bwd_reduce(const float* __restrict__ part, int nparts, in
 // (4 column blocks, K slices).  8 x 8 outputs per thread, as two 4-wide halves 64 apart so that the shared-memory fragments are read
 // with conflict-free 128-bit loads: 4 LDS.128 per 64 FMAs (the generic 4 x 4 kernel needs 2 per 16 and is bound by shared-memory
 // bandwidth: 161 us for this product at B = 100).  Global loads are register-prefetched one K block ahead.
-constexpr int DXK = 16, DXP = 132;
-__global__ void __launch_bounds__(256) k_dx_tallk(const float* __restrict__ A, const float* __restrict__ Bm, int M, int K, int kslice,
-                                                  float* __restrict__ part) {
-    __shared__ __align__(16) float As[DXK][DXP];
-    __shared__ __align__(16) float Bs[DXK][DXP];
+constexpr int DXK = 16, DXP = 132, DXS = 3;
+constexpr size_t DX_SMEM = (size_t)DXS * 2 * DXK * DXP * sizeof(float);
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = pred ? 4 : 0;                     // src-size 0: the 4 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+// Operand blocks travel global -> shared with 4-byte cp.async (the transposed [k][row] layout rules out wider copies; the row pitch of
+// both operands, 3V floats, is not 16-byte aligned anyway), three stages deep, so no registers are spent on staging and two CTAs fit an SM.
+__global__ void __launch_bounds__(256, 2) k_dx_tallk(const float* __restrict__ A, const float* __restrict__ Bm, int M, int K, int kslice,
+                                                     float* __restrict__ part) {
+    extern __shared__ __align__(16) float dx_smem[];
+    float (*As)[DXK][DXP] = reinterpret_cast<float (*)[DXK][DXP]>(dx_smem);
+    float (*Bs)[DXK][DXP] = reinterpret_cast<float (*)[DXK][DXP]>(dx_smem + DXS * DXK * DXP);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int n0 = blockIdx.x * 128, z = blockIdx.y;
     const int k_begin = z * kslice, k_end = min(K, k_begin + kslice);
+    const int nblk = (k_end - k_begin + DXK - 1) / DXK;
     const int lk = tid & 15, lr = tid >> 4;            // loader role: column lk of the K block, rows lr + 16 i
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float ra[8], rb[8];
-    auto load = [&](int k0) {
-        const int gk = k0 + lk;
-        const bool kin = gk < k_end;
+    auto issue = [&](int blk) {
+        if (blk < nblk) {
+            const int st = blk % DXS, gk = k_begin + blk * DXK + lk;
+            const bool kin = gk < k_end;
+            const int gkc = kin ? gk : k_begin;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = lr + 16 * i;
-            ra[i] = (kin && r < M) ? A[(size_t)r * K + gk] : 0.f;
-            rb[i] = kin ? __ldg(Bm + (size_t)(n0 + r) * K + gk) : 0.f;
+            for (int i = 0; i < 8; ++i) {
+                const int r = lr + 16 * i;
+                cp_async4(&As[st][lk][r], A + (size_t)min(r, M - 1) * K + gkc, kin && r < M);
+                cp_async4(&Bs[st][lk][r], Bm + (size_t)(n0 + r) * K + gkc, kin);
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // (an empty group past the end keeps the wait count uniform)
     };
-    load(k_begin);
-    for (int k0 = k_begin; k0 < k_end; k0 += DXK) {
-        __syncthreads();                                // previous block consumed
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { As[lk][lr + 16 * i] = ra[i]; Bs[lk][lr + 16 * i] = rb[i]; }
-        __syncthreads();
-        if (k0 + DXK < k_end) load(k0 + DXK);
+    issue(0);
+    issue(1);
+    for (int blk = 0; blk < nblk; ++blk) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // block `blk` has landed (this thread's copies)
+        __syncthreads();                                          // ... everybody's; and stage (blk + 2) % 3 is no longer being read
+        issue(blk + 2);
+        const int st = blk % DXS;
 #pragma unroll
         for (int k = 0; k < DXK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[st][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[st][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[st][k][64 + tx * 4]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -885,7 +898,9 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
             g.splitk = 2; g.C = c->part;
             if (B <= 128 && g_dx_tallk) {
                 const int kslice = cdiv(cdiv(3 * V, g.nz), DXK) * DXK;
-                k_dx_tallk<<<dim3(XK / 128, g.nz), 256, 0, st>>>(c->DVP, m->Wt, B, 3 * V, kslice, c->part);
+                static bool dx_cfg = false;
+                if (!dx_cfg) { LEMO_CUDA(cudaFuncSetAttribute(k_dx_tallk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DX_SMEM)); dx_cfg = true; }
+                k_dx_tallk<<<dim3(XK / 128, g.nz), 256, DX_SMEM, st>>>(c->DVP, m->Wt, B, 3 * V, kslice, c->part);
             } else LEMO_TRY(gemm_launch(g, st));
             k_slices_reduce<<<cdiv((long long)B * XK, 256), 256, 0, st>>>(c->part, g.nz, (long long)B * XK, ps->dX);
             LEMO_CUDA(cudaGetLastError());
