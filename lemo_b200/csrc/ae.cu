@@ -85,6 +85,7 @@ __global__ void k_mask_inplace(float* __restrict__ g, const float* __restrict__ 
 // range cut into 256-pixel chunks staged in shared memory.  Deterministic: the chunks are dealt to NG groups (blockIdx.z = n*NG + g),
 // a CTA accumulates its chunks in registers and stores ONE partial per (group, weight); k_wgrad_finish adds the N*NG partials in
 // order and writes the gradient in the state_dict layout (the first version atomicAdd-ed every chunk: order-dependent rounding).
+constexpr int AE_GB = 6;            // gradient buffers per resolution level (most tensors one backward pass leaves on a level)
 constexpr int WG_T = 16, WG_CP = 256, WG_DP = WG_CP + 4;      // WG_DP: pitch of the staged dpre rows (16-byte aligned rows)
 __global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ part,
                                                int Cin, int Cout, int H, int Wp, int PS, int nchunks, int NG, int SWX) {
@@ -262,14 +263,18 @@ int ae_create(int in_ch, const float* h_weights, long long n_weights, int maxN, 
     }
     if (sk) { LEMO_TRY(dalloc(&n->sk_scratch, sk)); n->sk_floats = sk; }
     if (with_backward) {
-        n->grad.resize(3, nullptr);
-        for (int i = 0; i < 3; ++i) LEMO_TRY(dalloc(&n->grad[i], gmax));
+        n->grad.resize(1, nullptr);
+        LEMO_TRY(dalloc(&n->grad[0], N * n->geom[0].PS));            // dpre of the last layer (1 channel, level 0)
+        const int cmax[6] = {32, 64, 128, 256, 256, 256};            // widest gradient tensor per level
+        n->glev.resize(6 * AE_GB, nullptr);
+        for (int l = 0; l < 6; ++l)
+            for (int k = 0; k < AE_GB; ++k) LEMO_TRY(dalloc(&n->glev[l * AE_GB + k], N * cmax[l] * n->geom[l].PS));
         LEMO_TRY(dalloc(&n->wg_scratch, wg)); n->wg_floats = wg;
         LEMO_TRY(dalloc(&n->wg_scratch2, wg));
         for (int i = 0; i < 2; ++i) { cudaStream_t s; LEMO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); n->bw_side[i] = s; }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 3; ++i) {
             cudaEvent_t e; LEMO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            if (i < 3) n->bw_done[i] = e; else n->bw_ready = e;
+            if (i < 2) n->bw_done[i] = e; else n->bw_ready = e;
         }
     }
     LEMO_CUDA(cudaDeviceSynchronize());
@@ -293,7 +298,7 @@ static int ae_forward_planes(ConvNet* n, int N, cudaStream_t st) {
     for (int b = 0; b < 5; ++b) {
         const PlaneGeom &gs = n->geom[5 - b], &gd = n->geom[4 - b];
         const ConvLayer &A = n->layers[10 + 2 * b], &B = n->layers[11 + 2 * b];
-        LEMO_CUDA(cudaMemsetAsync(n->act[DU(b)], 0, (size_t)N * dc[b] * gd.PS * sizeof(float), st));
+        // (act[DU(b)] was zeroed at create; only the (2y, 2x) positions are ever written, so the zeros in between persist)
         const long long tot = (long long)N * dc[b] * gs.H * gs.W;
         k_upsample_fwd<<<cdiv(tot, 256), 256, 0, st>>>(cur, N * dc[b], gs, gd, n->act[DU(b)]);
         LEMO_TRY(conv3x3_launch(n->act[DU(b)], A.wk_f, n->w_flat + A.b_off, nullptr, n->act[D1(b)], N, A.Cin, A.Cout, gd, EPI_BIAS_LRELU, st, n->sk_scratch, n->sk_floats));
@@ -308,76 +313,74 @@ static int ae_forward_planes(ConvNet* n, int N, cudaStream_t st) {
 
 // d_rec already packed into grad[0] (1 channel at level 0); writes d_weights (flat, state_dict order; every element is written).
 // The input-gradient chain runs on `st`; the weight gradient of each layer is forked onto one of two side streams (alternating, each with
-// its own partials scratch) as soon as that layer's dpre exists, and joined before `st` reuses the buffer it reads -- three rotating
-// gradient buffers, so a weight gradient may trail the chain by two layers.  Inside the captured fine-tune step these are graph branches.
+// its own partials scratch) as soon as that layer's dpre exists, and both are joined at the end.  Every tensor of the chain gets its own
+// buffer from a per-level pool (AE_GB per resolution level): nothing is overwritten within a pass, so the side streams need no
+// intermediate joins, and -- the buffers being zeroed once and producers writing plane interiors only -- the zero-border invariant of
+// the plane layout holds without the ~35 per-step clears the two-buffer version needed.  Inside the captured step these are graph branches.
 static int ae_backward_planes(ConvNet* n, int N, float* dW, cudaStream_t st) {
     const int ec[6] = {n->in_ch, 32, 64, 128, 256, 256}, dc[6] = {256, 256, 128, 64, 32, 1};
-    int c = 0;                    // n->grad[c] = dpre of the layer being processed
-    bool pending[3] = {false, false, false};
+    int ring[6] = {0, 0, 0, 0, 0, 0};
     int forks = 0;
+    bool used[2] = {false, false};
     cudaEvent_t ready = (cudaEvent_t)n->bw_ready;
-    // the gradient buffers are reused across resolution levels, so the zero-border invariant of the plane layout
-    // has to be re-established before every producer that only writes plane interiors
-    auto next_zeroed = [&](int C, const PlaneGeom& g) -> int {      // claim the next buffer of the ring: wait for its reader, clear it
-        const int nx = (c + 1) % 3;
-        if (pending[nx]) { if (cudaStreamWaitEvent(st, (cudaEvent_t)n->bw_done[nx], 0) != cudaSuccess) return -1; pending[nx] = false; }
-        if (cudaMemsetAsync(n->grad[nx], 0, (size_t)N * C * g.PS * sizeof(float), st) != cudaSuccess) return -1;
-        return nx;
-    };
-    auto wgrad = [&](const float* x, const ConvLayer& L, const PlaneGeom& g, bool transposed) -> int {
+    auto out_buf = [&](int level) -> float* { return ring[level] < AE_GB ? n->glev[level * AE_GB + ring[level]++] : nullptr; };
+    auto wgrad = [&](const float* x, const float* dpre, const ConvLayer& L, const PlaneGeom& g, bool transposed) -> int {
         const int k = forks++ & 1;
         cudaStream_t s = (cudaStream_t)n->bw_side[k];
         LEMO_CUDA(cudaEventRecord(ready, st));
         LEMO_CUDA(cudaStreamWaitEvent(s, ready, 0));
-        LEMO_TRY(conv3x3_wgrad_launch(x, n->grad[c], dW + L.w_off, dW + L.b_off, N, L.Cin, L.Cout, g, transposed, s,
+        LEMO_TRY(conv3x3_wgrad_launch(x, dpre, dW + L.w_off, dW + L.b_off, N, L.Cin, L.Cout, g, transposed, s,
                                       k ? n->wg_scratch2 : n->wg_scratch, n->wg_floats));
-        LEMO_CUDA(cudaEventRecord((cudaEvent_t)n->bw_done[c], s));
-        pending[c] = true;
+        used[k] = true;
         return 0;
     };
-    int nx;
+    const float* cur = n->grad[0];    // dpre of the layer being processed
+    float* nxt;
     for (int b = 4; b >= 0; --b) {
         const PlaneGeom &gs = n->geom[5 - b], &gd = n->geom[4 - b];
         const ConvLayer &A = n->layers[10 + 2 * b], &B = n->layers[11 + 2 * b];
-        // deconv2: dpre in grad[c] (for b<4 it already carries LeakyReLU'(D2))
-        LEMO_TRY(wgrad(n->act[D1(b)], B, gd, true));
-        LEMO_CHECK((nx = next_zeroed(B.Cin, gd)) >= 0, "stream error");
-        LEMO_TRY(conv3x3_launch(n->grad[c], B.wk_b, nullptr, n->act[D1(b)], n->grad[nx], N, B.Cout, B.Cin, gd, EPI_MASK, st, n->sk_scratch, n->sk_floats));
-        c = nx;
+        // deconv2: dpre in cur (for b<4 it already carries LeakyReLU'(D2))
+        LEMO_TRY(wgrad(n->act[D1(b)], cur, B, gd, true));
+        LEMO_CHECK((nxt = out_buf(4 - b)) != nullptr, "gradient buffer pool exhausted");
+        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[D1(b)], nxt, N, B.Cout, B.Cin, gd, EPI_MASK, st, n->sk_scratch, n->sk_floats));
+        cur = nxt;
         // deconv1
-        LEMO_TRY(wgrad(n->act[DU(b)], A, gd, true));
-        LEMO_CHECK((nx = next_zeroed(A.Cin, gd)) >= 0, "stream error");
-        LEMO_TRY(conv3x3_launch(n->grad[c], A.wk_b, nullptr, nullptr, n->grad[nx], N, A.Cout, A.Cin, gd, EPI_NONE, st, n->sk_scratch, n->sk_floats));
-        c = nx;
+        LEMO_TRY(wgrad(n->act[DU(b)], cur, A, gd, true));
+        LEMO_CHECK((nxt = out_buf(4 - b)) != nullptr, "gradient buffer pool exhausted");
+        LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, gd, EPI_NONE, st, n->sk_scratch, n->sk_floats));
+        cur = nxt;
         // through the zero-upsample to the tensor that fed this block: D2(b-1) (LeakyReLU output) or the pooled code z
         const long long tot = (long long)N * dc[b] * gs.H * gs.W;
         const float* mask = b > 0 ? n->act[D2(b - 1)] : nullptr;
-        LEMO_CHECK((nx = next_zeroed(dc[b], gs)) >= 0, "stream error");
-        k_upsample_bwd_mask<<<cdiv(tot, 256), 256, 0, st>>>(n->grad[c], mask, N * dc[b], gs, gd, n->grad[nx]);
-        c = nx;
+        LEMO_CHECK((nxt = out_buf(5 - b)) != nullptr, "gradient buffer pool exhausted");
+        k_upsample_bwd_mask<<<cdiv(tot, 256), 256, 0, st>>>(cur, mask, N * dc[b], gs, gd, nxt);
+        cur = nxt;
     }
-    // grad[c] = dL/dz on level-5 planes (pooled output of encoder level 4)
+    // cur = dL/dz on level-5 planes (pooled output of encoder level 4)
     for (int i = 4; i >= 0; --i) {
         const PlaneGeom &g = n->geom[i], &gd = n->geom[i + 1];
         const ConvLayer &A = n->layers[2 * i], &B = n->layers[2 * i + 1];
         const long long tot = (long long)N * ec[i + 1] * g.H * g.W;
-        LEMO_CHECK((nx = next_zeroed(ec[i + 1], g)) >= 0, "stream error");
-        k_maxpool_bwd_mask<<<cdiv(tot, 256), 256, 0, st>>>(n->grad[c], n->pool_idx[i], n->act[E2(i)], N * ec[i + 1], g, gd, n->grad[nx]);
-        c = nx;                       // dpre of conv2 at level i
-        LEMO_TRY(wgrad(n->act[E1(i)], B, g, false));
-        LEMO_CHECK((nx = next_zeroed(B.Cin, g)) >= 0, "stream error");
-        LEMO_TRY(conv3x3_launch(n->grad[c], B.wk_b, nullptr, n->act[E1(i)], n->grad[nx], N, B.Cout, B.Cin, g, EPI_MASK, st, n->sk_scratch, n->sk_floats));
-        c = nx;                       // dpre of conv1 at level i
+        LEMO_CHECK((nxt = out_buf(i)) != nullptr, "gradient buffer pool exhausted");
+        k_maxpool_bwd_mask<<<cdiv(tot, 256), 256, 0, st>>>(cur, n->pool_idx[i], n->act[E2(i)], N * ec[i + 1], g, gd, nxt);
+        cur = nxt;                    // dpre of conv2 at level i
+        LEMO_TRY(wgrad(n->act[E1(i)], cur, B, g, false));
+        LEMO_CHECK((nxt = out_buf(i)) != nullptr, "gradient buffer pool exhausted");
+        LEMO_TRY(conv3x3_launch(cur, B.wk_b, nullptr, n->act[E1(i)], nxt, N, B.Cout, B.Cin, g, EPI_MASK, st, n->sk_scratch, n->sk_floats));
+        cur = nxt;                    // dpre of conv1 at level i
         const float* xin = i > 0 ? n->act[EP(i - 1)] : n->act[0];
-        LEMO_TRY(wgrad(xin, A, g, false));
+        LEMO_TRY(wgrad(xin, cur, A, g, false));
         if (i > 0) {
-            LEMO_CHECK((nx = next_zeroed(A.Cin, g)) >= 0, "stream error");
-            LEMO_TRY(conv3x3_launch(n->grad[c], A.wk_b, nullptr, nullptr, n->grad[nx], N, A.Cout, A.Cin, g, EPI_NONE, st, n->sk_scratch, n->sk_floats));
-            c = nx;                   // dL/d(pooled output of level i-1), on level-i planes
+            LEMO_CHECK((nxt = out_buf(i)) != nullptr, "gradient buffer pool exhausted");
+            LEMO_TRY(conv3x3_launch(cur, A.wk_b, nullptr, nullptr, nxt, N, A.Cout, A.Cin, g, EPI_NONE, st, n->sk_scratch, n->sk_floats));
+            cur = nxt;                // dL/d(pooled output of level i-1), on level-i planes
         }
     }
-    for (int i = 0; i < 3; ++i)       // join: every weight gradient is complete before the caller's next operation on `st`
-        if (pending[i]) LEMO_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)n->bw_done[i], 0));
+    for (int k = 0; k < 2; ++k)       // join: every weight gradient is complete before the caller's next operation on `st`
+        if (used[k]) {
+            LEMO_CUDA(cudaEventRecord((cudaEvent_t)n->bw_done[k], (cudaStream_t)n->bw_side[k]));
+            LEMO_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)n->bw_done[k], 0));
+        }
     LEMO_CUDA(cudaGetLastError());
     n->launches += 64;
     return 0;

@@ -36,6 +36,9 @@ __global__ void __launch_bounds__(NW * 32) k_conv3x3(const float* __restrict__ i
                                                      int SW, int epi, int KS, int cps, int Nn) {
     // KS > 1: blockIdx.z = n * KS + ks; this CTA contracts input channels [ks*cps, (ks+1)*cps) only and stores its RAW partial sums
     // into out = scratch[ks][n][oc][q]; k_conv_splitk_finish adds the slices in order and applies the epilogue (deterministic).
+    // (Fusing that finish into this kernel -- the last-arriving CTA of a tile sums the slices, arrival counter per tile -- was measured:
+    // it removes 34 launches per AE step but confines each tile's 16 KS float4 loads per thread to ONE SM; on the deep levels (4 tiles,
+    // 32 slices) the tail is longer than the launch it saves: 71 -> 117 ms per clip.  The separate kernel spreads the sums over all SMs.)
     // Small feature maps (the deep AE levels: 16x16 planes, 256 channels) would otherwise run on 4-30 CTAs.
     constexpr int OCB = NW * 8, NT = NW * 32;
     extern __shared__ __align__(16) float smem[];
@@ -442,7 +445,8 @@ void convnet_free(ConvNet* n) {
     cudaFree(n->wg_scratch2);
     for (int i = 0; i < 2; ++i) if (n->bw_side[i]) cudaStreamDestroy((cudaStream_t)n->bw_side[i]);
     if (n->bw_ready) cudaEventDestroy((cudaEvent_t)n->bw_ready);
-    for (int i = 0; i < 3; ++i) if (n->bw_done[i]) cudaEventDestroy((cudaEvent_t)n->bw_done[i]);
+    for (int i = 0; i < 2; ++i) if (n->bw_done[i]) cudaEventDestroy((cudaEvent_t)n->bw_done[i]);
+    for (auto p : n->glev) cudaFree(p);
     if (n->ft_stream) { cudaStreamDestroy((cudaStream_t)n->ft_stream); cudaEventDestroy((cudaEvent_t)n->ft_ev_in); cudaEventDestroy((cudaEvent_t)n->ft_ev_out); }
     for (auto& L : n->layers) { cudaFree(L.wk_f); cudaFree(L.wk_b); }
     for (auto p : n->act) cudaFree(p);

@@ -70,9 +70,10 @@ struct ConvNet {
     // AE backward: the weight gradients of a layer run on two side streams beside the input-gradient chain (fork/join with events; captured
     // into the fine-tune graph as parallel branches); three rotating gradient buffers give every weight gradient two layers of slack
     float* wg_scratch2 = nullptr;
+    std::vector<float*> glev;          // AE: AE_GB gradient buffers per resolution level (zeroed once; producers write interiors only, so no per-step clears)
     void* bw_side[2] = {nullptr, nullptr};
     void* bw_ready = nullptr;
-    void* bw_done[3] = {nullptr, nullptr, nullptr};
+    void* bw_done[2] = {nullptr, nullptr};
     // fine-tune driver (lemo_ae_finetune_run): device-side step schedule + one captured step
     void *ft_sched = nullptr, *ft_graph = nullptr, *ft_gexec = nullptr, *ft_stream = nullptr, *ft_ev_in = nullptr, *ft_ev_out = nullptr;
     const void *ft_x = nullptr, *ft_mask = nullptr;
