@@ -58,6 +58,33 @@ def launches(tag):
         f.write('\ntotal %.1f us over %d launches\n' % (tot, n))
 
 
+def stage_launches(tag):
+    """gpurun_out/launches_<stage>.csv (tools/gpu_call.sh stages) -> profiles/<tag>_launches_<stage>.md: per-kernel totals of one stage run."""
+    for src in sorted(glob.glob(os.path.join(OUT, 'launches_*.csv'))):
+        stage = os.path.basename(src)[len('launches_'):-4]
+        lines = [l for l in open(src) if not l.startswith('==')]
+        agg, tot, n = collections.OrderedDict(), 0.0, 0
+        for row in csv.DictReader(io.StringIO(''.join(lines))):
+            if row.get('Metric Name') != 'gpu__time_duration.sum':
+                continue
+            v = float(row['Metric Value'].replace(',', ''))
+            v = v / 1000 if row['Metric Unit'] == 'ns' else v * 1000 if row['Metric Unit'] == 'ms' else v
+            a = agg.setdefault(row['Kernel Name'].split('(')[0][:72], [0, 0.0])
+            a[0] += 1
+            a[1] += v
+            tot += v
+            n += 1
+        if not n:
+            continue
+        with open(os.path.join(PROF, '%s_launches_%s_final.md' % (tag, stage)), 'w') as f:
+            f.write('# %s launch list of `python tools/run_stage.py %s` under `ncu --metrics gpu__time_duration.sum --clock-control none`\n'
+                    '# cold-cache, serialised launches, set-up launches of the stage included: compare SHARES, not absolutes\n\n'
+                    '| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|\n' % (tag, stage))
+            for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
+                f.write('| `%s` | %d | %.1f | %.1f%% | %.1f |\n' % (k, c, t, 100 * t / tot, t / c))
+            f.write('\ntotal %.1f us over %d launches\n' % (tot, n))
+
+
 def full(tag):
     traffic = {}
     path = os.path.join(PROF, 'ncu_traffic.json')
@@ -100,8 +127,12 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
+    stage_launches(tag)
     full(tag)
-    for src, dst in (('bench_n1.json', '_bench_n1.json'), ('bench_ref.json', '_bench_reference.json')):
+    for src, dst in (('bench_n1.json', '_bench_n1.json'), ('bench_ref.json', '_bench_reference.json'), ('bench_n2.json', '_bench_n2.json'),
+                     ('sanitizer_memcheck.log', '_sanitizer_memcheck.log'), ('sanitizer_racecheck_perframe.log', '_sanitizer_racecheck_perframe.log'),
+                     ('sanitizer_racecheck_prox.log', '_sanitizer_racecheck_prox.log'), ('sanitizer_racecheck_infill.log', '_sanitizer_racecheck_infill.log'),
+                     ('smoke.log', '_smoke.log'), ('diag_lbs.log', '_lbs_forward_timing.txt')):
         p = os.path.join(OUT, src)
         if os.path.exists(p) and os.path.getsize(p) > 0:
             shutil.copy(p, os.path.join(PROF, tag + dst))
