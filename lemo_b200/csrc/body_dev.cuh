@@ -121,8 +121,17 @@ __device__ __forceinline__ void pose_to_rot_bwd_body(const PoseK& p, const PoseG
 // (Two kernels -- one thread per (frame, joint), then this block shape -- cost 5.5 + 8 us per forward at B=120; forking the chain
 // onto a side stream beside the blend GEMM was measured too: the fork/join edges cost what the overlap saves.)
 // =============================================================================================
+// The tree tables are read inside the single-warp walks, where every load is on the critical path: callers that do not already keep them
+// in shared memory (the stand-alone kernels: TREE_SMEM = false) stage them here, before the body's first barrier.
+template <bool TREE_SMEM>
+__device__ __forceinline__ const int* stage_tree(const int* __restrict__ tree, int* s_tree, int nthreads) {
+    if (TREE_SMEM) return tree;
+    for (int i = threadIdx.x; i < TREE_N; i += nthreads) s_tree[i] = __ldg(tree + i);
+    return s_tree;
+}
+
 // want_aa = false skips the axis-angle of rotation-matrix overrides (only the saved [T,72] rows need it).
-template <bool SUB64 = false>
+template <bool SUB64 = false, bool TREE_SMEM = false>
 __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float* __restrict__ J_template,
                                                     const float* __restrict__ J_dirs, const int* __restrict__ tree, int max_depth,
                                                     float* __restrict__ full_pose,
@@ -137,7 +146,8 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
     __shared__ __align__(16) float sX[XK];
     const int j = threadIdx.x;
     const int nthr = SUB64 ? 64 : blockDim.x;
-    int e = tree[TREE_LANE + (threadIdx.x & 31)];          // level-0 word of the tree walk below, requested early
+    __shared__ int s_tree[TREE_SMEM ? 1 : TREE_N];
+    const int* T = stage_tree<TREE_SMEM>(tree, s_tree, nthr);
     BODY_STAMP(0);
     if (j < NBETA) {
         float v = 0.f;
@@ -196,8 +206,9 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
     // offset ahead of the barrier as well was measured: slower -- the loads must complete before the barrier, so a level then pays two
     // shared-memory latencies instead of one.)
     if (threadIdx.x < 32) {
+        int e = T[TREE_LANE + threadIdx.x];
         for (int lev = 0; lev <= max_depth; ++lev) {
-            const int e_next = lev < max_depth ? tree[TREE_LANE + (lev + 1) * 32 + threadIdx.x] : -1;
+            const int e_next = lev < max_depth ? T[TREE_LANE + (lev + 1) * 32 + threadIdx.x] : -1;
             if (e >= 0) {
                 const int jj = e & 255, par = ((e >> 8) & 255) - 1;
                 const float* r = sR[jj];
@@ -249,7 +260,7 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
 // adjoint of k_chain_fwd.  dA is joint-major [55][B*12]; dJp [B,55,3]; dX [B,512].
 // Writes dR [B,55,9]; betas/expression grads (per frame, or atomically into one row when betas_stride==0).
 // NEED_J = false drops the rest-joint adjoint (it only feeds the betas / expression gradients).
-template <bool SUB64 = false, bool NEED_J = true>
+template <bool SUB64 = false, bool NEED_J = true, bool TREE_SMEM = false>
 __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ Jrest,
                                                const float* __restrict__ dA, const float* __restrict__ dJp, const float* __restrict__ dX,
                                                const float* __restrict__ J_dirs, const int* __restrict__ tree, int max_depth, int B,
@@ -263,7 +274,8 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
     __shared__ float sR[NJ][9];
     __shared__ float sdR[NJ][9];      // chain part of dR; the blend-shape part dX is added by all threads after the walk
     const int j = threadIdx.x;
-    int e = tree[TREE_LANE + max_depth * 32 + (threadIdx.x & 31)];      // deepest level's word of the walk below, requested early
+    __shared__ int s_tree[TREE_SMEM ? 1 : TREE_N];
+    const int* T = stage_tree<TREE_SMEM>(tree, s_tree, SUB64 ? 64 : blockDim.x);
     BODY_STAMP(8);
     if (j < NJ) {
         float gl[12], Jr[3];
@@ -289,14 +301,15 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
     // reproducible, which the sequence-sharding contract relies on (same sequence, any slot / GPU -> same parameters).  One __syncwarp
     // per level.
     if (threadIdx.x < 32) {
+        int e = T[TREE_LANE + max_depth * 32 + threadIdx.x];
         for (int lev = max_depth; lev >= 0; --lev) {
-            const int e_next = lev > 0 ? tree[TREE_LANE + (lev - 1) * 32 + threadIdx.x] : -1;
+            const int e_next = lev > 0 ? T[TREE_LANE + (lev - 1) * 32 + threadIdx.x] : -1;
             if (e >= 0) {
                 const int jj = e & 255, par = ((e >> 8) & 255) - 1, k0 = (e >> 16) & 255, nk = (e >> 24) & 255;
                 float dG[12];
                 for (int k = 0; k < 12; ++k) dG[k] = sdG[jj][k];
                 for (int q = 0; q < nk; ++q) {
-                    const int c = tree[TREE_KLIST + k0 + q];
+                    const int c = T[TREE_KLIST + k0 + q];
                     for (int k = 0; k < 12; ++k) dG[k] += sC[c][k];
                 }
                 if (par >= 0) {
@@ -334,8 +347,8 @@ __device__ __forceinline__ void chain_bwd_body(const float* __restrict__ R, cons
     body_sync<SUB64>();
     BODY_STAMP(12);
     if (NEED_J && j < NJ) {                  // children's share of the rest-joint adjoint (ascending child index)
-        for (int q = tree[TREE_KOFF + j]; q < tree[TREE_KOFF + j + 1]; ++q) {
-            const int c = tree[TREE_KLIST + q];
+        for (int q = T[TREE_KOFF + j]; q < T[TREE_KOFF + j + 1]; ++q) {
+            const int c = T[TREE_KLIST + q];
             for (int k = 0; k < 3; ++k) sdJ[j][k] += sC[c][12 + k];
         }
     }

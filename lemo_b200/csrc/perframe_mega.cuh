@@ -225,7 +225,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 __syncthreads();
                 if (tid < NBODY) gs6d_fwd(b_o + tid * 6, b_Rb + tid * 9);
                 __syncthreads();
-                pose_chain_fwd_body(pk, c_Jt, c_Jd, c_tree, a.max_depth, b_fp, b_R, b_X, nullptr, b_G, s_A, b_Jr, b_Jp, nullptr, 0, last);
+                pose_chain_fwd_body<false, true>(pk, c_Jt, c_Jd, c_tree, a.max_depth, b_fp, b_R, b_X, nullptr, b_G, s_A, b_Jr, b_Jp, nullptr, 0, last);
                 __syncthreads();
                 if (last && rank == 0 && tid < 72) {                               // the [T,72] row the script saves: parameters of the LAST forward
                     float v;
@@ -343,7 +343,7 @@ __global__ void __cluster_dims__(PM_CL, 1, 1) __launch_bounds__(PM_NT, 1) k_perf
                 }
                 __syncthreads();
                 PM_STAMP(11);
-                chain_bwd_body<false, false>(b_R, b_G, b_Jr, b_dA, nullptr, b_dX, c_Jd, c_tree, a.max_depth, 1, 10, b_dR, nullptr, nullptr, 0);
+                chain_bwd_body<false, false, true>(b_R, b_G, b_Jr, b_dA, nullptr, b_dX, c_Jd, c_tree, a.max_depth, 1, 10, b_dR, nullptr, nullptr, 0);
                 __syncthreads();
                 PM_STAMP(12);
                 // Gram-Schmidt adjoints on warps 2-3, straight from dR, while warps 0-1 run the axis-angle adjoint of the hands

@@ -135,3 +135,27 @@ def test_bad_arguments_return_status_and_message(built_lib):
         assert status != 0, name
         msg = L.lemo_last_error().decode()
         assert msg and '@' in msg, (name, msg)             # "<what> (<failed condition>) @file:line"
+
+
+def test_sparse_synthetic_model_has_smplx_like_skinning_weights():
+    """synth.make_smplx_model(weights_nnz=4): at most 4 influences per vertex, on a joint and its ancestors, rows normalised, and a tile of
+    256 consecutive vertices touches a handful of joints (what the compact skinning adjoint keys on); the default model stays dense."""
+    import numpy as np
+    from lemo_b200 import synth
+    m = synth.make_smplx_model(0, weights_nnz=4)
+    w = m['lbs_weights']
+    nz = w != 0
+    assert nz.sum(1).max() == 4 and nz.sum(1).min() >= 1
+    assert np.allclose(w.sum(1), 1.0, atol=1e-6)
+    par = m['parents']
+    for v in (0, 1234, 5000, w.shape[0] - 1):
+        js = np.nonzero(nz[v])[0]
+        top = js.max()                                    # the home joint; the others are its ancestors
+        chain, c = {int(top)}, int(top)
+        while par[c] >= 0 and len(chain) < 4:
+            c = int(par[c]); chain.add(c)
+        assert set(js.tolist()) == chain
+    ntile = (w.shape[0] + 255) // 256
+    slots = sum(int(nz[t * 256:(t + 1) * 256].any(0).sum()) for t in range(ntile))
+    assert slots * 5 < ntile * 55 * 2
+    assert (synth.make_smplx_model(0)['lbs_weights'] != 0).all()
