@@ -77,6 +77,8 @@ void skin_tc_set(int on) { g_skin_tc = on ? 1 : 0; }
 // force the dense kernel (parity tests compare the two)
 static int g_skin_sparse = []() { const char* e = getenv("LEMO_SKIN_ADJ"); return (e && strcmp(e, "dense") == 0) ? 0 : 1; }();
 void skin_sparse_set(int on) { g_skin_sparse = on ? 1 : 0; }
+// LEMO_SKIN_SMALL=0: loss-row sub-models through the general skinning kernels (A/B measurements)
+static int g_skin_small = []() { const char* e = getenv("LEMO_SKIN_SMALL"); return (e && e[0] == '0') ? 0 : 1; }();
 // LEMO_DX=gemm routes the full-mesh dX product through the generic SGEMM instead of k_dx_tallk (A/B measurements)
 static int g_dx_tallk = []() { const char* e = getenv("LEMO_DX"); return (e && strcmp(e, "gemm") == 0) ? 0 : 1; }();
 
@@ -201,6 +203,7 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
         }
         for (int j = 0; j < NJ; ++j) {
             t[TREE_PAR + j] = m->h_parents[j];
+            t[TREE_DEPTH + j] = m->h_depth[j];
             t[TREE_KOFF + j] = k;
             for (int c = j + 1; c < NJ; ++c)
                 if (m->h_parents[c] == j) t[TREE_KLIST + k++] = c;
@@ -517,6 +520,117 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
     s = block_sum(gs1, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 1] = s; else atomicAdd(&dtr[b * 3 + 1], s); }
     s = block_sum(gs2, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 2] = s; else atomicAdd(&dtr[b * 3 + 2], s); }
 }
+// ---- loss-row sub-models (V <= SKS_V rows: the 81 marker / foot rows of the AMASS fits, one CTA per frame in the general kernels = 960
+// CTAs whose whole life is latency: 55 dependent-ish global weight loads per thread, staging loops, 46 us for 90 MFLOP).  Here a CTA keeps
+// the sub-model's weights [55][V] in shared memory (pitch 97: conflict-free by row and by column) and walks frames b = blockIdx.x,
+// blockIdx.x + gridDim.x, ...  Same summation orders as k_skin_fwd / k_skin_bwd: bit-identical results.
+constexpr int SKS_V = 96, SKS_P = 97;
+__global__ void __launch_bounds__(128) k_skin_fwd_small(const float* __restrict__ A, const float* __restrict__ w_jm,
+                                                        const float* __restrict__ v_template, const float* __restrict__ transl,
+                                                        int V, int B, float* __restrict__ VP, float* __restrict__ verts) {
+    __shared__ float s_w[NJ * SKS_P];
+    __shared__ __align__(16) float sA[NJ * 12];
+    for (int i = threadIdx.x; i < NJ * V; i += 128) { const int j = i / V, v = i - j * V; s_w[j * SKS_P + v] = w_jm[i]; }
+    const int v = threadIdx.x;
+    float vt0 = 0.f, vt1 = 0.f, vt2 = 0.f;
+    if (v < V) { vt0 = v_template[v * 3]; vt1 = v_template[v * 3 + 1]; vt2 = v_template[v * 3 + 2]; }
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NJ * 12; i += 128) sA[i] = A[(size_t)b * NJ * 12 + i];
+        __syncthreads();
+        if (v >= V) continue;
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = 0.f;
+#pragma unroll 5
+        for (int j = 0; j < NJ; ++j) {
+            const float w = s_w[j * SKS_P + v];
+            const float4* a = reinterpret_cast<const float4*>(sA + j * 12);
+            const float4 a0 = a[0], a1 = a[1], a2 = a[2];
+            T[0] = fmaf(w, a0.x, T[0]); T[1] = fmaf(w, a0.y, T[1]); T[2] = fmaf(w, a0.z, T[2]); T[3] = fmaf(w, a0.w, T[3]);
+            T[4] = fmaf(w, a1.x, T[4]); T[5] = fmaf(w, a1.y, T[5]); T[6] = fmaf(w, a1.z, T[6]); T[7] = fmaf(w, a1.w, T[7]);
+            T[8] = fmaf(w, a2.x, T[8]); T[9] = fmaf(w, a2.y, T[9]); T[10] = fmaf(w, a2.z, T[10]); T[11] = fmaf(w, a2.w, T[11]);
+        }
+        float* vp = VP + ((size_t)b * V + v) * 3;
+        const float p0 = vp[0] + vt0, p1 = vp[1] + vt1, p2 = vp[2] + vt2;
+        vp[0] = p0; vp[1] = p1; vp[2] = p2;
+        const float t0 = transl ? transl[b * 3] : 0.f, t1 = transl ? transl[b * 3 + 1] : 0.f, t2 = transl ? transl[b * 3 + 2] : 0.f;
+        float* o = verts + ((size_t)b * V + v) * 3;
+        o[0] = T[0] * p0 + T[1] * p1 + T[2] * p2 + T[3] + t0;
+        o[1] = T[4] * p0 + T[5] * p1 + T[6] * p2 + T[7] + t1;
+        o[2] = T[8] * p0 + T[9] * p1 + T[10] * p2 + T[11] + t2;
+    }
+}
+__global__ void __launch_bounds__(256) k_skin_bwd_small(const float* __restrict__ A, const float* __restrict__ w_jm,
+                                                        const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B,
+                                                        float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr) {
+    __shared__ float s_w[NJ * SKS_P];
+    __shared__ float sA[NJ * 12];
+    __shared__ __align__(16) float s_dt[SKS_V * 12];
+    __shared__ float s_acc[4][NJ * 12];
+    __shared__ float sred[32];
+    for (int i = threadIdx.x; i < NJ * V; i += 256) { const int j = i / V, v = i - j * V; s_w[j * SKS_P + v] = w_jm[i]; }
+    const int v = threadIdx.x;
+    const int jB = threadIdx.x % NJ, sB = threadIdx.x / NJ;       // phase-B role (threads < 220)
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NJ * 12; i += 256) sA[i] = A[(size_t)b * NJ * 12 + i];
+        __syncthreads();
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (v < V) {
+            float T[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) T[k] = 0.f;
+#pragma unroll 5
+            for (int j = 0; j < NJ; ++j) {
+                const float w = s_w[j * SKS_P + v];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) T[i * 3 + c] = fmaf(w, sA[j * 12 + i * 4 + c], T[i * 3 + c]);
+            }
+            const float* g = Gv + ((size_t)b * V + v) * 3;
+            g0 = g[0]; g1 = g[1]; g2 = g[2];
+            const float* vp = VP + ((size_t)b * V + v) * 3;
+            const float p[4] = {vp[0], vp[1], vp[2], 1.f};
+            float* dvp = DVP + ((size_t)b * V + v) * 3;
+            dvp[0] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+            dvp[1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+            dvp[2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+            const float gg[3] = {g0, g1, g2};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                *reinterpret_cast<float4*>(&s_dt[v * 12 + i * 4]) = make_float4(gg[i] * p[0], gg[i] * p[1], gg[i] * p[2], gg[i] * p[3]);
+        }
+        __syncthreads();
+        if (threadIdx.x < NJ * 4) {
+            float acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+            for (int u = sB; u < V; u += 4) {
+                const float w = s_w[jB * SKS_P + u];
+                const float4* d = reinterpret_cast<const float4*>(&s_dt[u * 12]);
+                const float4 d0 = d[0], d1 = d[1], d2 = d[2];
+                acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]); acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]); acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                acc[8] = fmaf(w, d2.x, acc[8]); acc[9] = fmaf(w, d2.y, acc[9]); acc[10] = fmaf(w, d2.z, acc[10]); acc[11] = fmaf(w, d2.w, acc[11]);
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_acc[sB][jB * 12 + k] = acc[k];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < NJ * 12; t += 256) {        // this CTA is the only writer of frame b's entries: plain read-modify-write
+            const float a = (s_acc[0][t] + s_acc[1][t]) + (s_acc[2][t] + s_acc[3][t]);
+            const int j = t / 12, k = t - j * 12;
+            dA[(size_t)j * B * 12 + (size_t)b * 12 + k] += a;
+        }
+        float q;
+        q = block_sum(g0, sred); if (threadIdx.x == 0) dtr[b * 3] += q;
+        q = block_sum(g1, sred); if (threadIdx.x == 0) dtr[b * 3 + 1] += q;
+        q = block_sum(g2, sred); if (threadIdx.x == 0) dtr[b * 3 + 2] += q;
+    }
+}
+
 // ---- compact skinning adjoint (full meshes with sparse weights; same result as k_skin_bwd up to summation order, fixed order throughout).
 // One CTA per (tile of 256 vertices, frame).  Phase A, thread = vertex: T = sum over the tile's ACTIVE joints of w A_j.R, d v_posed = T^T g,
 // dT = g (x) [v_posed, 1] parked in shared memory.  Phase B, thread = (active-joint slot a, vertex residue r of 16): the 12 entries of
@@ -827,6 +941,8 @@ static int body_apply_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, i
     const Model* m = c->m;
     const int V = m->V;
     if (both_tc(m, ps)) LEMO_TRY(skin_tc_launch(m->map_w2, ps->map_a2, c->VP, in.transl, V, B, verts, st));
+    else if (V <= SKS_V && g_skin_small)
+        k_skin_fwd_small<<<std::min(B, 148 * 4), 128, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, B, c->VP, verts);
     else k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
     if (joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");
@@ -880,6 +996,8 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
                                                                  partc, part_tr);
             k_skin_bwd_act_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(partc, m->sk_joff, m->sk_jslot, m->sk_nslot, part_tr, m->sk_ntile, B,
                                                                            ps->dA, ps->dtr);
+        } else if (V <= SKS_V && g_skin_small) {
+            k_skin_bwd_small<<<std::min(B, 148 * 3), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, c->DVP, ps->dA, ps->dtr);
         } else {
             k_skin_bwd<<<dim3(ctas, B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr, part);
             if (part) k_skin_bwd_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(part, ctas, B, ps->dA, ps->dtr);

@@ -13,7 +13,8 @@ constexpr int TREE_OFF = 112;      // [max_depth + 2] first position of each lev
 constexpr int TREE_KOFF = 128;     // [56] children of joint j = KLIST[KOFF[j] .. KOFF[j+1]) in ascending index
 constexpr int TREE_KLIST = 184;    // [54]
 constexpr int TREE_LANE = 240;     // [TREE_MAX_DEPTH + 1][32] one word per (level, lane): joint | (parent + 1) << 8 | KOFF << 16 | n_children << 24, or -1
-constexpr int TREE_N = 240 + 15 * 32;
+constexpr int TREE_DEPTH = 240 + 15 * 32;   // [55] depth of joint j (the stand-alone forward kernel walks thread-per-joint)
+constexpr int TREE_N = TREE_DEPTH + 56;
 constexpr int TREE_MAX_DEPTH = 14;
 
 constexpr int SKIN_TC_FR = 8;      // frames per unit of the tensor-core skinning kernel (layout of BodyCtx::A2)

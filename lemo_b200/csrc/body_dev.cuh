@@ -146,8 +146,10 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
     __shared__ __align__(16) float sX[XK];
     const int j = threadIdx.x;
     const int nthr = SUB64 ? 64 : blockDim.x;
-    __shared__ int s_tree[TREE_SMEM ? 1 : TREE_N];
-    const int* T = stage_tree<TREE_SMEM>(tree, s_tree, nthr);
+    const int* T = tree;
+    int par = -1, dep = 0;
+    if (!TREE_SMEM && j < NJ) { par = __ldg(tree + TREE_PAR + j); dep = __ldg(tree + TREE_DEPTH + j); }
+    float rj[9];
     BODY_STAMP(0);
     if (j < NBETA) {
         float v = 0.f;
@@ -171,7 +173,7 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
             rodrigues_fwd(aa, r);
         }
         for (int k = 0; k < 3; ++k) full_pose[b * 165 + j * 3 + k] = aa[k];
-        for (int k = 0; k < 9; ++k) { R[((size_t)b * NJ + j) * 9 + k] = r[k]; sR[j][k] = r[k]; }
+        for (int k = 0; k < 9; ++k) { R[((size_t)b * NJ + j) * 9 + k] = r[k]; sR[j][k] = r[k]; rj[k] = r[k]; }
         if (j >= 1)
             for (int k = 0; k < 9; ++k) sX[(j - 1) * 9 + k] = r[k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
     }
@@ -205,7 +207,28 @@ __device__ __forceinline__ void pose_chain_fwd_body(const PoseK& p, const float*
     // and lane, the next level's word requested a level ahead); only __syncwarp between levels.  (Fetching the next level's rotation and
     // offset ahead of the barrier as well was measured: slower -- the loads must complete before the barrier, so a level then pays two
     // shared-memory latencies instead of one.)
-    if (threadIdx.x < 32) {
+    if (!TREE_SMEM) {
+        // stand-alone kernel (64 threads, tables in global memory): thread j = joint j, parent / depth in registers, a two-warp CTA
+        // barrier per level -- cheaper here than staging the level tables for a single-warp walk (ncu at B = 120: 10.9 vs 13.0 us)
+        for (int lev = 0; lev <= max_depth; ++lev) {
+            if (j < NJ && dep == lev) {
+                float g[12];
+                if (lev == 0) {
+                    for (int q = 0; q < 3; ++q) { g[q * 4] = rj[q * 3]; g[q * 4 + 1] = rj[q * 3 + 1]; g[q * 4 + 2] = rj[q * 3 + 2]; g[q * 4 + 3] = sJ[j][q]; }
+                } else {
+                    const float* gp = sG[par];
+                    const float t[3] = {sJ[j][0] - sJ[par][0], sJ[j][1] - sJ[par][1], sJ[j][2] - sJ[par][2]};
+                    for (int q = 0; q < 3; ++q) {
+                        for (int c = 0; c < 3; ++c)
+                            g[q * 4 + c] = gp[q * 4] * rj[c] + gp[q * 4 + 1] * rj[3 + c] + gp[q * 4 + 2] * rj[6 + c];
+                        g[q * 4 + 3] = gp[q * 4] * t[0] + gp[q * 4 + 1] * t[1] + gp[q * 4 + 2] * t[2] + gp[q * 4 + 3];
+                    }
+                }
+                for (int k = 0; k < 12; ++k) sG[j][k] = g[k];
+            }
+            body_sync<SUB64>();
+        }
+    } else if (threadIdx.x < 32) {
         int e = T[TREE_LANE + threadIdx.x];
         for (int lev = 0; lev <= max_depth; ++lev) {
             const int e_next = lev < max_depth ? T[TREE_LANE + (lev + 1) * 32 + threadIdx.x] : -1;
