@@ -520,23 +520,26 @@ __global__ void __launch_bounds__(256) k_skin_bwd(const float* __restrict__ A, c
     s = block_sum(gs1, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 1] = s; else atomicAdd(&dtr[b * 3 + 1], s); }
     s = block_sum(gs2, sred); if (threadIdx.x == 0) { if (pz) pz[NJ * 12 + 2] = s; else atomicAdd(&dtr[b * 3 + 2], s); }
 }
-// ---- loss-row sub-models (V <= SKS_V rows: the 81 marker / foot rows of the AMASS fits, one CTA per frame in the general kernels = 960
+// ---- loss-row sub-models (V <= SKS_V rows: the 253 marker + foot rows of the AMASS fits, one CTA per frame in the general kernels = 960
 // CTAs whose whole life is latency: 55 dependent-ish global weight loads per thread, staging loops, 46 us for 90 MFLOP).  Here a CTA keeps
-// the sub-model's weights [55][V] in shared memory (pitch 97: conflict-free by row and by column) and walks frames b = blockIdx.x,
+// the sub-model's weights [55][V] in (dynamic) shared memory (pitch 257: conflict-free by row and by column) and walks frames b = blockIdx.x,
 // blockIdx.x + gridDim.x, ...  Same summation orders as k_skin_fwd / k_skin_bwd: bit-identical results.
-constexpr int SKS_V = 96, SKS_P = 97;
-__global__ void __launch_bounds__(128) k_skin_fwd_small(const float* __restrict__ A, const float* __restrict__ w_jm,
+constexpr int SKS_V = 256, SKS_P = 257;
+constexpr size_t SKS_FWD_SMEM = (size_t)(NJ * SKS_P + NJ * 12 + 4) * sizeof(float);
+constexpr size_t SKS_BWD_SMEM = (size_t)(NJ * SKS_P + 3 + NJ * 12 + SKS_V * 12 + 4 * NJ * 12 + 32) * sizeof(float);
+__global__ void __launch_bounds__(256) k_skin_fwd_small(const float* __restrict__ A, const float* __restrict__ w_jm,
                                                         const float* __restrict__ v_template, const float* __restrict__ transl,
                                                         int V, int B, float* __restrict__ VP, float* __restrict__ verts) {
-    __shared__ float s_w[NJ * SKS_P];
-    __shared__ __align__(16) float sA[NJ * 12];
-    for (int i = threadIdx.x; i < NJ * V; i += 128) { const int j = i / V, v = i - j * V; s_w[j * SKS_P + v] = w_jm[i]; }
+    extern __shared__ __align__(16) float sks_smem[];
+    float* sA = sks_smem;                                  // [660], 16-byte aligned
+    float* s_w = sks_smem + NJ * 12 + 4;                   // [55][SKS_P]
+    for (int i = threadIdx.x; i < NJ * V; i += 256) { const int j = i / V, v = i - j * V; s_w[j * SKS_P + v] = w_jm[i]; }
     const int v = threadIdx.x;
     float vt0 = 0.f, vt1 = 0.f, vt2 = 0.f;
     if (v < V) { vt0 = v_template[v * 3]; vt1 = v_template[v * 3 + 1]; vt2 = v_template[v * 3 + 2]; }
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
-        for (int i = threadIdx.x; i < NJ * 12; i += 128) sA[i] = A[(size_t)b * NJ * 12 + i];
+        for (int i = threadIdx.x; i < NJ * 12; i += 256) sA[i] = A[(size_t)b * NJ * 12 + i];
         __syncthreads();
         if (v >= V) continue;
         float T[12];
@@ -564,11 +567,12 @@ __global__ void __launch_bounds__(128) k_skin_fwd_small(const float* __restrict_
 __global__ void __launch_bounds__(256) k_skin_bwd_small(const float* __restrict__ A, const float* __restrict__ w_jm,
                                                         const float* __restrict__ VP, const float* __restrict__ Gv, int V, int B,
                                                         float* __restrict__ DVP, float* __restrict__ dA, float* __restrict__ dtr) {
-    __shared__ float s_w[NJ * SKS_P];
-    __shared__ float sA[NJ * 12];
-    __shared__ __align__(16) float s_dt[SKS_V * 12];
-    __shared__ float s_acc[4][NJ * 12];
-    __shared__ float sred[32];
+    extern __shared__ __align__(16) float sks_smem[];
+    float* s_dt = sks_smem;                                // [SKS_V][12], 16-byte aligned
+    float* sA = s_dt + SKS_V * 12;                         // [660]
+    float (*s_acc)[NJ * 12] = reinterpret_cast<float (*)[NJ * 12]>(sA + NJ * 12);
+    float* sred = sA + NJ * 12 + 4 * NJ * 12;              // [32]
+    float* s_w = sred + 32;                                // [55][SKS_P]
     for (int i = threadIdx.x; i < NJ * V; i += 256) { const int j = i / V, v = i - j * V; s_w[j * SKS_P + v] = w_jm[i]; }
     const int v = threadIdx.x;
     const int jB = threadIdx.x % NJ, sB = threadIdx.x / NJ;       // phase-B role (threads < 220)
@@ -942,7 +946,11 @@ static int body_apply_forward(BodyCtx* c, const BodyCtx* ps, const PoseIn& in, i
     const int V = m->V;
     if (both_tc(m, ps)) LEMO_TRY(skin_tc_launch(m->map_w2, ps->map_a2, c->VP, in.transl, V, B, verts, st));
     else if (V <= SKS_V && g_skin_small)
-        k_skin_fwd_small<<<std::min(B, 148 * 4), 128, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, B, c->VP, verts);
+    {
+        static bool cfg = false;
+        if (!cfg) { LEMO_CUDA(cudaFuncSetAttribute(k_skin_fwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKS_FWD_SMEM)); cfg = true; }
+        k_skin_fwd_small<<<std::min(B, 148 * 3), 256, SKS_FWD_SMEM, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, B, c->VP, verts);
+    }
     else k_skin_fwd<<<dim3(cdiv(V, 256), B), 256, 0, st>>>(ps->A, m->w_jm, m->v_template, in.transl, V, c->VP, verts);
     if (joints) {
         LEMO_CHECK(!m->is_sub, "output joints need the full model");
@@ -997,7 +1005,9 @@ int body_skin_backward(BodyCtx* c, BodyCtx* ps, int B, const float* d_verts, con
             k_skin_bwd_act_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(partc, m->sk_joff, m->sk_jslot, m->sk_nslot, part_tr, m->sk_ntile, B,
                                                                            ps->dA, ps->dtr);
         } else if (V <= SKS_V && g_skin_small) {
-            k_skin_bwd_small<<<std::min(B, 148 * 3), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, c->DVP, ps->dA, ps->dtr);
+            static bool cfg = false;
+            if (!cfg) { LEMO_CUDA(cudaFuncSetAttribute(k_skin_bwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKS_BWD_SMEM)); cfg = true; }
+            k_skin_bwd_small<<<std::min(B, 148 * 2), 256, SKS_BWD_SMEM, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, c->DVP, ps->dA, ps->dtr);
         } else {
             k_skin_bwd<<<dim3(ctas, B), 256, 0, st>>>(ps->A, m->w_jm, c->VP, c->Gv, V, B, tiles, c->DVP, ps->dA, ps->dtr, part);
             if (part) k_skin_bwd_reduce<<<cdiv(B * SKB_PART, 256), 256, 0, st>>>(part, ctas, B, ps->dA, ps->dtr);
