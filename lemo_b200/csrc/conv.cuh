@@ -1,12 +1,15 @@
 // 3x3 convolution stack of the motion priors (reference models/AE_sep.py, models/AE.py) on sm_100a.
 //
 // Activation layout ("padded pitch-linear planes"): a [N,C,H,W] tensor is stored as [N][C][Hp*Wp] with
-// Hp = H+2, Wp = roundup(W+2, 8); pixel (y,x) lives at (y+1)*Wp + (x+1) and every border element is 0.
+// Hp = H+2, Wp = roundup(W+1, 8); pixel (y,x) lives at (y+1)*Wp + (x+1) and every border element is 0.  ONE pad column is enough: in the
+// linear pixel order the right neighbour of a row's last pixel is the next row's column 0, which is that row's (zero) left pad.  (Round 1
+// used roundup(W+2, 8) = 144 for the 135-column velocity image; 136 computes 5.6 % fewer padded pixels per layer.)
 // With the zero border physically present a 3x3/pad-1 convolution is a pure 1-D correlation over the
 // linear index  out[q] = sum in[q + (ky-1)*Wp + (kx-1)] * w[ky][kx], so CTAs tile the LINEAR pixel range
 // in 256-pixel tiles: no 2-D tile-edge waste on the 245x134 (or any T) image, 16-byte aligned vector
 // smem reads for every (ky,kx) shift, coalesced 512-byte output rows.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include <vector>
 
@@ -17,7 +20,8 @@ struct PlaneGeom {
 };
 inline PlaneGeom make_geom(int H, int W) {
     PlaneGeom g;
-    g.H = H; g.W = W; g.Hp = H + 2; g.Wp = (W + 2 + 7) / 8 * 8; g.PS = g.Hp * g.Wp;
+    static const int pad = []() { const char* e = getenv("LEMO_PLANE_PAD"); return (e && e[0] == '2') ? 2 : 1; }();   // 2 = the round-1 layout (A/B measurements)
+    g.H = H; g.W = W; g.Hp = H + 2; g.Wp = (W + pad + 7) / 8 * 8; g.PS = g.Hp * g.Wp;
     return g;
 }
 
