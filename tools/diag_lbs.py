@@ -1,11 +1,25 @@
 """GPU diagnostic: full-mesh lemo_smplx_forward at B=120 -- eager and CUDA-graph-replayed time per back end, parity between them."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 import numpy as np, torch
-from lemo_b200 import _lib
-from oracle import synth
-from gpu_common import smplx_module, rand_pose, rel
+from lemo_b200 import _lib, synth
+import lemo_b200.smplx as smplx
+
+
+def smplx_module(n_verts):
+    return smplx.create(synth.make_smplx_model(0, n_verts=n_verts), model_type='smplx', gender='male', ext='npz', num_pca_comps=12,
+                        batch_size=1).to('cuda:0')
+
+
+def rand_pose(B, seed, scale=0.3):
+    g = np.random.default_rng(seed)
+    f = lambda *s: (scale * g.standard_normal(s)).astype(np.float32)
+    return dict(transl=f(B, 3), global_orient=f(B, 3), body_pose=f(B, 63), jaw_pose=f(B, 3), leye_pose=f(B, 3), reye_pose=f(B, 3),
+                left_hand_pose=f(B, 12), right_hand_pose=f(B, 12), betas=g.standard_normal((B, 10)).astype(np.float32), expression=f(B, 10))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 dev = 'cuda:0'
 Bs = [int(x) for x in sys.argv[1:]] or [120]
 for B in Bs:
