@@ -9,6 +9,7 @@
 #include "fit_common.cuh"
 #include "../../include/lemo_b200.h"
 #include <algorithm>
+#include <mutex>
 
 namespace lemo {
 
@@ -173,10 +174,14 @@ int conv3x3_wgrad_launch(const float* x, const float* dpre, float* dW, float* db
     const int NG = wgrad_groups(N, Cin, Cout, g);
     const int SWX = (WG_CP + 2 * g.Wp + 2 + 4 + 3) / 4 * 4;          // window + the 2 floats the last vector read runs over, 16-byte pitch
     const size_t smem = (size_t)(WG_T * WG_DP + WG_T * SWX) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        LEMO_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    {                                             // monotonic under a lock: several host threads launch (see conv_main_launch)
+        static std::mutex mu;
+        static size_t configured = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (smem > configured) {
+            LEMO_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
     }
     dim3 grid(cdiv(Cout, WG_T), cdiv(Cin, WG_T), N * NG);
     k_wgrad<<<grid, 256, smem, st>>>(x, dpre, scratch, Cin, Cout, g.H, g.Wp, g.PS, nchunks, NG, SWX);
@@ -409,9 +414,10 @@ __global__ void __launch_bounds__(256) k_ae_l1(const float* __restrict__ rec_pla
 }
 // k_ae_l1 for the graph-replayed driver: the loss of step t lands in losses[t-1] (k_sched has already advanced the step counter)
 __global__ void __launch_bounds__(256) k_ae_l1_sched(const float* __restrict__ rec_planes, const float* __restrict__ x_planes,
-                                                     const float* __restrict__ row_mask, int N, int C, PlaneGeom g, float inv_count,
+                                                     const float* __restrict__ row_mask, int N, int C, PlaneGeom g,
                                                      float* __restrict__ d_planes, float* __restrict__ losses, const Sched* __restrict__ sc) {
     __shared__ float sred[32];
+    const float inv_count = sc->aux;                       // 1 / (N * selected rows * W): a per-run value, read from the schedule
     float part = 0.f;
     const long long tot = (long long)N * g.H * g.W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
@@ -481,8 +487,7 @@ static int ae_finetune_graph_step(ConvNet* n, cudaStream_t st) {
     k_sched<<<1, 1, 0, st>>>((Sched*)n->ft_sched);
     LEMO_TRY(ae_forward_planes(n, N, st));
     LEMO_CUDA(cudaMemsetAsync(n->grad[0], 0, (size_t)N * g.PS * sizeof(float), st));
-    const float inv_count = 1.f / ((float)N * (float)n->ft_rows * (float)g.W);
-    k_ae_l1_sched<<<64, 256, 0, st>>>(n->act[18 + 3 * 4], n->act[0], (const float*)n->ft_mask, N, n->in_ch, g, inv_count, n->grad[0],
+    k_ae_l1_sched<<<64, 256, 0, st>>>(n->act[18 + 3 * 4], n->act[0], (const float*)n->ft_mask, N, n->in_ch, g, n->grad[0],
                                      n->ft_losses, (const Sched*)n->ft_sched);
     LEMO_TRY(ae_backward_planes(n, N, dW, st));
     k_adam_dev<<<cdiv(n->n_weights, 256), 256, 0, st>>>(n->w_flat, dW, m1, m2, (int)n->n_weights, (const Sched*)n->ft_sched);
@@ -503,11 +508,12 @@ int lemo_ae_finetune_run(LemoConvNet* h, const float* x, const float* row_mask, 
     LEMO_CUDA(cudaMemsetAsync(n->d_wflat + n->n_weights, 0, 2 * n->n_weights * sizeof(float), st));
     Sched s{};
     s.it = 0; s.lr0 = s.lr1 = s.lr2 = (float)lr; s.sw1 = s.sw2 = 1 << 30;
+    s.aux = 1.f / ((float)N * (float)n_rows_selected * (float)n->geom[0].W);     // scale of the masked L1 (read by k_ae_l1_sched)
     LEMO_CUDA(cudaMemcpyAsync(n->ft_sched, &s, sizeof(Sched), cudaMemcpyHostToDevice, st));
     if (losses_out) LEMO_CUDA(cudaMemsetAsync(losses_out, 0, (size_t)steps * sizeof(float), st));
     LEMO_TRY(pack_planes(x, n->act[0], N * n->in_ch, n->geom[0], st));          // the input is the same for every step (:164-184)
-    // the captured step bakes these pointers / sizes: re-capture when they change
-    const bool same = n->ft_gexec && n->ft_mask == row_mask && n->ft_losses == losses_out && n->ft_N == N && n->ft_rows == n_rows_selected;
+    // the captured step bakes these pointers / sizes: re-capture when they change (the number of selected rows is NOT baked: Sched::aux)
+    const bool same = n->ft_gexec && n->ft_mask == row_mask && n->ft_losses == losses_out && n->ft_N == N;
     if (!same) {
         if (n->ft_gexec) { cudaGraphExecDestroy((cudaGraphExec_t)n->ft_gexec); n->ft_gexec = nullptr; }
         if (n->ft_graph) { cudaGraphDestroy((cudaGraph_t)n->ft_graph); n->ft_graph = nullptr; }

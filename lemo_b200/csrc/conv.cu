@@ -5,6 +5,7 @@
 #include "conv.cuh"
 #include "../../include/lemo_b200.h"
 #include <algorithm>
+#include <mutex>
 
 namespace lemo {
 
@@ -236,10 +237,17 @@ static int conv_main_launch(const float* in, const float* wk, const float* bias,
                             int Cout, const PlaneGeom& g, ConvEpi epi, cudaStream_t st, float* scratch, size_t scratch_floats) {
     const int SW = (TP + 2 * g.Wp + 2 + 3) / 4 * 4;
     const size_t smem = 2 * (size_t)(CT * SW + CT * 9 * NW * 8) * sizeof(float);      // two pipeline stages
-    static size_t configured = 0;             // one process per GPU: a per-process cache is enough
-    if (smem > configured) {
-        LEMO_CUDA(cudaFuncSetAttribute(k_conv3x3<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // one process per GPU: a per-process cache is enough -- but several host threads may launch (InfillPool drives
+    // every stage from its own thread), and the limit must only ever GROW: an unlocked check-then-set let a thread with a smaller layer
+    // overwrite a larger limit another thread had just set, whose next launch then failed inside its stream capture
+    {
+        static std::mutex mu;
+        static size_t configured = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (smem > configured) {
+            LEMO_CUDA(cudaFuncSetAttribute(k_conv3x3<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
     }
     int KS = scratch ? conv3x3_splitk(N, Cin, Cout, g) : 1;
     if (KS > 1 && (size_t)KS * N * Cout * g.PS > scratch_floats) KS = 1;

@@ -12,6 +12,7 @@ struct Sched {            // device-resident schedule: constants set per run, sc
     float lr0, lr1, lr2;  // lr = it > sw2 ? lr2 : it > sw1 ? lr1 : lr0   (`if step > 60` semantics of the scripts)
     int sw1, sw2;
     int frame;            // per-frame mode: which frame of every sequence is being fitted
+    float aux;            // per-run scalar of the driver (AE fine-tune: 1 / number of selected elements), so that it is not baked into the graph
 };
 
 static __global__ void k_sched(Sched* s) {

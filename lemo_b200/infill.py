@@ -126,7 +126,11 @@ class InfillPool:
 
     def run_many(self, clip_imgs, rot0s):
         """clip_imgs: sequence of [4,208,T] tensors; rot0s: sequence of rot_0_pivot values.  -> list of (markers_rec, contact, markers_in),
-        in input order.  The caller's current stream waits for all of them."""
+        in input order.  The caller's current stream waits for all of them.
+
+        Measured (tools/ab_infill_pool.py): 49 ms per clip for 4, 8, 12, 16 or 24 clips in flight, and the same when every stage is driven
+        from its own host thread -- the pool is bound by the rate at which the device accepts graph nodes (~190 per fine-tune step,
+        ~4 us each across all streams), not by SM time and not by the issuing thread.  Fewer, fatter nodes per step is what moves it."""
         cur = torch.cuda.current_stream(self.device)
         outs = [None] * len(clip_imgs)
         for st in self.streams:
