@@ -345,6 +345,13 @@ int lemo_fit_prox_get(LemoProxFit* fit, const LemoProxParamsOutC* params, const 
 int64_t lemo_fit_prox_kernel_launches(const LemoProxFit* fit);
 
 /* ---------------------------------------------------------------- test hooks (host math, no GPU) -------- */
+/* Host-side builder of the kinematic-tree tables the chain kernels walk (csrc/body.cuh TREE_*; replaces the Python loop over `parents` of
+   lbs.py:246-251 `batch_rigid_transform`).  parents: 55 ints, parents[j] < j, parents[0] ignored (root).  tables: >= 776 ints:
+     [0,55) parent (-1 root) | [56,111) joints ordered by (depth, index) | [112,..) first position of each level in that order |
+     [128,184) children of joint j = list[koff[j] .. koff[j+1]) | [184,238) that list, ascending per parent |
+     [240,720) one word per (level, lane < 32): joint | (parent+1) << 8 | koff << 16 | n_children << 24, or -1 | [720,775) depth.
+   Returns 0, 1 (bad arguments), 11 (parents[j] >= j), 12 (deeper than 14 levels), 13 (more than 32 joints on a level). */
+int lemo_host_tree_tables(const int32_t* parents, int32_t* tables, int32_t n_tables, int32_t* max_depth);
 void lemo_host_rodrigues(const float* aa, float* R);
 void lemo_host_rodrigues_bwd(const float* aa, const float* dR, float* daa);
 void lemo_host_gs6d(const float* x6, float* R);

@@ -116,6 +116,7 @@ SIGNATURES = {
     'lemo_debug_set_blend_tc': (C.c_int, [_I]),
     'lemo_debug_set_skin_tc': (C.c_int, [_I]),
     'lemo_debug_set_skin_sparse': (C.c_int, [_I]),
+    'lemo_host_tree_tables': (C.c_int, [_P, _P, _I, _P]),
     'lemo_gather_rows': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_scatter_rows_add': (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'lemo_rot6d_to_rotmat': (C.c_int, [_P, _I, _P, _P]),

@@ -88,6 +88,13 @@ int lemo_smplx_backward(LemoBody* body, const LemoPoseC* pose, int32_t B, const 
 int lemo_debug_set_blend_tc(int32_t on) { blend_tc_set(on); return 0; }
 int lemo_debug_set_skin_tc(int32_t on) { skin_tc_set(on); return 0; }
 int lemo_debug_set_skin_sparse(int32_t on) { skin_sparse_set(on); return 0; }
+int lemo_host_tree_tables(const int32_t* parents, int32_t* tables, int32_t n_tables, int32_t* max_depth) {
+    if (!parents || !tables || !max_depth || n_tables < TREE_N) return 1;
+    int md = 0;
+    const int rc = build_tree_tables(parents, tables, &md);
+    *max_depth = md;
+    return rc ? 10 + rc : 0;
+}
 
 int lemo_gather_rows(const float* src, const int32_t* idx, int32_t B, int32_t V, int32_t n, float* out, void* stream) {
     LEMO_CHECK(src && idx && out, "null argument");

@@ -50,6 +50,43 @@ static int dev_alloc(T** dst, size_t n) {
     return 0;
 }
 
+// Level-ordered tables of the kinematic tree (layout: TREE_* in body.cuh), pure host code -- exported as lemo_host_tree_tables for the CPU tests.
+// parents[0] is taken as the root (-1).  Returns 0, or 1 (parents[j] >= j or < 0), 2 (deeper than TREE_MAX_DEPTH), 3 (a level wider than 32).
+static int compute_depth(const int* parents, int* depth, int* max_depth);
+int build_tree_tables(const int* parents_in, int* t, int* max_depth_out) {
+    int parents[NJ], depth[NJ], max_depth = 0;
+    for (int j = 0; j < NJ; ++j) parents[j] = parents_in[j];
+    parents[0] = -1;
+    if (compute_depth(parents, depth, &max_depth)) return 1;
+    if (max_depth > TREE_MAX_DEPTH) return 2;
+    for (int i = 0; i < TREE_N; ++i) t[i] = 0;
+    int pos = 0, k = 0;
+    for (int lev = 0; lev <= max_depth + 1; ++lev) {
+        t[TREE_OFF + lev] = pos;
+        for (int j = 0; j < NJ; ++j)
+            if (depth[j] == lev) t[TREE_ORDER + pos++] = j;
+    }
+    for (int j = 0; j < NJ; ++j) {
+        t[TREE_PAR + j] = parents[j];
+        t[TREE_DEPTH + j] = depth[j];
+        t[TREE_KOFF + j] = k;
+        for (int c = j + 1; c < NJ; ++c)
+            if (parents[c] == j) t[TREE_KLIST + k++] = c;
+    }
+    t[TREE_KOFF + NJ] = k;
+    for (int i = 0; i < (TREE_MAX_DEPTH + 1) * 32; ++i) t[TREE_LANE + i] = -1;
+    for (int lev = 0; lev <= max_depth; ++lev) {
+        const int o0 = t[TREE_OFF + lev], o1 = t[TREE_OFF + lev + 1];
+        if (o1 - o0 > 32) return 3;
+        for (int i = o0; i < o1; ++i) {
+            const int j = t[TREE_ORDER + i];
+            t[TREE_LANE + lev * 32 + (i - o0)] = j | ((parents[j] + 1) << 8) | (t[TREE_KOFF + j] << 16) | ((t[TREE_KOFF + j + 1] - t[TREE_KOFF + j]) << 24);
+        }
+    }
+    *max_depth_out = max_depth;
+    return 0;
+}
+
 static int compute_depth(const int* parents, int* depth, int* max_depth) {
     *max_depth = 0;
     for (int j = 0; j < NJ; ++j) {
@@ -192,32 +229,11 @@ int model_create_from_host(const LemoModelDescC* d, int device, Model** out) {
     LEMO_TRY(dev_upload(&m->parents, m->h_parents, NJ));
     LEMO_TRY(dev_upload(&m->depth, m->h_depth, NJ));
     {
-        LEMO_CHECK(m->max_depth <= TREE_MAX_DEPTH, "kinematic tree deeper than the level table");
-        int t[TREE_N];
-        memset(t, 0, sizeof(t));
-        int pos = 0, k = 0;
-        for (int lev = 0; lev <= m->max_depth + 1; ++lev) {
-            t[TREE_OFF + lev] = pos;
-            for (int j = 0; j < NJ; ++j)
-                if (m->h_depth[j] == lev) t[TREE_ORDER + pos++] = j;
-        }
-        for (int j = 0; j < NJ; ++j) {
-            t[TREE_PAR + j] = m->h_parents[j];
-            t[TREE_DEPTH + j] = m->h_depth[j];
-            t[TREE_KOFF + j] = k;
-            for (int c = j + 1; c < NJ; ++c)
-                if (m->h_parents[c] == j) t[TREE_KLIST + k++] = c;
-        }
-        t[TREE_KOFF + NJ] = k;
-        for (int i = 0; i < (TREE_MAX_DEPTH + 1) * 32; ++i) t[TREE_LANE + i] = -1;
-        for (int lev = 0; lev <= m->max_depth; ++lev) {
-            const int o0 = t[TREE_OFF + lev], o1 = t[TREE_OFF + lev + 1];
-            LEMO_CHECK(o1 - o0 <= 32, "more than 32 joints on one level of the kinematic tree");
-            for (int i = o0; i < o1; ++i) {
-                const int j = t[TREE_ORDER + i];
-                t[TREE_LANE + lev * 32 + (i - o0)] = j | ((m->h_parents[j] + 1) << 8) | (t[TREE_KOFF + j] << 16) | ((t[TREE_KOFF + j + 1] - t[TREE_KOFF + j]) << 24);
-            }
-        }
+        int t[TREE_N], md = 0;
+        const int rc = build_tree_tables(m->h_parents, t, &md);
+        LEMO_CHECK(rc != 2, "kinematic tree deeper than the level table");
+        LEMO_CHECK(rc != 3, "more than 32 joints on one level of the kinematic tree");
+        LEMO_CHECK(rc == 0 && md == m->max_depth, "parents must satisfy parents[j] < j");
         LEMO_TRY(dev_upload(&m->tree, t, TREE_N));
     }
     LEMO_TRY(dev_upload(&m->hand_l, d->h_hand_comp_l, (size_t)m->npc * 45));

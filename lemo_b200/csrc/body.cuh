@@ -178,6 +178,7 @@ int skin_tc_launch(const void* map_w2, const void* map_a2, const float* VP, cons
 bool skin_tc_enabled();
 void skin_tc_set(int on);
 void skin_sparse_set(int on);
+int build_tree_tables(const int* parents, int* tables /*TREE_N*/, int* max_depth_out);
 
 int gather_rows(const float* src, const int* idx_dev, int B, int V, int n, float* out, cudaStream_t st);
 int scatter_rows_add(const float* g_rows, const int* idx_dev, int B, int V, int n, float* g_dense, cudaStream_t st);

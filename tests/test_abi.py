@@ -159,3 +159,87 @@ def test_sparse_synthetic_model_has_smplx_like_skinning_weights():
     slots = sum(int(nz[t * 256:(t + 1) * 256].any(0).sum()) for t in range(ntile))
     assert slots * 5 < ntile * 55 * 2
     assert (synth.make_smplx_model(0)['lbs_weights'] != 0).all()
+
+
+def _tree_tables_py(parents):
+    """Independent construction of the tables of lemo_host_tree_tables (layout documented in include/lemo_b200.h)."""
+    import numpy as np
+    J = 55
+    par = np.array(parents, np.int64).copy()
+    par[0] = -1
+    depth = np.zeros(J, np.int64)
+    for j in range(1, J):
+        depth[j] = depth[par[j]] + 1
+    t = np.zeros(776, np.int64)
+    t[0:J] = par
+    order = sorted(range(J), key=lambda j: (depth[j], j))
+    t[56:56 + J] = order
+    md = int(depth.max())
+    for lev in range(md + 2):
+        t[112 + lev] = sum(1 for j in range(J) if depth[j] < lev)
+    kids = [[c for c in range(J) if par[c] == j] for j in range(J)]
+    k = 0
+    for j in range(J):
+        t[128 + j] = k
+        for c in kids[j]:
+            t[184 + k] = c
+            k += 1
+    t[128 + J] = k
+    t[240:720] = -1
+    if md > 14 or np.bincount(depth).max() > 32:
+        return None, md
+    for lev in range(md + 1):
+        lv = [j for j in order if depth[j] == lev]
+        for i, j in enumerate(lv):
+            t[240 + lev * 32 + i] = j | ((par[j] + 1) << 8) | (t[128 + j] << 16) | (len(kids[j]) << 24)
+    t[720:720 + J] = depth
+    return t, md
+
+
+def test_host_tree_tables_match_independent_construction():
+    """The level-ordered kinematic-tree tables the chain kernels walk (host code, exported for this test): the real SMPL-X tree and random
+    trees against an independent Python construction; structural properties; the error codes."""
+    import ctypes as C
+    import numpy as np
+    from lemo_b200 import _lib, synth
+    L = _lib.lib()
+    g = np.random.default_rng(0)
+    cases = [synth.PARENTS.astype(np.int32)]
+    for _ in range(20):
+        p = np.zeros(55, np.int32)
+        for j in range(1, 55):
+            p[j] = g.integers(0, max(1, (2 * j) // 3))          # bushy enough to stay within 14 levels, narrow enough for 32 per level (mostly)
+        cases.append(p)
+    checked = 0
+    for p in cases:
+        out = np.zeros(776, np.int32)
+        md = C.c_int32(0)
+        rc = L.lemo_host_tree_tables(p.ctypes.data, out.ctypes.data, 776, C.byref(md))
+        ref, md_ref = _tree_tables_py(p)
+        if ref is None:
+            assert rc in (12, 13)
+            continue
+        assert rc == 0 and md.value == md_ref
+        assert np.array_equal(out.astype(np.int64), ref), np.nonzero(out != ref)[0][:10]
+        # every joint appears exactly once among the packed words, on its own level, after its parent's level
+        words = out[240:720].reshape(15, 32)
+        seen = {}
+        for lev in range(md_ref + 1):
+            for w in words[lev]:
+                if w >= 0:
+                    seen[int(w) & 255] = lev
+        assert sorted(seen) == list(range(55))
+        assert all(seen[j] == seen[int(p[j])] + 1 for j in range(1, 55))
+        checked += 1
+    assert checked >= 10
+    # the real tree: 11 levels, at most 10 joints on one (the finger levels)
+    out = np.zeros(776, np.int32); md = C.c_int32(0)
+    assert L.lemo_host_tree_tables(cases[0].ctypes.data, out.ctypes.data, 776, C.byref(md)) == 0 and md.value == 10
+    assert np.bincount(out[720:775]).max() == 10
+    bad = cases[0].copy(); bad[5] = 7
+    assert L.lemo_host_tree_tables(bad.ctypes.data, out.ctypes.data, 776, C.byref(md)) == 11
+    chain = np.arange(-1, 54, dtype=np.int32)                    # a 55-deep chain: deeper than the level table
+    assert L.lemo_host_tree_tables(chain.ctypes.data, out.ctypes.data, 776, C.byref(md)) == 12
+    star = np.zeros(55, np.int32)                                # 54 children of the root: a level wider than a warp
+    assert L.lemo_host_tree_tables(star.ctypes.data, out.ctypes.data, 776, C.byref(md)) == 13
+    assert L.lemo_host_tree_tables(cases[0].ctypes.data, out.ctypes.data, 100, C.byref(md)) == 1
